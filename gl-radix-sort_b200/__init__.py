@@ -1,0 +1,285 @@
+"""gl-radix-sort_b200 — B200-native (sm_100a) replacement for loryruta/gl-radix-sort's hot path.
+
+Python mirror of the reference's three classes over the C ABI in ``include/glu_b200.h``:
+
+    glu::Reduce(DataType, ReduceOperator)(buffer, count)                     glu/Reduce.hpp:62,111
+    glu::BlellochScan(DataType)(buffer, count, num_partitions=1)             glu/BlellochScan.hpp:91,130
+    glu::RadixSort()(key_buffer, val_buffer, count, num_steps=0)             glu/RadixSort.hpp:205,273
+    glu::RadixSort::prepare_internal_buffers(count)                          glu/RadixSort.hpp:237
+
+A ``buffer`` is a CUDA ``torch.Tensor`` (its ``data_ptr()`` plays the role of the GL buffer handle) or a
+raw device pointer (``int``).  PyTorch is plumbing only: device memory for the scratch the reference
+classes own, and the current stream.  All compute happens in ``libglu_b200.so`` (hand-written CUDA);
+there is NO fallback — importing this package without the built library raises ImportError, and every
+call needs a CUDA device.
+
+The directory name contains a hyphen, so load it with ``__graft_entry__.load_package()`` (or
+``importlib``) — it registers itself as ``gl_radix_sort_b200``.
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libglu_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C gl-radix-sort_b200`). There is no CPU / PyTorch fallback for the glu hot path.")
+
+_lib = ctypes.CDLL(LIB_PATH)
+
+_sz = ctypes.c_size_t
+_vp = ctypes.c_void_p
+_int = ctypes.c_int
+
+# name -> (restype, argtypes); must list every symbol include/glu_b200.h declares (tests/test_abi.py checks)
+ABI = {
+    "glu_version": (_int, []),
+    "glu_status_string": (ctypes.c_char_p, [_int]),
+    "glu_last_cuda_error": (ctypes.c_char_p, []),
+    "glu_data_type_size": (_sz, [_int]),
+    "glu_kernel_launch_count": (ctypes.c_uint64, []),
+    "glu_reduce_tmp_bytes": (_sz, [_sz, _int]),
+    "glu_reduce": (_int, [_vp, _sz, _int, _int, _vp, _sz, _vp]),
+    "glu_scan_exclusive_tmp_bytes": (_sz, [_sz, _sz, _int]),
+    "glu_scan_exclusive": (_int, [_vp, _sz, _sz, _int, _vp, _sz, _vp]),
+    "glu_radix_sort_u32kv_tmp_bytes": (_sz, [_sz]),
+    "glu_radix_sort_u32kv": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _vp]),
+    "glu_reduce_host": (_int, [_vp, _sz, _int, _int]),
+    "glu_scan_exclusive_host": (_int, [_vp, _sz, _sz, _int]),
+    "glu_radix_sort_u32kv_host": (_int, [_vp, _vp, _sz, _sz]),
+    "glu_device_count": (_int, [ctypes.POINTER(_int)]),
+    "glu_set_device": (_int, [_int]),
+    "glu_device_info": (_int, [_int, ctypes.c_char_p, _sz, ctypes.POINTER(_int), ctypes.POINTER(_int),
+                               ctypes.POINTER(_int), ctypes.POINTER(_sz), ctypes.POINTER(_int)]),
+    "glu_malloc": (_int, [ctypes.POINTER(_vp), _sz]),
+    "glu_free": (_int, [_vp]),
+    "glu_malloc_host": (_int, [ctypes.POINTER(_vp), _sz]),
+    "glu_free_host": (_int, [_vp]),
+    "glu_memcpy_h2d": (_int, [_vp, _vp, _sz, _vp]),
+    "glu_memcpy_d2h": (_int, [_vp, _vp, _sz, _vp]),
+    "glu_memcpy_d2d": (_int, [_vp, _vp, _sz, _vp]),
+    "glu_memset_u32": (_int, [_vp, ctypes.c_uint32, _sz, _vp]),
+    "glu_stream_create": (_int, [ctypes.POINTER(_vp)]),
+    "glu_stream_destroy": (_int, [_vp]),
+    "glu_stream_synchronize": (_int, [_vp]),
+    "glu_event_create": (_int, [ctypes.POINTER(_vp)]),
+    "glu_event_destroy": (_int, [_vp]),
+    "glu_event_record": (_int, [_vp, _vp]),
+    "glu_event_synchronize": (_int, [_vp]),
+    "glu_event_elapsed_ms": (_int, [ctypes.POINTER(ctypes.c_float), _vp, _vp]),
+}
+for _name, (_res, _args) in ABI.items():
+    _fn = getattr(_lib, _name)  # AttributeError here == the library does not export what the header declares
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+lib = _lib
+
+
+class DataType(enum.IntEnum):
+    """glu/data_types.hpp:8-22"""
+    Float = 0
+    Double = 1
+    Int = 2
+    Uint = 3
+    Vec2 = 4
+    Vec4 = 5
+    DVec2 = 6
+    DVec4 = 7
+    UVec2 = 8
+    UVec4 = 9
+    IVec2 = 10
+    IVec4 = 11
+
+
+class ReduceOperator(enum.IntEnum):
+    """glu/Reduce.hpp:42-48"""
+    Sum = 0
+    Mul = 1
+    Min = 2
+    Max = 3
+
+
+# reference-style aliases
+DataType_Float, DataType_Double, DataType_Int, DataType_Uint = DataType.Float, DataType.Double, DataType.Int, DataType.Uint
+DataType_Vec2, DataType_Vec4, DataType_DVec2, DataType_DVec4 = DataType.Vec2, DataType.Vec4, DataType.DVec2, DataType.DVec4
+DataType_UVec2, DataType_UVec4, DataType_IVec2, DataType_IVec4 = DataType.UVec2, DataType.UVec4, DataType.IVec2, DataType.IVec4
+ReduceOperator_Sum, ReduceOperator_Mul, ReduceOperator_Min, ReduceOperator_Max = (
+    ReduceOperator.Sum, ReduceOperator.Mul, ReduceOperator.Min, ReduceOperator.Max)
+
+
+class GluError(RuntimeError):
+    """Raised where the reference's GLU_CHECK_ARGUMENT / GLU_FAIL would print and exit(1) (glu/errors.hpp:8-18)."""
+
+    def __init__(self, status: int, where: str):
+        self.status = status
+        msg = _lib.glu_status_string(status).decode()
+        if status == 7:
+            msg += ": " + _lib.glu_last_cuda_error().decode()
+        super().__init__(f"{where}: {msg}")
+
+
+def check(status: int, where: str) -> None:
+    if status != 0:
+        raise GluError(status, where)
+
+
+def kernel_launch_count() -> int:
+    return int(_lib.glu_kernel_launch_count())
+
+
+def data_type_size(data_type: int) -> int:
+    return int(_lib.glu_data_type_size(int(data_type)))
+
+
+def _ptr_and_device(buffer):
+    """Device pointer (+ torch device or None) of a buffer argument."""
+    if isinstance(buffer, int):
+        return buffer, None
+    if hasattr(buffer, "data_ptr"):
+        if not buffer.is_cuda:
+            raise GluError(1, "buffer must live on a CUDA device (no CPU path exists)")
+        if not buffer.is_contiguous():
+            raise GluError(1, "buffer must be contiguous")
+        return buffer.data_ptr(), buffer.device
+    raise TypeError(f"unsupported buffer type {type(buffer)!r}")
+
+
+def _current_stream(device) -> int:
+    import torch
+
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+class _Scratch:
+    """Grow-only device scratch owned by an operator object (glu/RadixSort.hpp:193-200, :237-271)."""
+
+    def __init__(self):
+        self._buf = None
+
+    def ensure(self, nbytes: int, device):
+        import torch
+
+        if self._buf is None or self._buf.numel() < nbytes or self._buf.device != device:
+            self._buf = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            if os.environ.get("GLU_VERBOSE"):
+                print(f"[glu] scratch reallocated to: {nbytes}")
+        return self._buf.data_ptr(), self._buf.numel()
+
+
+def _device_of(dev):
+    import torch
+
+    return dev if dev is not None else torch.device("cuda", torch.cuda.current_device())
+
+
+class Reduce:
+    """glu::Reduce — in-place reduction, result in element 0 (glu/Reduce.hpp:51-135)."""
+
+    def __init__(self, data_type, operator_):
+        if int(data_type) not in set(int(d) for d in DataType):
+            raise GluError(2, f"Invalid data type: {int(data_type)}")
+        if int(operator_) not in (0, 1, 2, 3):
+            raise GluError(3, f"Invalid reduction operator: {int(operator_)}")  # glu/Reduce.hpp:93
+        self.data_type = DataType(int(data_type))
+        self.operator = ReduceOperator(int(operator_))
+        self._scratch = _Scratch()
+
+    def __call__(self, buffer, count: int, stream: int | None = None) -> None:
+        ptr, dev = _ptr_and_device(buffer)
+        if not ptr:
+            raise GluError(1, "Invalid buffer")
+        if count <= 0:
+            raise GluError(1, "Count must be greater than zero")
+        dev = _device_of(dev)
+        need = int(_lib.glu_reduce_tmp_bytes(count, int(self.data_type)))
+        tmp, tmp_bytes = self._scratch.ensure(need, dev)
+        st = _current_stream(dev) if stream is None else stream
+        check(_lib.glu_reduce(ptr, count, int(self.data_type), int(self.operator), tmp, tmp_bytes, st), "Reduce")
+
+
+class BlellochScan:
+    """glu::BlellochScan — in-place exclusive prefix sum over num_partitions adjacent segments
+    (glu/BlellochScan.hpp:79-139).  Any count is accepted (the reference requires a power of two)."""
+
+    def __init__(self, data_type):
+        if int(data_type) not in set(int(d) for d in DataType):
+            raise GluError(2, f"Invalid data type: {int(data_type)}")
+        self.data_type = DataType(int(data_type))
+        self._scratch = _Scratch()
+
+    def __call__(self, buffer, count: int, num_partitions: int = 1, stream: int | None = None) -> None:
+        ptr, dev = _ptr_and_device(buffer)
+        if not ptr:
+            raise GluError(1, "Invalid buffer")
+        if count <= 0:
+            raise GluError(1, "Count must be greater than zero")
+        if num_partitions < 1:
+            raise GluError(1, "Num of partitions must be >= 1")
+        dev = _device_of(dev)
+        need = int(_lib.glu_scan_exclusive_tmp_bytes(count, num_partitions, int(self.data_type)))
+        tmp, tmp_bytes = self._scratch.ensure(need, dev)
+        st = _current_stream(dev) if stream is None else stream
+        check(_lib.glu_scan_exclusive(ptr, count, num_partitions, int(self.data_type), tmp, tmp_bytes, st),
+              "BlellochScan")
+
+
+class RadixSort:
+    """glu::RadixSort — stable in-place sort of uint32 (key, value) pairs by key (glu/RadixSort.hpp:186-354)."""
+
+    def __init__(self):
+        self._scratch = _Scratch()
+        self._device = None
+
+    def prepare_internal_buffers(self, count: int, device=None) -> None:
+        """glu/RadixSort.hpp:237-271 — grow-only pre-sizing of the internal scratch."""
+        dev = _device_of(device if device is not None else self._device)
+        need = int(_lib.glu_radix_sort_u32kv_tmp_bytes(count))
+        if need == 0:
+            raise GluError(6, "RadixSort")
+        self._scratch.ensure(need, dev)
+        self._device = dev
+
+    def __call__(self, key_buffer, val_buffer, count: int, num_steps: int = 0, stream: int | None = None) -> None:
+        kptr, kdev = _ptr_and_device(key_buffer)
+        vptr, vdev = _ptr_and_device(val_buffer)
+        if not kptr:
+            raise GluError(1, "Invalid key buffer")
+        if not vptr:
+            raise GluError(1, "Invalid value buffer")
+        if count <= 1:
+            return  # glu/RadixSort.hpp:278-279
+        dev = _device_of(kdev if kdev is not None else vdev)
+        self.prepare_internal_buffers(count, dev)
+        tmp, tmp_bytes = self._scratch.ensure(0, dev)
+        st = _current_stream(dev) if stream is None else stream
+        check(_lib.glu_radix_sort_u32kv(kptr, vptr, count, num_steps, tmp, tmp_bytes, st), "RadixSort")
+
+
+# ---- host-buffer entry points (numpy arrays; upload + hot path + download inside the call) ------------------------
+
+def _np_ptr(a):
+    import numpy as np
+
+    if not isinstance(a, np.ndarray) or not a.flags["C_CONTIGUOUS"] or not a.flags["WRITEABLE"]:
+        raise GluError(1, "host buffers must be writable C-contiguous numpy arrays")
+    return a.ctypes.data
+
+
+def reduce_host(data, count: int, data_type, operator_) -> None:
+    check(_lib.glu_reduce_host(_np_ptr(data), count, int(data_type), int(operator_)), "reduce_host")
+
+
+def scan_exclusive_host(data, count: int, num_partitions: int, data_type) -> None:
+    check(_lib.glu_scan_exclusive_host(_np_ptr(data), count, num_partitions, int(data_type)), "scan_exclusive_host")
+
+
+def radix_sort_u32kv_host(keys, vals, count: int | None = None, num_steps: int = 0) -> None:
+    if count is None:
+        count = keys.size
+    check(_lib.glu_radix_sort_u32kv_host(_np_ptr(keys), _np_ptr(vals), count, num_steps), "radix_sort_u32kv_host")

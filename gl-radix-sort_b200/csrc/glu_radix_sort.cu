@@ -1,0 +1,621 @@
+// glu_radix_sort.cu — glu_radix_sort_u32kv(): the B200 replacement for glu::RadixSort::operator()
+// (glu/RadixSort.hpp:273-334; counting shader :11-58, reordering shader :60-183).
+//
+// The reference sorts with 8 passes over 4-bit digits; every pass is a counting dispatch (one global
+// atomic per key), a 16-partition Blelloch scan of the per-block counts (2*log2(blocks) dispatches) and
+// a reordering dispatch that runs 16 sequential 1024-wide shared-memory scans per block: 176..304
+// dispatches per sort and a sync-bound ~53 Mpairs/s plateau.  Here the same stable LSD sort is
+//   1 memset + 1 histogram kernel + ceil(bits/8) "onesweep" kernels   (68 B of HBM traffic per pair):
+//   * histogram_kernel reads the keys ONCE (128-bit streaming loads) and builds the 256-bin
+//     histograms of all digit places in shared memory; warps whose keys mostly share a digit
+//     aggregate with __match_any_sync so skewed inputs do not serialise on one shared-memory bank;
+//     the last CTA turns the histograms into exclusive digit offsets;
+//   * onesweep_kernel (one launch per 8-bit digit) processes one tile per CTA: keys are ranked with
+//     warp-wide digit matching against per-warp digit counters (stable: warp-striped order is input
+//     order), the per-tile digit counts are chained across tiles with a decoupled look-back
+//     (status + 30-bit count in one 32-bit word per (tile, digit)), keys and values are reordered
+//     through shared memory so that every digit run leaves the SM as one contiguous, coalesced
+//     store burst.  Tile ids come from an atomic ticket (forward progress by construction).
+// Results are bit-identical to std::stable_sort of the (key, value) pairs by key — and therefore to
+// the reference's 8 x 4-bit passes, which are stable as well (oracle/glu_oracle.cpp radix_sort_glsl).
+#include <cstdlib>
+
+#include "glu_common.cuh"
+
+namespace glu_b200
+{
+    namespace
+    {
+        constexpr int k_radix = 256;
+        constexpr int k_max_passes = 4;
+        constexpr uint32_t k_lb_local = 1u << 30;     // tile-local digit count published
+        constexpr uint32_t k_lb_inclusive = 2u << 30; // inclusive prefix over tiles 0..t published
+        constexpr uint32_t k_lb_value_mask = (1u << 30) - 1u;
+        constexpr size_t k_max_count = size_t(1) << 30;
+
+        struct PassPlan
+        {
+            int num_passes;
+            uint32_t key_mask; // bits that take part in the sort (glu/RadixSort.hpp:331 num_steps)
+            uint32_t shift[k_max_passes];
+            uint32_t mask[k_max_passes];
+        };
+
+        PassPlan make_pass_plan(size_t num_steps)
+        {
+            PassPlan p{};
+            int bits = (num_steps == 0 || num_steps >= 8) ? 32 : int(4 * num_steps);
+            p.key_mask = bits == 32 ? 0xffffffffu : ((1u << bits) - 1u);
+            p.num_passes = (bits + 7) / 8;
+            for (int i = 0; i < p.num_passes; i++)
+            {
+                int b = bits - 8 * i < 8 ? bits - 8 * i : 8;
+                p.shift[i] = 8u * i;
+                p.mask[i] = (1u << b) - 1u;
+            }
+            return p;
+        }
+
+        // ------------------------------------------------------------------------------------ histogram
+
+        constexpr int k_hist_threads = 512;
+        constexpr int k_hist_unroll = 4;
+        constexpr int k_hist_blocks_per_sm = 2;
+
+        // One key's contribution to the shared histogram of one digit place.  When at least a quarter of
+        // the warp shares lane 0's digit the warp aggregates equal digits (match.any) so that a
+        // constant or heavily skewed digit costs one atomic instead of a 32-way bank conflict.
+        __device__ __forceinline__ void hist_add(uint32_t* s_bins, uint32_t digit, bool ok)
+        {
+            const uint32_t d0 = __shfl_sync(k_full_mask, digit, 0);
+            const uint32_t same0 = __ballot_sync(k_full_mask, ok && digit == d0);
+            if (__popc(same0) >= 8)
+            {
+                const uint32_t peers = __match_any_sync(k_full_mask, ok ? digit : 0xffffffffu);
+                if (ok && (peers & lanemask_lt()) == 0)
+                    atomicAdd(&s_bins[digit], uint32_t(__popc(peers)));
+            }
+            else if (ok)
+                atomicAdd(&s_bins[digit], 1u);
+        }
+
+        // hist: [k_max_passes][256] zero-initialised; on exit hist holds EXCLUSIVE digit offsets.
+        __global__ void __launch_bounds__(k_hist_threads)
+            histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t head, uint32_t n_units,
+                             int num_passes, uint32_t key_mask, uint32_t* hist, uint32_t* ticket)
+        {
+            __shared__ uint32_t s_hist[k_max_passes][k_radix];
+            __shared__ uint32_t s_scan[k_hist_threads / 32];
+            __shared__ bool s_is_last;
+
+            for (int i = threadIdx.x; i < k_max_passes * k_radix; i += k_hist_threads)
+                (&s_hist[0][0])[i] = 0;
+            __syncthreads();
+
+            const unsigned lane = threadIdx.x & 31;
+            const uint4* body = reinterpret_cast<const uint4*>(keys + head);
+            const uint32_t stride = gridDim.x * k_hist_threads;
+            // warp-uniform loop bounds: the match/ballot collectives need every lane of the warp
+            for (uint32_t v0 = blockIdx.x * k_hist_threads + (threadIdx.x & ~31u); v0 < n_units;
+                 v0 += stride * k_hist_unroll)
+            {
+                uint4 k[k_hist_unroll];
+                bool ok[k_hist_unroll];
+#pragma unroll
+                for (int u = 0; u < k_hist_unroll; u++)
+                {
+                    const uint64_t v = uint64_t(v0) + uint64_t(u) * stride + lane;
+                    ok[u] = v < n_units;
+                    k[u] = ok[u] ? ld_stream_v4(body + v) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < k_hist_unroll; u++)
+                {
+                    if (__ballot_sync(k_full_mask, ok[u]) == 0)
+                        continue;
+                    const uint32_t kk[4] = {k[u].x & key_mask, k[u].y & key_mask, k[u].z & key_mask,
+                                            k[u].w & key_mask};
+                    for (int p = 0; p < num_passes; p++)
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+                            hist_add(s_hist[p], (kk[c] >> (8 * p)) & 0xffu, ok[u]);
+                }
+            }
+            // unaligned head and sub-vector tail (at most 3 keys each)
+            if (blockIdx.x == 0 && threadIdx.x < 32)
+            {
+                const uint32_t tail_begin = head + n_units * 4;
+                const uint32_t idx = lane < head ? lane : tail_begin + (lane - head);
+                const bool ok = idx < n && (lane < head || idx >= tail_begin) && lane < head + 3;
+                const uint32_t key = ok ? (keys[idx] & key_mask) : 0;
+                for (int p = 0; p < num_passes; p++)
+                    hist_add(s_hist[p], (key >> (8 * p)) & 0xffu, ok);
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < num_passes * k_radix; i += k_hist_threads)
+            {
+                const uint32_t c = (&s_hist[0][0])[i];
+                if (c)
+                    atomicAdd(&hist[i], c);
+            }
+
+            // last CTA: counts -> exclusive offsets, one digit place at a time
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0)
+                s_is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+            __syncthreads();
+            if (!s_is_last)
+                return;
+            __threadfence();
+            const unsigned warp = threadIdx.x >> 5;
+            for (int p = 0; p < num_passes; p++)
+            {
+                uint32_t c = 0, inc = 0;
+                if (threadIdx.x < k_radix)
+                {
+                    c = __ldcg(&hist[p * k_radix + threadIdx.x]);
+                    inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1)
+                    {
+                        uint32_t t = __shfl_up_sync(k_full_mask, inc, o);
+                        if (lane >= unsigned(o))
+                            inc += t;
+                    }
+                    if (lane == 31)
+                        s_scan[warp] = inc;
+                }
+                __syncthreads();
+                if (threadIdx.x < k_radix)
+                {
+                    uint32_t off = 0;
+                    for (unsigned w = 0; w < warp; w++)
+                        off += s_scan[w];
+                    hist[p * k_radix + threadIdx.x] = off + inc - c;
+                }
+                __syncthreads();
+            }
+        }
+
+        // ------------------------------------------------------------------------------------ onesweep
+
+        enum RankMode
+        {
+            Rank_Match = 0, // match.any.sync
+            Rank_Ballot = 1 // one ballot per digit bit
+        };
+
+        template<int MODE> __device__ __forceinline__ uint32_t match_digit(uint32_t d)
+        {
+            if (MODE == Rank_Match)
+                return __match_any_sync(k_full_mask, d);
+            uint32_t peers = k_full_mask;
+#pragma unroll
+            for (int b = 0; b < 8; b++)
+            {
+                const bool bit = (d >> b) & 1u;
+                const uint32_t vote = __ballot_sync(k_full_mask, bit);
+                peers &= bit ? vote : ~vote;
+            }
+            return peers;
+        }
+
+        template<int THREADS, int IPT> struct SweepSmem
+        {
+            static constexpr int WARPS = THREADS / 32;
+            static constexpr int TILE = THREADS * IPT;
+            alignas(128) uint32_t keys[TILE];   // TMA destination (input order), then tile-sorted keys
+            alignas(128) uint32_t vals[TILE];   // TMA destination (input order), then tile-sorted values
+            uint32_t warp_hist[WARPS][k_radix]; // per-warp digit counters, then per-warp digit offsets
+            uint32_t gbase[k_radix];            // global index of tile-sorted slot 0, per digit
+            uint32_t scan[8];
+            alignas(8) uint64_t bar_keys;       // mbarriers completed by the bulk copies
+            alignas(8) uint64_t bar_vals;
+            uint32_t tile;
+        };
+
+        // One tile per CTA.  digit(key) = (key >> shift) & mask; keys with equal digits keep their order.
+        //
+        //   1. ticket -> tile id; one thread issues two cp.async.bulk (TMA) copies: the tile's keys and
+        //      values land in shared memory asynchronously, completion on an mbarrier each (the last,
+        //      partial tile and 16-byte-misaligned inputs take a cooperative ld/st path instead);
+        //   2. every thread takes IPT keys warp-striped (slot = warp*IPT*32 + i*32 + lane, i.e. input
+        //      order inside the warp) and ranks each against the warp's earlier equal digits:
+        //      peers = match(digit); rank = counter[warp][digit] + popc(peers below me);
+        //   3. one thread per digit: tile count -> published for look-back -> exclusive scan over the
+        //      256 digits and the warps -> per-(warp, digit) slot offsets;
+        //   4. keys are scattered to their tile-sorted slot IN PLACE, values are pulled out of their
+        //      staging buffer into registers; meanwhile the digit threads walk back over the earlier
+        //      tiles' published counts until they meet an inclusive prefix;
+        //   5. values are scattered in place; then slot p of both arrays goes to
+        //      global[gbase[digit(key_p)] + p] — neighbouring threads, neighbouring addresses.
+        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE>
+        __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+            onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                            uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
+                            uint32_t shift, uint32_t mask, const uint32_t* __restrict__ digit_offset,
+                            uint32_t* lookback, uint32_t* ticket, int allow_tma)
+        {
+            static_assert(THREADS >= k_radix && THREADS % 32 == 0, "one thread per digit is required");
+            static_assert(IPT % 2 == 0, "ranks are packed two per register");
+            using Smem = SweepSmem<THREADS, IPT>;
+            constexpr int WARPS = Smem::WARPS;
+            constexpr int TILE = Smem::TILE;
+            constexpr int WARP_ELEMS = IPT * 32;
+            static_assert(TILE <= 65536, "16-bit tile-local ranks");
+            extern __shared__ __align__(128) unsigned char smem_raw[];
+            Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+
+            const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+            if (tid == 0)
+            {
+                s.tile = atomicAdd(ticket, 1u);
+                mbarrier_init(&s.bar_keys, 1);
+                mbarrier_init(&s.bar_vals, 1);
+                mbarrier_init_fence();
+            }
+            for (int i = tid; i < WARPS * k_radix; i += THREADS)
+                (&s.warp_hist[0][0])[i] = 0;
+            __syncthreads();
+            const uint32_t tile = s.tile;
+            const uint32_t tile_base = tile * uint32_t(TILE);
+            const uint32_t valid = n - tile_base < uint32_t(TILE) ? n - tile_base : uint32_t(TILE);
+            const bool full = valid == uint32_t(TILE);
+            const bool use_tma = full && allow_tma;
+            const uint32_t my_off = warp * WARP_ELEMS + lane; // + i * 32   (warp-striped)
+
+            // ---- stage the tile
+            if (use_tma)
+            {
+                if (tid == 0)
+                {
+                    const uint64_t policy = l2_policy_evict_first();
+                    mbarrier_arrive_expect_tx(&s.bar_keys, TILE * 4);
+                    tma_load_1d(s.keys, keys_in + tile_base, TILE * 4, &s.bar_keys, policy);
+                    mbarrier_arrive_expect_tx(&s.bar_vals, TILE * 4);
+                    tma_load_1d(s.vals, vals_in + tile_base, TILE * 4, &s.bar_vals, policy);
+                }
+                mbarrier_wait(&s.bar_keys, 0);
+            }
+            else
+            {
+                // Slots past the end of the input hold the largest key: they rank after every real key
+                // of the tile and are never written back.
+                for (uint32_t idx = tid; idx < uint32_t(TILE); idx += THREADS)
+                {
+                    s.keys[idx] = idx < valid ? keys_in[tile_base + idx] : 0xffffffffu;
+                    s.vals[idx] = idx < valid ? vals_in[tile_base + idx] : 0u;
+                }
+                __syncthreads();
+            }
+
+            // ---- rank inside the warp: position among the warp's earlier keys with the same digit
+            uint32_t key[IPT];
+#pragma unroll
+            for (int i = 0; i < IPT; i++)
+                key[i] = s.keys[my_off + i * 32];
+            uint32_t rank2[IPT / 2]; // two 16-bit ranks per register
+            uint32_t* wh = s.warp_hist[warp];
+            const uint32_t lt = lanemask_lt();
+#pragma unroll
+            for (int i = 0; i < IPT; i++)
+            {
+                const uint32_t d = (key[i] >> shift) & mask;
+                const uint32_t peers = match_digit<MODE>(d);
+                const uint32_t before = wh[d];
+                __syncwarp();
+                if ((peers & lt) == 0)
+                    wh[d] = before + __popc(peers);
+                __syncwarp();
+                const uint32_t r = before + __popc(peers & lt);
+                if (i & 1)
+                    rank2[i / 2] |= r << 16;
+                else
+                    rank2[i / 2] = r;
+            }
+            __syncthreads(); // every key is in registers; the counters are final
+
+            // ---- per-digit: tile count, offsets of each warp inside the tile, look-back publication
+            uint32_t total = 0, inc = 0, count_valid = 0;
+            if (tid < k_radix)
+            {
+#pragma unroll
+                for (int w = 0; w < WARPS; w++)
+                    total += s.warp_hist[w][tid];
+                // padding slots all carry digit `mask`
+                count_valid = total - (tid == mask ? uint32_t(TILE) - valid : 0u);
+                st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid],
+                               (tile == 0 ? k_lb_inclusive : k_lb_local) | count_valid);
+                inc = total;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    uint32_t t = __shfl_up_sync(k_full_mask, inc, o);
+                    if (lane >= unsigned(o))
+                        inc += t;
+                }
+                if (lane == 31)
+                    s.scan[warp] = inc;
+            }
+            __syncthreads();
+            uint32_t tile_start = 0; // first tile-sorted slot of this thread's digit
+            if (tid < k_radix)
+            {
+                for (unsigned w = 0; w < warp; w++)
+                    tile_start += s.scan[w];
+                tile_start += inc - total;
+                uint32_t running = tile_start;
+#pragma unroll
+                for (int w = 0; w < WARPS; w++)
+                {
+                    const uint32_t c = s.warp_hist[w][tid];
+                    s.warp_hist[w][tid] = running;
+                    running += c;
+                }
+            }
+            __syncthreads();
+
+            // ---- keys -> tile-sorted slots (in place: all keys were read before the barrier above)
+#pragma unroll
+            for (int i = 0; i < IPT; i += 2)
+            {
+                const uint32_t d0 = (key[i] >> shift) & mask;
+                const uint32_t d1 = (key[i + 1] >> shift) & mask;
+                rank2[i / 2] += wh[d0] | (wh[d1] << 16); // both sums stay below 2^16
+                s.keys[rank2[i / 2] & 0xffffu] = key[i];
+                s.keys[rank2[i / 2] >> 16] = key[i + 1];
+            }
+            // ---- values: staging buffer -> registers (the key registers are dead now)
+            if (use_tma)
+                mbarrier_wait(&s.bar_vals, 0);
+            uint32_t val[IPT];
+#pragma unroll
+            for (int i = 0; i < IPT; i++)
+                val[i] = s.vals[my_off + i * 32];
+
+            // ---- decoupled look-back: digits' counts in all earlier tiles
+            if (tid < k_radix)
+            {
+                uint32_t exclusive = 0;
+                if (tile > 0)
+                {
+                    const uint32_t* p = lookback + size_t(tile - 1) * k_radix + tid;
+                    while (true)
+                    {
+                        const uint32_t w = ld_relaxed_u32(p);
+                        if ((w & ~k_lb_value_mask) == 0)
+                            continue; // predecessor has not published yet
+                        exclusive += w & k_lb_value_mask;
+                        if (w & k_lb_inclusive)
+                            break;
+                        p -= k_radix;
+                    }
+                    st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid],
+                                   k_lb_inclusive | ((exclusive + count_valid) & k_lb_value_mask));
+                }
+                s.gbase[tid] = digit_offset[tid] + exclusive - tile_start;
+            }
+            __syncthreads(); // all values are in registers; sorted keys and gbase are visible
+#pragma unroll
+            for (int i = 0; i < IPT; i += 2)
+            {
+                s.vals[rank2[i / 2] & 0xffffu] = val[i];
+                s.vals[rank2[i / 2] >> 16] = val[i + 1];
+            }
+            __syncthreads();
+
+            // ---- out: consecutive threads write consecutive addresses inside each digit run
+#pragma unroll
+            for (int k = 0; k < IPT; k++)
+            {
+                const uint32_t p = tid + k * THREADS;
+                const uint32_t kk = s.keys[p];
+                const uint32_t vv = s.vals[p];
+                const uint32_t dst = s.gbase[(kk >> shift) & mask] + p;
+                if (full || p < valid)
+                {
+                    keys_out[dst] = kk;
+                    vals_out[dst] = vv;
+                }
+            }
+        }
+
+        // ------------------------------------------------------------------------------------ host side
+
+        struct SweepConfig
+        {
+            int id;
+            int threads, ipt;
+        };
+        constexpr SweepConfig k_configs[] = {
+            {0, 512, 16}, // 8192-pair tiles, 2 CTAs/SM
+            {1, 384, 18}, // 6912, 3 CTAs/SM
+            {2, 256, 16}, // 4096, 4 CTAs/SM
+            {3, 512, 12}, // 6144, 2 CTAs/SM
+            {4, 384, 22}, // 8448, 2 CTAs/SM
+            {5, 256, 8},  // 2048 (small inputs: more CTAs)
+        };
+        constexpr int k_num_configs = int(sizeof(k_configs) / sizeof(k_configs[0]));
+
+        int env_int(const char* name, int fallback)
+        {
+            const char* v = std::getenv(name);
+            return v && *v ? std::atoi(v) : fallback;
+        }
+
+        const SweepConfig& select_config(size_t count)
+        {
+            static const int forced = env_int("GLU_SORT_CONFIG", -1); // tuning sweeps only
+            if (forced >= 0 && forced < k_num_configs)
+                return k_configs[forced];
+            if (count <= (size_t(1) << 18))
+                return k_configs[5];
+            if (count <= (size_t(1) << 21))
+                return k_configs[2];
+            return k_configs[1];
+        }
+
+        bool use_tma_env()
+        {
+            static const int v = env_int("GLU_SORT_TMA", 1); // 0: force the ld/st staging path (tuning, tests)
+            return v != 0;
+        }
+
+        int rank_mode()
+        {
+            static const int mode = env_int("GLU_SORT_RANK", Rank_Match);
+            return mode == Rank_Ballot ? Rank_Ballot : Rank_Match;
+        }
+
+        struct TmpLayout
+        {
+            size_t tiles;
+            size_t control_bytes; // tickets + histograms + look-back words: zeroed at the start of a sort
+            size_t off_hist, off_lookback, off_keys, off_vals, total;
+        };
+
+        TmpLayout make_layout(size_t count)
+        {
+            const SweepConfig& c = select_config(count);
+            TmpLayout l;
+            const size_t tile = size_t(c.threads) * c.ipt;
+            l.tiles = (count + tile - 1) / tile;
+            l.off_hist = k_tmp_align; // tickets live in [0, 256)
+            l.off_lookback = l.off_hist + k_max_passes * k_radix * sizeof(uint32_t);
+            l.control_bytes = align_up(l.off_lookback + k_max_passes * l.tiles * k_radix * sizeof(uint32_t), k_tmp_align);
+            l.off_keys = l.control_bytes;
+            l.off_vals = l.off_keys + align_up(count * sizeof(uint32_t), k_tmp_align);
+            l.total = l.off_vals + align_up(count * sizeof(uint32_t), k_tmp_align);
+            return l;
+        }
+
+        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE>
+        int launch_sweep(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint32_t n, uint32_t shift,
+                         uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback, uint32_t* ticket,
+                         unsigned tiles, cudaStream_t s)
+        {
+            auto kernel = onesweep_kernel<THREADS, IPT, MIN_BLOCKS, MODE>;
+            // TMA bulk copies need 16-byte aligned sources (tiles are multiples of 4 elements)
+            const int allow_tma =
+                ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
+            constexpr size_t smem = sizeof(SweepSmem<THREADS, IPT>);
+            static bool configured[64] = {};
+            int dev = 0;
+            GLU_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev < 64 && !configured[dev])
+            {
+                GLU_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+                configured[dev] = true;
+            }
+            kernel<<<tiles, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket,
+                                                allow_tma);
+            GLU_LAUNCH_CHECK();
+            return GLU_SUCCESS;
+        }
+
+        template<int MODE>
+        int dispatch_sweep(const SweepConfig& c, const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo,
+                           uint32_t n, uint32_t shift, uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback,
+                           uint32_t* ticket, unsigned tiles, cudaStream_t s)
+        {
+            switch (c.id)
+            {
+            case 0: return launch_sweep<512, 16, 2, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+            case 1: return launch_sweep<384, 18, 3, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+            case 2: return launch_sweep<256, 16, 4, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+            case 3: return launch_sweep<512, 12, 2, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+            case 4: return launch_sweep<384, 22, 2, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+            default: return launch_sweep<256, 8, 4, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+            }
+        }
+    } // namespace
+} // namespace glu_b200
+
+using namespace glu_b200;
+
+extern "C" size_t glu_radix_sort_u32kv_tmp_bytes(size_t count)
+{
+    if (count > k_max_count)
+        return 0;
+    if (count <= 1)
+        return k_tmp_align;
+    return make_layout(count).total;
+}
+
+extern "C" int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t count, size_t num_steps, void* d_tmp,
+                                    size_t tmp_bytes, glu_stream_t stream)
+{
+    if (!d_keys || !d_vals) // glu/RadixSort.hpp:275-276
+        return GLU_ERROR_INVALID_ARGUMENT;
+    if (count <= 1) // glu/RadixSort.hpp:278-279
+        return GLU_SUCCESS;
+    if (count > k_max_count)
+        return GLU_ERROR_COUNT_TOO_LARGE;
+    if ((reinterpret_cast<uintptr_t>(d_keys) | reinterpret_cast<uintptr_t>(d_vals)) % sizeof(uint32_t) != 0)
+        return GLU_ERROR_MISALIGNED;
+    const TmpLayout l = make_layout(count);
+    if (!d_tmp || tmp_bytes < l.total)
+        return GLU_ERROR_TMP_TOO_SMALL;
+    if (reinterpret_cast<uintptr_t>(d_tmp) % k_tmp_align != 0)
+        return GLU_ERROR_MISALIGNED;
+    const int sms = current_sm_count();
+    if (sms <= 0)
+        return GLU_ERROR_CUDA;
+
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    char* tmp = static_cast<char*>(d_tmp);
+    uint32_t* tickets = reinterpret_cast<uint32_t*>(tmp); // [0..3] sweep passes, [4] histogram
+    uint32_t* hist = reinterpret_cast<uint32_t*>(tmp + l.off_hist);
+    uint32_t* lookback = reinterpret_cast<uint32_t*>(tmp + l.off_lookback);
+    uint32_t* alt_keys = reinterpret_cast<uint32_t*>(tmp + l.off_keys);
+    uint32_t* alt_vals = reinterpret_cast<uint32_t*>(tmp + l.off_vals);
+    const PassPlan plan = make_pass_plan(num_steps);
+    const uint32_t n = uint32_t(count);
+
+    const size_t used_control = l.off_lookback + size_t(plan.num_passes) * l.tiles * k_radix * sizeof(uint32_t);
+    GLU_CUDA_TRY(cudaMemsetAsync(tmp, 0, used_control, s));
+
+    {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(d_keys);
+        uint32_t head = uint32_t(((16 - (addr & 15)) & 15) / sizeof(uint32_t));
+        if (head > n)
+            head = n;
+        const uint32_t n_units = (n - head) / 4;
+        const size_t per_block = size_t(k_hist_threads) * k_hist_unroll;
+        size_t grid = (size_t(n_units) + per_block - 1) / per_block;
+        const size_t cap = size_t(sms) * k_hist_blocks_per_sm;
+        grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
+        histogram_kernel<<<unsigned(grid), k_hist_threads, 0, s>>>(d_keys, n, head, n_units, plan.num_passes,
+                                                                    plan.key_mask, hist, tickets + 4);
+        GLU_LAUNCH_CHECK();
+    }
+
+    const SweepConfig& cfg = select_config(count);
+    const int mode = rank_mode();
+    uint32_t* kbuf[2] = {d_keys, alt_keys};
+    uint32_t* vbuf[2] = {d_vals, alt_vals};
+    for (int p = 0; p < plan.num_passes; p++)
+    {
+        const uint32_t* ki = kbuf[p & 1];
+        const uint32_t* vi = vbuf[p & 1];
+        uint32_t* ko = kbuf[(p + 1) & 1];
+        uint32_t* vo = vbuf[(p + 1) & 1];
+        uint32_t* lb = lookback + size_t(p) * l.tiles * k_radix;
+        int rc = mode == Rank_Ballot
+                     ? dispatch_sweep<Rank_Ballot>(cfg, ki, vi, ko, vo, n, plan.shift[p], plan.mask[p],
+                                                   hist + p * k_radix, lb, tickets + p, unsigned(l.tiles), s)
+                     : dispatch_sweep<Rank_Match>(cfg, ki, vi, ko, vo, n, plan.shift[p], plan.mask[p],
+                                                  hist + p * k_radix, lb, tickets + p, unsigned(l.tiles), s);
+        if (rc != GLU_SUCCESS)
+            return rc;
+    }
+    if (plan.num_passes & 1)
+    {
+        // an odd number of passes leaves the result in the scratch: bring it home (the reference would
+        // leave it there, glu/RadixSort.hpp:315-329 — documented deviation)
+        GLU_CUDA_TRY(cudaMemcpyAsync(d_keys, alt_keys, count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        GLU_CUDA_TRY(cudaMemcpyAsync(d_vals, alt_vals, count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+    }
+    return GLU_SUCCESS;
+}

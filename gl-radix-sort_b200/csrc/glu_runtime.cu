@@ -1,0 +1,345 @@
+// glu_runtime.cu — the non-kernel part of the C ABI: status strings, data-type table, device memory /
+// stream / event plumbing (the ShaderStorageBuffer + measure_gl_elapsed_time roles of
+// glu/gl_utils.hpp:146-265) and the host-buffer entry points used for end-to-end measurements.
+#include <cstdio>
+#include <cstring>
+
+#include "glu_common.cuh"
+
+namespace glu_b200
+{
+    std::atomic<uint64_t> g_kernel_launches{0};
+    thread_local cudaError_t t_last_cuda_error = cudaSuccess;
+
+    int current_sm_count()
+    {
+        static std::atomic<int> cache[64];
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+        {
+            t_last_cuda_error = cudaGetLastError();
+            return 0;
+        }
+        int v = cache[dev].load(std::memory_order_relaxed);
+        if (v == 0)
+        {
+            if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+            {
+                t_last_cuda_error = cudaGetLastError();
+                return 0;
+            }
+            cache[dev].store(v, std::memory_order_relaxed);
+        }
+        return v;
+    }
+
+    bool data_type_info(int data_type, DataTypeInfo* out)
+    {
+        // {scalar kind, components}; scalar kind: 0 f32, 1 f64, 2 i32, 3 u32  (glu/data_types.hpp:8-22)
+        static const int table[12][2] = {{0, 1}, {1, 1}, {2, 1}, {3, 1}, {0, 2}, {0, 4},
+                                         {1, 2}, {1, 4}, {3, 2}, {3, 4}, {2, 2}, {2, 4}};
+        if (data_type < 0 || data_type > 11)
+            return false;
+        out->scalar = table[data_type][0];
+        out->ncomp = table[data_type][1];
+        out->scalar_size = out->scalar == 1 ? 8 : 4;
+        return true;
+    }
+} // namespace glu_b200
+
+using namespace glu_b200;
+
+namespace
+{
+    __global__ void fill_u32_kernel(uint32_t* dst, uint32_t value, size_t count)
+    {
+        for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x)
+            dst[i] = value;
+    }
+} // namespace
+
+extern "C"
+{
+    int glu_version(void) { return 100; }
+
+    const char* glu_status_string(int status)
+    {
+        switch (status)
+        {
+        case GLU_SUCCESS: return "success";
+        case GLU_ERROR_INVALID_ARGUMENT: return "invalid argument";
+        case GLU_ERROR_INVALID_DATA_TYPE: return "invalid data type";
+        case GLU_ERROR_INVALID_OPERATOR: return "invalid reduction operator";
+        case GLU_ERROR_TMP_TOO_SMALL: return "temporary storage missing or too small";
+        case GLU_ERROR_MISALIGNED: return "misaligned buffer";
+        case GLU_ERROR_COUNT_TOO_LARGE: return "count too large";
+        case GLU_ERROR_CUDA: return "CUDA error";
+        default: return "unknown status";
+        }
+    }
+
+    const char* glu_last_cuda_error(void) { return cudaGetErrorString(t_last_cuda_error); }
+
+    size_t glu_data_type_size(int data_type)
+    {
+        DataTypeInfo info;
+        if (!data_type_info(data_type, &info))
+            return 0;
+        return info.scalar_size * size_t(info.ncomp);
+    }
+
+    uint64_t glu_kernel_launch_count(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
+
+    // ------------------------------------------------------------------------------------------ plumbing
+
+    int glu_device_count(int* count)
+    {
+        if (!count)
+            return GLU_ERROR_INVALID_ARGUMENT;
+        *count = 0;
+        GLU_CUDA_TRY(cudaGetDeviceCount(count));
+        return GLU_SUCCESS;
+    }
+
+    int glu_set_device(int device)
+    {
+        GLU_CUDA_TRY(cudaSetDevice(device));
+        return GLU_SUCCESS;
+    }
+
+    int glu_device_info(int device, char* name, size_t name_cap, int* sm_count, int* cc_major, int* cc_minor,
+                        size_t* total_mem_bytes, int* warp_size)
+    {
+        cudaDeviceProp prop;
+        GLU_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (name && name_cap)
+        {
+            std::strncpy(name, prop.name, name_cap - 1);
+            name[name_cap - 1] = 0;
+        }
+        if (sm_count)
+            *sm_count = prop.multiProcessorCount;
+        if (cc_major)
+            *cc_major = prop.major;
+        if (cc_minor)
+            *cc_minor = prop.minor;
+        if (total_mem_bytes)
+            *total_mem_bytes = prop.totalGlobalMem;
+        if (warp_size)
+            *warp_size = prop.warpSize;
+        return GLU_SUCCESS;
+    }
+
+    int glu_malloc(void** d_ptr, size_t bytes)
+    {
+        if (!d_ptr)
+            return GLU_ERROR_INVALID_ARGUMENT;
+        *d_ptr = nullptr;
+        if (bytes == 0)
+            return GLU_SUCCESS;
+        GLU_CUDA_TRY(cudaMalloc(d_ptr, bytes));
+        return GLU_SUCCESS;
+    }
+
+    int glu_free(void* d_ptr)
+    {
+        if (d_ptr)
+            GLU_CUDA_TRY(cudaFree(d_ptr));
+        return GLU_SUCCESS;
+    }
+
+    int glu_malloc_host(void** h_ptr, size_t bytes)
+    {
+        if (!h_ptr)
+            return GLU_ERROR_INVALID_ARGUMENT;
+        *h_ptr = nullptr;
+        if (bytes == 0)
+            return GLU_SUCCESS;
+        GLU_CUDA_TRY(cudaMallocHost(h_ptr, bytes));
+        return GLU_SUCCESS;
+    }
+
+    int glu_free_host(void* h_ptr)
+    {
+        if (h_ptr)
+            GLU_CUDA_TRY(cudaFreeHost(h_ptr));
+        return GLU_SUCCESS;
+    }
+
+    int glu_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, glu_stream_t stream)
+    {
+        GLU_CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+        return GLU_SUCCESS;
+    }
+
+    int glu_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, glu_stream_t stream)
+    {
+        GLU_CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+        return GLU_SUCCESS;
+    }
+
+    int glu_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, glu_stream_t stream)
+    {
+        GLU_CUDA_TRY(
+            cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+        return GLU_SUCCESS;
+    }
+
+    int glu_memset_u32(void* d_dst, uint32_t value, size_t count, glu_stream_t stream)
+    {
+        // glu/gl_utils.hpp:213-217 — ShaderStorageBuffer::clear(GLuint value)
+        if (count == 0)
+            return GLU_SUCCESS;
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const uint32_t b = value & 0xffu;
+        if (value == (b | (b << 8) | (b << 16) | (b << 24)))
+            GLU_CUDA_TRY(cudaMemsetAsync(d_dst, int(b), count * sizeof(uint32_t), s));
+        else
+        {
+            int grid = int((count + 255) / 256 < 65535 * 8 ? (count + 255) / 256 : 65535 * 8);
+            fill_u32_kernel<<<grid, 256, 0, s>>>(static_cast<uint32_t*>(d_dst), value, count);
+            GLU_LAUNCH_CHECK();
+        }
+        return GLU_SUCCESS;
+    }
+
+    int glu_stream_create(glu_stream_t* stream)
+    {
+        if (!stream)
+            return GLU_ERROR_INVALID_ARGUMENT;
+        cudaStream_t s;
+        GLU_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        *stream = s;
+        return GLU_SUCCESS;
+    }
+
+    int glu_stream_destroy(glu_stream_t stream)
+    {
+        GLU_CUDA_TRY(cudaStreamDestroy(static_cast<cudaStream_t>(stream)));
+        return GLU_SUCCESS;
+    }
+
+    int glu_stream_synchronize(glu_stream_t stream)
+    {
+        GLU_CUDA_TRY(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+        return GLU_SUCCESS;
+    }
+
+    int glu_event_create(glu_event_t* event)
+    {
+        if (!event)
+            return GLU_ERROR_INVALID_ARGUMENT;
+        cudaEvent_t e;
+        GLU_CUDA_TRY(cudaEventCreate(&e));
+        *event = e;
+        return GLU_SUCCESS;
+    }
+
+    int glu_event_destroy(glu_event_t event)
+    {
+        GLU_CUDA_TRY(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+        return GLU_SUCCESS;
+    }
+
+    int glu_event_record(glu_event_t event, glu_stream_t stream)
+    {
+        GLU_CUDA_TRY(cudaEventRecord(static_cast<cudaEvent_t>(event), static_cast<cudaStream_t>(stream)));
+        return GLU_SUCCESS;
+    }
+
+    int glu_event_synchronize(glu_event_t event)
+    {
+        GLU_CUDA_TRY(cudaEventSynchronize(static_cast<cudaEvent_t>(event)));
+        return GLU_SUCCESS;
+    }
+
+    int glu_event_elapsed_ms(float* ms, glu_event_t start, glu_event_t stop)
+    {
+        if (!ms)
+            return GLU_ERROR_INVALID_ARGUMENT;
+        GLU_CUDA_TRY(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)));
+        return GLU_SUCCESS;
+    }
+
+    // ------------------------------------------------------------------------- host-buffer entry points
+
+    namespace
+    {
+        struct DeviceScratch // RAII for the synchronous host variants
+        {
+            void* p = nullptr;
+            ~DeviceScratch()
+            {
+                if (p)
+                    cudaFree(p);
+            }
+        };
+    } // namespace
+
+    int glu_reduce_host(void* h_data, size_t count, int data_type, int op)
+    {
+        size_t esz = glu_data_type_size(data_type);
+        if (esz == 0)
+            return GLU_ERROR_INVALID_DATA_TYPE;
+        if (!h_data || count == 0)
+            return GLU_ERROR_INVALID_ARGUMENT;
+        DeviceScratch data, tmp;
+        size_t tmp_bytes = glu_reduce_tmp_bytes(count, data_type);
+        GLU_CUDA_TRY(cudaMalloc(&data.p, count * esz));
+        GLU_CUDA_TRY(cudaMalloc(&tmp.p, tmp_bytes));
+        GLU_CUDA_TRY(cudaMemcpyAsync(data.p, h_data, count * esz, cudaMemcpyHostToDevice, 0));
+        int rc = glu_reduce(data.p, count, data_type, op, tmp.p, tmp_bytes, nullptr);
+        if (rc != GLU_SUCCESS)
+            return rc;
+        GLU_CUDA_TRY(cudaMemcpyAsync(h_data, data.p, esz, cudaMemcpyDeviceToHost, 0));
+        GLU_CUDA_TRY(cudaStreamSynchronize(0));
+        return GLU_SUCCESS;
+    }
+
+    int glu_scan_exclusive_host(void* h_data, size_t count, size_t num_partitions, int data_type)
+    {
+        size_t esz = glu_data_type_size(data_type);
+        if (esz == 0)
+            return GLU_ERROR_INVALID_DATA_TYPE;
+        if (!h_data || count == 0 || num_partitions == 0)
+            return GLU_ERROR_INVALID_ARGUMENT;
+        DeviceScratch data, tmp;
+        size_t bytes = count * num_partitions * esz;
+        size_t tmp_bytes = glu_scan_exclusive_tmp_bytes(count, num_partitions, data_type);
+        GLU_CUDA_TRY(cudaMalloc(&data.p, bytes));
+        GLU_CUDA_TRY(cudaMalloc(&tmp.p, tmp_bytes));
+        GLU_CUDA_TRY(cudaMemcpyAsync(data.p, h_data, bytes, cudaMemcpyHostToDevice, 0));
+        int rc = glu_scan_exclusive(data.p, count, num_partitions, data_type, tmp.p, tmp_bytes, nullptr);
+        if (rc != GLU_SUCCESS)
+            return rc;
+        GLU_CUDA_TRY(cudaMemcpyAsync(h_data, data.p, bytes, cudaMemcpyDeviceToHost, 0));
+        GLU_CUDA_TRY(cudaStreamSynchronize(0));
+        return GLU_SUCCESS;
+    }
+
+    int glu_radix_sort_u32kv_host(uint32_t* h_keys, uint32_t* h_vals, size_t count, size_t num_steps)
+    {
+        if (!h_keys || !h_vals)
+            return GLU_ERROR_INVALID_ARGUMENT;
+        if (count <= 1)
+            return GLU_SUCCESS;
+        DeviceScratch keys, vals, tmp;
+        size_t bytes = count * sizeof(uint32_t);
+        size_t tmp_bytes = glu_radix_sort_u32kv_tmp_bytes(count);
+        if (tmp_bytes == 0)
+            return GLU_ERROR_COUNT_TOO_LARGE;
+        GLU_CUDA_TRY(cudaMalloc(&keys.p, bytes));
+        GLU_CUDA_TRY(cudaMalloc(&vals.p, bytes));
+        GLU_CUDA_TRY(cudaMalloc(&tmp.p, tmp_bytes));
+        GLU_CUDA_TRY(cudaMemcpyAsync(keys.p, h_keys, bytes, cudaMemcpyHostToDevice, 0));
+        GLU_CUDA_TRY(cudaMemcpyAsync(vals.p, h_vals, bytes, cudaMemcpyHostToDevice, 0));
+        int rc = glu_radix_sort_u32kv(static_cast<uint32_t*>(keys.p), static_cast<uint32_t*>(vals.p), count, num_steps,
+                                      tmp.p, tmp_bytes, nullptr);
+        if (rc != GLU_SUCCESS)
+            return rc;
+        GLU_CUDA_TRY(cudaMemcpyAsync(h_keys, keys.p, bytes, cudaMemcpyDeviceToHost, 0));
+        GLU_CUDA_TRY(cudaMemcpyAsync(h_vals, vals.p, bytes, cudaMemcpyDeviceToHost, 0));
+        GLU_CUDA_TRY(cudaStreamSynchronize(0));
+        return GLU_SUCCESS;
+    }
+}

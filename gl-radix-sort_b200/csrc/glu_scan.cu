@@ -1,0 +1,578 @@
+// glu_scan.cu — glu_scan_exclusive(): the B200 replacement for glu::BlellochScan::operator()
+// (glu/BlellochScan.hpp:130-139, host loops :142-190, shaders :13-76).
+//
+// The reference runs a Blelloch up-sweep and down-sweep in GLOBAL memory, one dispatch per tree level
+// (2*log2(N) dispatches, stride-2^k gathers, ~5 element-sized transfers per element, power-of-two N
+// only).  Here the scan is ONE kernel launch that reads every element once and writes it once
+// (8 B of HBM traffic per 32-bit element):
+//   * a tile of THREADS x VPT 16-byte vectors is loaded warp-striped with 128-bit streaming loads,
+//     scanned in registers (4-element serial scan + shuffle scan across the warp + chunk chaining);
+//   * tiles are chained with a decoupled look-back (Merrill & Garland): each tile publishes its
+//     aggregate, then walks back over its predecessors' {aggregate | inclusive prefix} words, a warp
+//     at a time, until it meets an inclusive prefix;  status and value share one 64-bit word, so a
+//     single relaxed 64-bit store / load is the whole protocol for 4-byte element types;
+//   * tile ids come from an atomic ticket, so a tile's predecessors are always already running
+//     (forward progress does not depend on the hardware's CTA scheduling order);
+//   * `num_partitions` adjacent segments are native: tiles never straddle a segment, the first tile
+//     of each segment publishes an inclusive prefix directly and look-back stops at the segment start;
+//   * any `count` is accepted (the reference aborts on non powers of two, glu/BlellochScan.hpp:134).
+// Element types wider than 4 bytes (double, vecN, dvecN, ...) use the same structure with one
+// element per lane per item and a {flag, aggregate, inclusive} record published with release /
+// acquire ordering.
+#include "glu_common.cuh"
+
+namespace glu_b200
+{
+    namespace
+    {
+        constexpr uint64_t k_flag_aggregate = 1ull << 32;
+        constexpr uint64_t k_flag_inclusive = 2ull << 32;
+
+        template<typename T> __device__ __forceinline__ uint32_t to_bits(T v);
+        template<> __device__ __forceinline__ uint32_t to_bits<uint32_t>(uint32_t v) { return v; }
+        template<> __device__ __forceinline__ uint32_t to_bits<float>(float v) { return __float_as_uint(v); }
+        template<typename T> __device__ __forceinline__ T from_bits(uint32_t v);
+        template<> __device__ __forceinline__ uint32_t from_bits<uint32_t>(uint32_t v) { return v; }
+        template<> __device__ __forceinline__ float from_bits<float>(uint32_t v) { return __uint_as_float(v); }
+
+        template<typename T> struct is_float_type
+        {
+            static constexpr bool value = false;
+        };
+        template<> struct is_float_type<float>
+        {
+            static constexpr bool value = true;
+        };
+
+        // inclusive scan of `v` across the warp
+        template<typename T> __device__ __forceinline__ T warp_inclusive_scan(T v, unsigned lane)
+        {
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                T t = __shfl_up_sync(k_full_mask, v, o);
+                if (lane >= unsigned(o))
+                    v += t;
+            }
+            return v;
+        }
+
+        template<typename T> __device__ __forceinline__ T warp_sum(T v)
+        {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                v += __shfl_xor_sync(k_full_mask, v, o);
+            return v;
+        }
+        template<> __device__ __forceinline__ uint32_t warp_sum<uint32_t>(uint32_t v)
+        {
+            return __reduce_add_sync(k_full_mask, v);
+        }
+
+        // ------------------------------------------------------------------------ 4-byte element types
+        //
+        // T = uint32_t (also serves Int: two's-complement addition is the same bit pattern) or float.
+        template<typename T, int THREADS, int VPT>
+        __global__ void __launch_bounds__(THREADS)
+            scan_b32_kernel(T* __restrict__ data, size_t count, uint32_t tiles_per_part, uint32_t* ticket,
+                            uint64_t* state)
+        {
+            constexpr int TILE = THREADS * VPT * 4;
+            constexpr int WARPS = THREADS / 32;
+            constexpr int WARP_ELEMS = VPT * 128;
+            static_assert(WARPS <= 32, "one warp scans the warp totals");
+
+            __shared__ T s_warp_total[WARPS];
+            __shared__ T s_warp_prefix[WARPS];
+            __shared__ T s_tile_prefix;
+            __shared__ uint32_t s_tile;
+
+            const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+            if (threadIdx.x == 0)
+                s_tile = atomicAdd(ticket, 1u);
+            __syncthreads();
+            const uint32_t tile = s_tile;
+            const uint32_t part = tile / tiles_per_part;
+            const uint32_t tp = tile - part * tiles_per_part; // tile index inside its partition
+            const size_t in_part = size_t(tp) * TILE;
+            const size_t base = size_t(part) * count + in_part;
+            const uint32_t valid = uint32_t(count - in_part < size_t(TILE) ? count - in_part : size_t(TILE));
+            const bool vec = valid == uint32_t(TILE) && (reinterpret_cast<uintptr_t>(data + base) & 15) == 0;
+            const uint32_t my_off = warp * WARP_ELEMS + lane * 4; // + j * 128
+
+            T x[VPT][4];
+            if (vec)
+            {
+#pragma unroll
+                for (int j = 0; j < VPT; j++)
+                {
+                    uint4 r = ld_stream_v4(data + base + my_off + j * 128);
+                    x[j][0] = from_bits<T>(r.x);
+                    x[j][1] = from_bits<T>(r.y);
+                    x[j][2] = from_bits<T>(r.z);
+                    x[j][3] = from_bits<T>(r.w);
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int j = 0; j < VPT; j++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                    {
+                        uint32_t idx = my_off + j * 128 + c;
+                        x[j][c] = idx < valid ? data[base + idx] : T(0);
+                    }
+            }
+
+            // per-vector sums, then VPT independent warp scans, then chain the VPT chunks of the warp
+            T sum4[VPT], inc[VPT], ex[VPT];
+#pragma unroll
+            for (int j = 0; j < VPT; j++)
+                inc[j] = sum4[j] = x[j][0] + x[j][1] + x[j][2] + x[j][3];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+                for (int j = 0; j < VPT; j++)
+                {
+                    T t = __shfl_up_sync(k_full_mask, inc[j], o);
+                    if (lane >= unsigned(o))
+                        inc[j] += t;
+                }
+            T chunk_base = T(0);
+#pragma unroll
+            for (int j = 0; j < VPT; j++)
+            {
+                T total = __shfl_sync(k_full_mask, inc[j], 31);
+                T lane_ex;
+                if (is_float_type<T>::value)
+                {
+                    lane_ex = __shfl_up_sync(k_full_mask, inc[j], 1); // exact: no inclusive-minus-own rounding
+                    if (lane == 0)
+                        lane_ex = T(0);
+                }
+                else
+                    lane_ex = inc[j] - sum4[j];
+                ex[j] = chunk_base + lane_ex;
+                chunk_base += total;
+            }
+            if (lane == 0)
+                s_warp_total[warp] = chunk_base;
+            __syncthreads();
+
+            if (warp == 0)
+            {
+                T wt = lane < WARPS ? s_warp_total[lane] : T(0);
+                T winc = warp_inclusive_scan(wt, lane);
+                T wex = __shfl_up_sync(k_full_mask, winc, 1);
+                if (lane == 0)
+                    wex = T(0);
+                if (lane < WARPS)
+                    s_warp_prefix[lane] = wex;
+                const T aggregate = __shfl_sync(k_full_mask, winc, 31);
+
+                T exclusive = T(0);
+                if (tp == 0)
+                {
+                    if (lane == 0)
+                        st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(aggregate));
+                }
+                else
+                {
+                    if (lane == 0)
+                        st_relaxed_u64(&state[tile], k_flag_aggregate | to_bits<T>(aggregate));
+                    // decoupled look-back, 32 predecessors per step; lanes past the partition start behave
+                    // as an inclusive prefix of 0, which ends the walk
+                    uint32_t remaining = tp;
+                    uint32_t pred = tile - 1;
+                    while (true)
+                    {
+                        const bool in_range = lane < remaining;
+                        uint64_t w;
+                        uint32_t inclusive_mask;
+                        while (true)
+                        {
+                            w = in_range ? ld_relaxed_u64(&state[pred - lane]) : k_flag_inclusive;
+                            const uint32_t flag = uint32_t(w >> 32);
+                            const uint32_t empty_mask = __ballot_sync(k_full_mask, flag == 0);
+                            inclusive_mask = __ballot_sync(k_full_mask, flag == 2);
+                            // only the lanes up to the first inclusive prefix matter
+                            const uint32_t need =
+                                inclusive_mask ? ((2u << (__ffs(inclusive_mask) - 1)) - 1u) : k_full_mask;
+                            if ((empty_mask & need) == 0)
+                                break;
+                        }
+                        const uint32_t first = inclusive_mask ? uint32_t(__ffs(inclusive_mask) - 1) : 31u;
+                        T contrib = lane <= first ? from_bits<T>(uint32_t(w)) : T(0);
+                        exclusive += warp_sum(contrib);
+                        if (inclusive_mask)
+                            break;
+                        pred -= 32;
+                        remaining -= 32;
+                    }
+                    if (lane == 0)
+                        st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(exclusive + aggregate));
+                }
+                if (lane == 0)
+                    s_tile_prefix = exclusive;
+            }
+            __syncthreads();
+
+            const T prefix = s_tile_prefix + s_warp_prefix[warp];
+            if (vec)
+            {
+#pragma unroll
+                for (int j = 0; j < VPT; j++)
+                {
+                    T b = prefix + ex[j];
+                    uint4 r;
+                    r.x = to_bits<T>(b);
+                    b += x[j][0];
+                    r.y = to_bits<T>(b);
+                    b += x[j][1];
+                    r.z = to_bits<T>(b);
+                    b += x[j][2];
+                    r.w = to_bits<T>(b);
+                    st_stream_v4(data + base + my_off + j * 128, r);
+                }
+            }
+            else
+            {
+#pragma unroll
+                for (int j = 0; j < VPT; j++)
+                {
+                    T b = prefix + ex[j];
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                    {
+                        uint32_t idx = my_off + j * 128 + c;
+                        if (idx < valid)
+                            data[base + idx] = b;
+                        b += x[j][c];
+                    }
+                }
+            }
+        }
+
+        // ------------------------------------------------------------------------ wide element types
+        template<typename S, int NC> struct alignas(sizeof(S) * NC) Elem
+        {
+            S c[NC];
+        };
+
+        template<typename S, int NC> __device__ __forceinline__ Elem<S, NC> elem_zero()
+        {
+            Elem<S, NC> e;
+#pragma unroll
+            for (int k = 0; k < NC; k++)
+                e.c[k] = S(0);
+            return e;
+        }
+        template<typename S, int NC> __device__ __forceinline__ void elem_add(Elem<S, NC>& a, const Elem<S, NC>& b)
+        {
+#pragma unroll
+            for (int k = 0; k < NC; k++)
+                a.c[k] += b.c[k];
+        }
+        template<typename S, int NC>
+        __device__ __forceinline__ Elem<S, NC> elem_shfl_up(const Elem<S, NC>& a, int o)
+        {
+            Elem<S, NC> r;
+#pragma unroll
+            for (int k = 0; k < NC; k++)
+                r.c[k] = __shfl_up_sync(k_full_mask, a.c[k], o);
+            return r;
+        }
+        template<typename S, int NC> __device__ __forceinline__ Elem<S, NC> elem_shfl(const Elem<S, NC>& a, int src)
+        {
+            Elem<S, NC> r;
+#pragma unroll
+            for (int k = 0; k < NC; k++)
+                r.c[k] = __shfl_sync(k_full_mask, a.c[k], src);
+            return r;
+        }
+        template<typename S, int NC> __device__ __forceinline__ Elem<S, NC> elem_warp_sum(Elem<S, NC> a)
+        {
+#pragma unroll
+            for (int k = 0; k < NC; k++)
+                a.c[k] = warp_sum<S>(a.c[k]);
+            return a;
+        }
+        template<typename S, int NC>
+        __device__ __forceinline__ Elem<S, NC> elem_warp_inclusive_scan(Elem<S, NC> v, unsigned lane)
+        {
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                Elem<S, NC> t = elem_shfl_up(v, o);
+                if (lane >= unsigned(o))
+                    elem_add(v, t);
+            }
+            return v;
+        }
+        template<typename S, int NC> __device__ __forceinline__ Elem<S, NC> elem_ldcg(const Elem<S, NC>* p)
+        {
+            Elem<S, NC> r;
+            const S* q = reinterpret_cast<const S*>(p);
+#pragma unroll
+            for (int k = 0; k < NC; k++)
+                r.c[k] = __ldcg(q + k);
+            return r;
+        }
+
+        // state layout: flags u32[tiles] | aggregates E[tiles] | inclusives E[tiles]
+        template<typename S, int NC, int THREADS, int IPT>
+        __global__ void __launch_bounds__(THREADS)
+            scan_wide_kernel(Elem<S, NC>* __restrict__ data, size_t count, uint32_t tiles_per_part, uint32_t* ticket,
+                             uint32_t* flags, Elem<S, NC>* aggregates, Elem<S, NC>* inclusives)
+        {
+            using E = Elem<S, NC>;
+            constexpr int TILE = THREADS * IPT;
+            constexpr int WARPS = THREADS / 32;
+            constexpr int WARP_ELEMS = IPT * 32;
+
+            __shared__ E s_warp_total[WARPS];
+            __shared__ E s_warp_prefix[WARPS];
+            __shared__ E s_tile_prefix;
+            __shared__ uint32_t s_tile;
+
+            const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            if (threadIdx.x == 0)
+                s_tile = atomicAdd(ticket, 1u);
+            __syncthreads();
+            const uint32_t tile = s_tile;
+            const uint32_t part = tile / tiles_per_part;
+            const uint32_t tp = tile - part * tiles_per_part;
+            const size_t in_part = size_t(tp) * TILE;
+            const size_t base = size_t(part) * count + in_part;
+            const uint32_t valid = uint32_t(count - in_part < size_t(TILE) ? count - in_part : size_t(TILE));
+            const uint32_t my_off = warp * WARP_ELEMS + lane; // + j * 32
+
+            E x[IPT], ex[IPT];
+#pragma unroll
+            for (int j = 0; j < IPT; j++)
+            {
+                uint32_t idx = my_off + j * 32;
+                x[j] = idx < valid ? data[base + idx] : elem_zero<S, NC>();
+            }
+            E chunk_base = elem_zero<S, NC>();
+#pragma unroll
+            for (int j = 0; j < IPT; j++)
+            {
+                E inc = elem_warp_inclusive_scan(x[j], lane);
+                E total = elem_shfl(inc, 31);
+                E lane_ex = elem_shfl_up(inc, 1);
+                if (lane == 0)
+                    lane_ex = elem_zero<S, NC>();
+                ex[j] = chunk_base;
+                elem_add(ex[j], lane_ex);
+                elem_add(chunk_base, total);
+            }
+            if (lane == 0)
+                s_warp_total[warp] = chunk_base;
+            __syncthreads();
+
+            if (warp == 0)
+            {
+                E wt = lane < WARPS ? s_warp_total[lane] : elem_zero<S, NC>();
+                E winc = elem_warp_inclusive_scan(wt, lane);
+                E wex = elem_shfl_up(winc, 1);
+                if (lane == 0)
+                    wex = elem_zero<S, NC>();
+                if (lane < WARPS)
+                    s_warp_prefix[lane] = wex;
+                const E aggregate = elem_shfl(winc, 31);
+
+                E exclusive = elem_zero<S, NC>();
+                if (tp == 0)
+                {
+                    if (lane == 0)
+                    {
+                        inclusives[tile] = aggregate;
+                        st_release_u32(&flags[tile], 2u);
+                    }
+                }
+                else
+                {
+                    if (lane == 0)
+                    {
+                        aggregates[tile] = aggregate;
+                        st_release_u32(&flags[tile], 1u);
+                    }
+                    uint32_t remaining = tp;
+                    uint32_t pred = tile - 1;
+                    while (true)
+                    {
+                        const bool in_range = lane < remaining;
+                        uint32_t flag, inclusive_mask;
+                        while (true)
+                        {
+                            flag = in_range ? ld_acquire_u32(&flags[pred - lane]) : 2u;
+                            const uint32_t empty_mask = __ballot_sync(k_full_mask, flag == 0);
+                            inclusive_mask = __ballot_sync(k_full_mask, flag == 2);
+                            const uint32_t need =
+                                inclusive_mask ? ((2u << (__ffs(inclusive_mask) - 1)) - 1u) : k_full_mask;
+                            if ((empty_mask & need) == 0)
+                                break;
+                        }
+                        const uint32_t first = inclusive_mask ? uint32_t(__ffs(inclusive_mask) - 1) : 31u;
+                        E contrib = elem_zero<S, NC>();
+                        if (in_range && lane <= first)
+                            contrib = elem_ldcg(flag == 2 ? &inclusives[pred - lane] : &aggregates[pred - lane]);
+                        elem_add(exclusive, elem_warp_sum(contrib));
+                        if (inclusive_mask)
+                            break;
+                        pred -= 32;
+                        remaining -= 32;
+                    }
+                    if (lane == 0)
+                    {
+                        E inclusive = exclusive;
+                        elem_add(inclusive, aggregate);
+                        inclusives[tile] = inclusive;
+                        st_release_u32(&flags[tile], 2u);
+                    }
+                }
+                if (lane == 0)
+                    s_tile_prefix = exclusive;
+            }
+            __syncthreads();
+
+            E prefix = s_tile_prefix;
+            elem_add(prefix, s_warp_prefix[warp]);
+#pragma unroll
+            for (int j = 0; j < IPT; j++)
+            {
+                uint32_t idx = my_off + j * 32;
+                E b = prefix;
+                elem_add(b, ex[j]);
+                if (idx < valid)
+                    data[base + idx] = b;
+            }
+        }
+
+        // ------------------------------------------------------------------------------------ host side
+        struct ScanPlan
+        {
+            uint32_t tile;           // elements per tile
+            uint32_t tiles_per_part; // ceil(count / tile)
+            uint64_t total_tiles;
+            int variant;             // 0 = large tile, 1 = small tile
+        };
+
+        constexpr int k_big_threads = 256, k_big_vpt = 4;     // 4096-element tiles (16 KiB in, 16 KiB out)
+        constexpr int k_small_threads = 64, k_small_vpt = 2;  // 512-element tiles for short segments
+        constexpr int k_wide_threads = 256, k_wide_ipt = 4;   // 1024-element tiles
+        constexpr int k_wide_small_threads = 64, k_wide_small_ipt = 2;
+
+        ScanPlan make_plan(size_t count, size_t num_partitions, bool wide)
+        {
+            ScanPlan p;
+            const uint32_t big = wide ? k_wide_threads * k_wide_ipt : k_big_threads * k_big_vpt * 4;
+            const uint32_t small = wide ? k_wide_small_threads * k_wide_small_ipt : k_small_threads * k_small_vpt * 4;
+            // short segments: a big tile would be mostly padding
+            p.variant = (num_partitions > 1 && count <= big / 2) ? 1 : 0;
+            p.tile = p.variant ? small : big;
+            p.tiles_per_part = uint32_t((count + p.tile - 1) / p.tile);
+            p.total_tiles = uint64_t(p.tiles_per_part) * num_partitions;
+            return p;
+        }
+
+        size_t state_bytes(const ScanPlan& p, size_t elem_size)
+        {
+            if (elem_size == 4)
+                return align_up(p.total_tiles * sizeof(uint64_t), k_tmp_align);
+            return align_up(p.total_tiles * sizeof(uint32_t), k_tmp_align) +
+                   2 * align_up(p.total_tiles * elem_size, k_tmp_align);
+        }
+
+        template<typename T>
+        int launch_b32(void* d_data, size_t count, const ScanPlan& p, void* d_tmp, cudaStream_t s)
+        {
+            uint32_t* ticket = static_cast<uint32_t*>(d_tmp);
+            uint64_t* state = reinterpret_cast<uint64_t*>(static_cast<char*>(d_tmp) + k_tmp_align);
+            GLU_CUDA_TRY(cudaMemsetAsync(d_tmp, 0, k_tmp_align + state_bytes(p, 4), s));
+            if (p.variant == 0)
+                scan_b32_kernel<T, k_big_threads, k_big_vpt><<<unsigned(p.total_tiles), k_big_threads, 0, s>>>(
+                    static_cast<T*>(d_data), count, p.tiles_per_part, ticket, state);
+            else
+                scan_b32_kernel<T, k_small_threads, k_small_vpt><<<unsigned(p.total_tiles), k_small_threads, 0, s>>>(
+                    static_cast<T*>(d_data), count, p.tiles_per_part, ticket, state);
+            GLU_LAUNCH_CHECK();
+            return GLU_SUCCESS;
+        }
+
+        template<typename S, int NC>
+        int launch_wide(void* d_data, size_t count, const ScanPlan& p, void* d_tmp, cudaStream_t s)
+        {
+            using E = Elem<S, NC>;
+            char* base = static_cast<char*>(d_tmp);
+            uint32_t* ticket = reinterpret_cast<uint32_t*>(base);
+            uint32_t* flags = reinterpret_cast<uint32_t*>(base + k_tmp_align);
+            size_t flag_bytes = align_up(p.total_tiles * sizeof(uint32_t), k_tmp_align);
+            size_t val_bytes = align_up(p.total_tiles * sizeof(E), k_tmp_align);
+            E* aggregates = reinterpret_cast<E*>(base + k_tmp_align + flag_bytes);
+            E* inclusives = reinterpret_cast<E*>(base + k_tmp_align + flag_bytes + val_bytes);
+            GLU_CUDA_TRY(cudaMemsetAsync(d_tmp, 0, k_tmp_align + flag_bytes, s));
+            if (p.variant == 0)
+                scan_wide_kernel<S, NC, k_wide_threads, k_wide_ipt><<<unsigned(p.total_tiles), k_wide_threads, 0, s>>>(
+                    static_cast<E*>(d_data), count, p.tiles_per_part, ticket, flags, aggregates, inclusives);
+            else
+                scan_wide_kernel<S, NC, k_wide_small_threads, k_wide_small_ipt>
+                    <<<unsigned(p.total_tiles), k_wide_small_threads, 0, s>>>(
+                        static_cast<E*>(d_data), count, p.tiles_per_part, ticket, flags, aggregates, inclusives);
+            GLU_LAUNCH_CHECK();
+            return GLU_SUCCESS;
+        }
+    } // namespace
+} // namespace glu_b200
+
+using namespace glu_b200;
+
+extern "C" size_t glu_scan_exclusive_tmp_bytes(size_t count, size_t num_partitions, int data_type)
+{
+    DataTypeInfo info;
+    if (!data_type_info(data_type, &info) || count == 0 || num_partitions == 0)
+        return 0;
+    size_t esz = info.scalar_size * info.ncomp;
+    ScanPlan p = make_plan(count, num_partitions, esz != 4);
+    return k_tmp_align + state_bytes(p, esz);
+}
+
+extern "C" int glu_scan_exclusive(void* d_data, size_t count, size_t num_partitions, int data_type, void* d_tmp,
+                                  size_t tmp_bytes, glu_stream_t stream)
+{
+    DataTypeInfo info;
+    if (!data_type_info(data_type, &info))
+        return GLU_ERROR_INVALID_DATA_TYPE;
+    if (!d_data || count == 0 || num_partitions == 0) // glu/BlellochScan.hpp:132-135
+        return GLU_ERROR_INVALID_ARGUMENT;
+    const size_t esz = info.scalar_size * info.ncomp;
+    if (reinterpret_cast<uintptr_t>(d_data) % esz != 0)
+        return GLU_ERROR_MISALIGNED;
+    if (count > (size_t(1) << 40) / esz / num_partitions)
+        return GLU_ERROR_COUNT_TOO_LARGE;
+    ScanPlan p = make_plan(count, num_partitions, esz != 4);
+    if (p.total_tiles >= (uint64_t(1) << 31))
+        return GLU_ERROR_COUNT_TOO_LARGE;
+    if (!d_tmp || tmp_bytes < k_tmp_align + state_bytes(p, esz))
+        return GLU_ERROR_TMP_TOO_SMALL;
+    if (reinterpret_cast<uintptr_t>(d_tmp) % k_tmp_align != 0)
+        return GLU_ERROR_MISALIGNED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (data_type)
+    {
+    case GLU_DATA_TYPE_UINT:
+    case GLU_DATA_TYPE_INT: return launch_b32<uint32_t>(d_data, count, p, d_tmp, s);
+    case GLU_DATA_TYPE_FLOAT: return launch_b32<float>(d_data, count, p, d_tmp, s);
+    case GLU_DATA_TYPE_DOUBLE: return launch_wide<double, 1>(d_data, count, p, d_tmp, s);
+    case GLU_DATA_TYPE_VEC2: return launch_wide<float, 2>(d_data, count, p, d_tmp, s);
+    case GLU_DATA_TYPE_VEC4: return launch_wide<float, 4>(d_data, count, p, d_tmp, s);
+    case GLU_DATA_TYPE_DVEC2: return launch_wide<double, 2>(d_data, count, p, d_tmp, s);
+    case GLU_DATA_TYPE_DVEC4: return launch_wide<double, 4>(d_data, count, p, d_tmp, s);
+    case GLU_DATA_TYPE_UVEC2:
+    case GLU_DATA_TYPE_IVEC2: return launch_wide<uint32_t, 2>(d_data, count, p, d_tmp, s);
+    default: return launch_wide<uint32_t, 4>(d_data, count, p, d_tmp, s);
+    }
+}

@@ -1,0 +1,162 @@
+/* glu_b200.h — C ABI of the B200-native replacement for loryruta/gl-radix-sort's hot path.
+ *
+ * The reference ("GLU") is a header-only C++17/OpenGL library; its hot path is three classes whose
+ * operator() takes GL shader-storage-buffer handles:
+ *     glu::Reduce(DataType, ReduceOperator)   void operator()(GLuint buffer, size_t count)
+ *                                                              glu/Reduce.hpp:62,111
+ *     glu::BlellochScan(DataType)             void operator()(GLuint buffer, size_t count, size_t num_partitions = 1)
+ *                                                              glu/BlellochScan.hpp:91,130
+ *     glu::RadixSort()                        void prepare_internal_buffers(size_t count)
+ *                                             void operator()(GLuint key_buffer, GLuint val_buffer, size_t count,
+ *                                                             size_t num_steps = 0)
+ *                                                              glu/RadixSort.hpp:205,237,273
+ * There is no FFI layer in the reference; this header is what one would bind.  The only change of
+ * meaning is that a GLuint SSBO handle becomes a CUDA device pointer, and the scratch the reference
+ * classes own (glu/RadixSort.hpp:193-200) becomes caller-provided temporary storage sized by the
+ * matching *_tmp_bytes query.  include/glu/{Reduce,BlellochScan,RadixSort}.hpp re-create the classes
+ * on top of these entry points (same names, arguments and print-and-exit error behaviour);
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every function returns a glu_status (0 = success); nothing here prints or exits;
+ *  - all hot-path calls only ENQUEUE work on `stream` (a cudaStream_t; NULL = default stream) of the
+ *    current CUDA device and return without synchronising — like the reference's glDispatchCompute +
+ *    glMemoryBarrier sequences (glu/Reduce.hpp:131-133);
+ *  - results are produced IN PLACE in the caller's device buffers, as in the reference;
+ *  - d_tmp must be 256-byte aligned (any cudaMalloc pointer) and at least *_tmp_bytes large; its
+ *    contents are undefined before and after a call;
+ *  - no CPU fallback exists: without a CUDA device every compute call returns GLU_ERROR_CUDA.
+ */
+#ifndef GLU_B200_H
+#define GLU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define GLU_API
+#else
+#define GLU_API __attribute__((visibility("default")))
+#endif
+
+typedef void* glu_stream_t; /* cudaStream_t */
+typedef void* glu_event_t;  /* cudaEvent_t  */
+
+typedef enum glu_status
+{
+    GLU_SUCCESS = 0,
+    GLU_ERROR_INVALID_ARGUMENT = 1,  /* null buffer, count == 0 where the reference rejects it, ... */
+    GLU_ERROR_INVALID_DATA_TYPE = 2, /* glu/data_types.hpp:40 "Invalid data type"                   */
+    GLU_ERROR_INVALID_OPERATOR = 3,  /* glu/Reduce.hpp:93 "Invalid reduction operator"              */
+    GLU_ERROR_TMP_TOO_SMALL = 4,
+    GLU_ERROR_MISALIGNED = 5,        /* buffer not aligned to its scalar type / tmp not 256 B aligned */
+    GLU_ERROR_COUNT_TOO_LARGE = 6,   /* see the per-function limits below                            */
+    GLU_ERROR_CUDA = 7               /* a CUDA runtime call failed; see glu_last_cuda_error()        */
+} glu_status;
+
+/* glu/data_types.hpp:8-22 — same names, same values */
+typedef enum glu_data_type
+{
+    GLU_DATA_TYPE_FLOAT = 0,
+    GLU_DATA_TYPE_DOUBLE,
+    GLU_DATA_TYPE_INT,
+    GLU_DATA_TYPE_UINT,
+    GLU_DATA_TYPE_VEC2,
+    GLU_DATA_TYPE_VEC4,
+    GLU_DATA_TYPE_DVEC2,
+    GLU_DATA_TYPE_DVEC4,
+    GLU_DATA_TYPE_UVEC2,
+    GLU_DATA_TYPE_UVEC4,
+    GLU_DATA_TYPE_IVEC2,
+    GLU_DATA_TYPE_IVEC4
+} glu_data_type;
+
+/* glu/Reduce.hpp:42-48 */
+typedef enum glu_reduce_operator
+{
+    GLU_REDUCE_OPERATOR_SUM = 0,
+    GLU_REDUCE_OPERATOR_MUL,
+    GLU_REDUCE_OPERATOR_MIN,
+    GLU_REDUCE_OPERATOR_MAX
+} glu_reduce_operator;
+
+GLU_API int glu_version(void);
+GLU_API const char* glu_status_string(int status);
+/* cudaGetErrorString of the CUDA error behind the calling thread's last GLU_ERROR_CUDA */
+GLU_API const char* glu_last_cuda_error(void);
+/* size in bytes of one element of `data_type` (std430 array stride: 4/8/16/32), 0 if invalid */
+GLU_API size_t glu_data_type_size(int data_type);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+GLU_API uint64_t glu_kernel_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------- hot path */
+
+/* Replaces glu::Reduce::operator() (glu/Reduce.hpp:111-135).
+ * Folds d_data[0..count) with `op` (component-wise for vector types) and leaves the result in
+ * element 0.  Elements 1..count-1 are left untouched (the reference clobbers some of them with
+ * partials; callers can rely on element 0 only, in both).  count == 1 is a no-op, count == 0 is
+ * GLU_ERROR_INVALID_ARGUMENT (glu/Reduce.hpp:114).  Integer types wrap mod 2^32; floating types are
+ * reduced in a fixed order (deterministic run to run). */
+GLU_API size_t glu_reduce_tmp_bytes(size_t count, int data_type);
+GLU_API int glu_reduce(void* d_data, size_t count, int data_type, int op, void* d_tmp, size_t tmp_bytes,
+                       glu_stream_t stream);
+
+/* Replaces glu::BlellochScan::operator() (glu/BlellochScan.hpp:130-139).
+ * In-place exclusive prefix sum (operator +, identity 0) over each of `num_partitions` adjacent
+ * segments of `count` elements.  Unlike the reference (glu/BlellochScan.hpp:134) `count` need not be
+ * a power of two; on powers of two the results are identical.  count == 0 or num_partitions == 0 is
+ * GLU_ERROR_INVALID_ARGUMENT.  count * num_partitions must be < 2^40 / element size. */
+GLU_API size_t glu_scan_exclusive_tmp_bytes(size_t count, size_t num_partitions, int data_type);
+GLU_API int glu_scan_exclusive(void* d_data, size_t count, size_t num_partitions, int data_type, void* d_tmp,
+                               size_t tmp_bytes, glu_stream_t stream);
+
+/* Replaces glu::RadixSort::operator() (glu/RadixSort.hpp:273-334).
+ * Stable ascending sort of (key, value) uint32 pairs by key, in place in d_keys / d_vals.
+ * num_steps keeps the reference's meaning (number of 4-bit steps: only the low 4*num_steps key bits
+ * take part; 0 or >= 8 = all 32 bits).  Deviation: the result always lands in d_keys / d_vals (the
+ * reference leaves an odd-num_steps result in its internal scratch).  count <= 1 is a no-op
+ * (glu/RadixSort.hpp:278).  count must be <= 2^30. */
+GLU_API size_t glu_radix_sort_u32kv_tmp_bytes(size_t count);
+GLU_API int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t count, size_t num_steps, void* d_tmp,
+                                 size_t tmp_bytes, glu_stream_t stream);
+
+/* ------------------------------------------------------------------------ host-buffer entry points (e2e)
+ * Same semantics on HOST arrays: upload -> hot path -> download, synchronous.  These are what the
+ * reference's test-suite does around every call with ShaderStorageBuffer(data) ... get_data<T>()
+ * (glu/gl_utils.hpp:157-171,226-235; test/radix_sort_tests.cpp:100-106). */
+GLU_API int glu_reduce_host(void* h_data, size_t count, int data_type, int op);
+GLU_API int glu_scan_exclusive_host(void* h_data, size_t count, size_t num_partitions, int data_type);
+GLU_API int glu_radix_sort_u32kv_host(uint32_t* h_keys, uint32_t* h_vals, size_t count, size_t num_steps);
+
+/* ------------------------------------------------------- device plumbing for the C++ classes and test runner
+ * (the ShaderStorageBuffer / measure_gl_elapsed_time roles, glu/gl_utils.hpp:146-265) */
+GLU_API int glu_device_count(int* count);
+GLU_API int glu_set_device(int device);
+GLU_API int glu_device_info(int device, char* name, size_t name_cap, int* sm_count, int* cc_major, int* cc_minor,
+                            size_t* total_mem_bytes, int* warp_size);
+GLU_API int glu_malloc(void** d_ptr, size_t bytes);
+GLU_API int glu_free(void* d_ptr);
+GLU_API int glu_malloc_host(void** h_ptr, size_t bytes); /* pinned */
+GLU_API int glu_free_host(void* h_ptr);
+GLU_API int glu_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, glu_stream_t stream);
+GLU_API int glu_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, glu_stream_t stream);
+GLU_API int glu_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, glu_stream_t stream);
+GLU_API int glu_memset_u32(void* d_dst, uint32_t value, size_t count, glu_stream_t stream);
+GLU_API int glu_stream_create(glu_stream_t* stream);
+GLU_API int glu_stream_destroy(glu_stream_t stream);
+GLU_API int glu_stream_synchronize(glu_stream_t stream);
+GLU_API int glu_event_create(glu_event_t* event);
+GLU_API int glu_event_destroy(glu_event_t event);
+GLU_API int glu_event_record(glu_event_t event, glu_stream_t stream);
+GLU_API int glu_event_synchronize(glu_event_t event);
+GLU_API int glu_event_elapsed_ms(float* ms, glu_event_t start, glu_event_t stop);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* GLU_B200_H */

@@ -37,3 +37,35 @@ def oracle():
 
     _oracle.build()
     return _oracle
+
+
+@pytest.fixture(scope="session")
+def glu():
+    """The product package (ctypes over gl-radix-sort_b200/libglu_b200.so). Raises if the library is missing."""
+    import __graft_entry__ as entry
+
+    return entry.load_package()
+
+
+@pytest.fixture(scope="session")
+def cuda_device():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("this test is marked gpu and needs a CUDA device; no CPU fallback exists")
+    torch.cuda.set_device(0)
+    return torch.device("cuda", 0)
+
+
+def to_device(a: np.ndarray, device):
+    """Upload a numpy array (uint32 goes through an int32 view: torch has no native uint32 arithmetic)."""
+    import torch
+
+    if a.dtype == np.uint32:
+        return torch.from_numpy(a.view(np.int32).copy()).to(device)
+    return torch.from_numpy(a.copy()).to(device)
+
+
+def to_host(t, dtype) -> np.ndarray:
+    a = t.detach().cpu().numpy()
+    return a.view(dtype) if a.dtype != dtype else a

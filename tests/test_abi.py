@@ -1,0 +1,123 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports exactly what
+include/glu_b200.h declares, and rejects bad arguments with the documented status codes
+(no compute is launched here — every rejected call returns before touching CUDA)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "glu_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"GLU_API\s+[\w\s\*]*?\b(glu_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(glu):
+    declared = declared_symbols()
+    assert len(declared) >= 30
+    out = subprocess.run(["nm", "-D", "--defined-only", glu.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r"\bT (glu_\w+)", out))
+    assert set(declared) <= exported, sorted(set(declared) - exported)
+    # nothing undeclared leaks out of the library, and the Python binding covers the whole header
+    assert exported == set(declared), sorted(exported - set(declared))
+    assert set(glu.ABI) == set(declared)
+    for name in declared:
+        assert getattr(glu.lib, name) is not None
+
+
+def test_library_is_self_contained_and_has_sm100a_code(glu):
+    out = subprocess.run(["ldd", glu.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "not found" not in out
+    elf = subprocess.run(["cuobjdump", "-lelf", glu.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elf, elf
+
+
+def test_enums_and_sizes_match_reference(glu):
+    # glu/data_types.hpp:8-22 values 0..11; std430 strides
+    sizes = [4, 8, 4, 4, 8, 16, 16, 32, 8, 16, 8, 16]
+    for dt, sz in enumerate(sizes):
+        assert glu.lib.glu_data_type_size(dt) == sz
+    assert glu.lib.glu_data_type_size(12) == 0 and glu.lib.glu_data_type_size(-1) == 0
+    assert [int(x) for x in glu.ReduceOperator] == [0, 1, 2, 3]  # glu/Reduce.hpp:42-48
+    assert int(glu.DataType_Uint) == 3 and int(glu.DataType_IVec4) == 11
+    assert glu.lib.glu_version() >= 100
+    assert glu.lib.glu_status_string(0) == b"success"
+
+
+def test_argument_errors_are_status_codes_not_exits(glu):
+    L = glu.lib
+    fake = ctypes.c_void_p(0x1000)  # never dereferenced: all of these fail validation first
+    # glu/Reduce.hpp:113-114
+    assert L.glu_reduce(None, 10, 3, 0, fake, 1 << 20, None) == 1
+    assert L.glu_reduce(fake, 0, 3, 0, fake, 1 << 20, None) == 1
+    assert L.glu_reduce(fake, 10, 12, 0, fake, 1 << 20, None) == 2
+    assert L.glu_reduce(fake, 10, 3, 4, fake, 1 << 20, None) == 3  # glu/Reduce.hpp:93
+    assert L.glu_reduce(ctypes.c_void_p(0x1002), 10, 3, 0, fake, 1 << 20, None) == 5
+    assert L.glu_reduce(fake, 10, 3, 0, None, 0, None) == 4
+    assert L.glu_reduce(fake, 1, 3, 0, None, 0, None) == 0  # count == 1: nothing to do (glu/Reduce.hpp:124)
+    # glu/BlellochScan.hpp:132-135
+    assert L.glu_scan_exclusive(None, 8, 1, 3, fake, 1 << 20, None) == 1
+    assert L.glu_scan_exclusive(fake, 0, 1, 3, fake, 1 << 20, None) == 1
+    assert L.glu_scan_exclusive(fake, 8, 0, 3, fake, 1 << 20, None) == 1
+    assert L.glu_scan_exclusive(fake, 8, 1, 99, fake, 1 << 20, None) == 2
+    assert L.glu_scan_exclusive(fake, 8, 1, 3, None, 0, None) == 4
+    # glu/RadixSort.hpp:275-279
+    assert L.glu_radix_sort_u32kv(None, fake, 8, 0, fake, 1 << 20, None) == 1
+    assert L.glu_radix_sort_u32kv(fake, None, 8, 0, fake, 1 << 20, None) == 1
+    assert L.glu_radix_sort_u32kv(fake, fake, 1, 0, None, 0, None) == 0  # count <= 1 is a silent no-op
+    assert L.glu_radix_sort_u32kv(fake, fake, 0, 0, None, 0, None) == 0
+    assert L.glu_radix_sort_u32kv(fake, fake, 8, 0, None, 0, None) == 4
+    assert L.glu_radix_sort_u32kv(fake, fake, (1 << 30) + 1, 0, fake, 1 << 40, None) == 6
+
+
+def test_tmp_size_queries(glu):
+    L = glu.lib
+    assert L.glu_reduce_tmp_bytes(1 << 28, 3) >= 256
+    assert L.glu_reduce_tmp_bytes(10, 99) == 0
+    assert L.glu_scan_exclusive_tmp_bytes(1 << 28, 1, 3) >= (1 << 28) // 4096 * 8
+    assert L.glu_scan_exclusive_tmp_bytes(0, 1, 3) == 0
+    n = 1 << 20
+    need = L.glu_radix_sort_u32kv_tmp_bytes(n)
+    assert 2 * 4 * n <= need <= 2 * 4 * n + (8 << 20)  # two scratch arrays + O(tiles) control words
+    assert L.glu_radix_sort_u32kv_tmp_bytes((1 << 30) + 1) == 0
+
+
+def test_python_mirror_validates_like_the_reference(glu):
+    with pytest.raises(glu.GluError):
+        glu.Reduce(99, glu.ReduceOperator_Sum)
+    with pytest.raises(glu.GluError):
+        glu.Reduce(glu.DataType_Uint, 7)
+    with pytest.raises(glu.GluError):
+        glu.BlellochScan(-1)
+    r = glu.Reduce(glu.DataType_Uint, glu.ReduceOperator_Sum)
+    with pytest.raises(glu.GluError):
+        r(0, 10)  # "Invalid buffer"
+    with pytest.raises(glu.GluError):
+        r(0x1000, 0)  # "Count must be greater than zero"
+    s = glu.RadixSort()
+    with pytest.raises(glu.GluError):
+        s(0, 0x1000, 10)
+    s(0x1000, 0x1000, 1)  # no-op, never touches the device
+
+
+def test_no_product_import_of_oracle(glu):
+    """The product must not route through the oracle (or any CPU fallback): no import / include / dlopen of
+    anything under oracle/, and the shared library neither links nor references it."""
+    bad = re.compile(r"^\s*(import|from)\s+oracle|#\s*include\s*[<\"][^>\"]*oracle|glu_oracle_\w+\s*\(|libglu_oracle|dlopen",
+                     re.M)
+    roots = [os.path.join(ROOT, "gl-radix-sort_b200"), os.path.join(ROOT, "include")]
+    for root in roots:
+        for dirpath, _, files in os.walk(root):
+            if os.path.basename(dirpath) == "build":
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert not bad.search(text), os.path.join(dirpath, f)
+    syms = subprocess.run(["nm", "-D", glu.LIB_PATH], capture_output=True, text=True).stdout
+    assert "glu_oracle" not in syms

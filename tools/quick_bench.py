@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Quick device-side timing of the three primitives (development aid; bench.py is the contract)."""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as entry  # noqa: E402
+
+p = argparse.ArgumentParser()
+p.add_argument("--log2n", type=int, default=28)
+p.add_argument("--reps", type=int, default=10)
+p.add_argument("--what", default="sort,scan,reduce")
+p.add_argument("--dist", default="uniform")
+args = p.parse_args()
+
+glu = entry.load_package()
+dev = torch.device("cuda", 0)
+n = 1 << args.log2n
+g = torch.Generator(device=dev).manual_seed(1)
+st = torch.cuda.current_stream().cuda_stream
+
+
+def timeit(fn, prep=None, reps=args.reps):
+    times = []
+    for i in range(reps + 3):
+        if prep:
+            prep()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            times.append(a.elapsed_time(b))
+    times.sort()
+    return times[len(times) // 2], times[0]
+
+
+if "sort" in args.what:
+    if args.dist == "uniform":
+        keys0 = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int32, device=dev, generator=g)
+    elif args.dist == "zero":
+        keys0 = torch.zeros(n, dtype=torch.int32, device=dev)
+    elif args.dist == "ent16":
+        keys0 = torch.randint(0, 1 << 16, (n,), dtype=torch.int32, device=dev, generator=g)
+    vals0 = torch.arange(n, dtype=torch.int32, device=dev)
+    keys, vals = keys0.clone(), vals0.clone()
+    sorter = glu.RadixSort()
+    sorter.prepare_internal_buffers(n)
+
+    def prep():
+        keys.copy_(keys0)
+        vals.copy_(vals0)
+
+    med, best = timeit(lambda: sorter(keys, vals, n), prep)
+    print(f"sort   n=2^{args.log2n} {args.dist}: median {med:.3f} ms  best {best:.3f} ms  "
+          f"{n / med / 1e6:.2f} Gpairs/s  {68 * n / med / 1e6:.0f} GB/s(68B/pair)  "
+          f"cfg={os.environ.get('GLU_SORT_CONFIG', 'auto')} rank={os.environ.get('GLU_SORT_RANK', '0')} "
+          f"tma={os.environ.get('GLU_SORT_TMA', '1')}")
+    k64 = keys.to(torch.int64) & 0xFFFFFFFF
+    assert bool((k64[1:] >= k64[:-1]).all()), "not sorted"
+    del k64
+
+if "scan" in args.what:
+    data0 = torch.randint(0, 100, (n,), dtype=torch.int32, device=dev, generator=g)
+    data = data0.clone()
+    scan = glu.BlellochScan(glu.DataType_Uint)
+    med, best = timeit(lambda: scan(data, n), lambda: data.copy_(data0))
+    print(f"scan   n=2^{args.log2n}: median {med:.3f} ms  best {best:.3f} ms  {8 * n / med / 1e6:.0f} GB/s")
+
+if "reduce" in args.what:
+    data0 = torch.randint(0, 100, (n,), dtype=torch.int32, device=dev, generator=g)
+    data = data0.clone()
+    red = glu.Reduce(glu.DataType_Uint, glu.ReduceOperator_Sum)
+    med, best = timeit(lambda: red(data, n), lambda: data.copy_(data0))
+    print(f"reduce n=2^{args.log2n}: median {med:.3f} ms  best {best:.3f} ms  {4 * n / med / 1e6:.0f} GB/s")
+    a = torch.empty(n, dtype=torch.int32, device=dev)
+    med, best = timeit(lambda: a.copy_(data0))
+    print(f"torch copy (read+write) n=2^{args.log2n}: median {med:.3f} ms  {8 * n / med / 1e6:.0f} GB/s")
