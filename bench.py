@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the glu hot path on B200 (contract: see the task prompt / DESIGN.md §measurement).
+
+Metric (BASELINE.json): Gpairs/s of RadixSort on 32-bit key + 32-bit value pairs.
+  N = 1 : one step = one stable sort of 2^28 uniform-random uint32 (key, value) pairs (BASELINE config 3),
+          inputs resident in HBM, K independent unsorted inputs (one per step; 2 GiB each, far larger than L2).
+  N > 1 : weak scaling, 2^28 pairs per GPU per step, MSD split + NVLink all-to-all + local sort
+          (gl-radix-sort_b200/distributed.py); value = pairs of all ranks / max-over-ranks device time.
+Extra keys on the JSON line: roofline (dominant kernel = onesweep pass, 16 B/pair per launch, CUDA events on
+the launch stream inside the timed region), cpu_baseline (std::stable_sort of the oracle on a bounded sample),
+e2e (same sort through the host-buffer C-ABI entry point, pinned host memory, H2D + D2H inside), clocks,
+gpu_launches, and the scan / reduce side metrics of BASELINE config 2.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--log2-pairs 28]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SORT_BYTES_PER_PAIR = 68  # 4 B histogram read + 4 passes x (8 B read + 8 B write)   
+PASS_BYTES_PER_PAIR = 16  # one onesweep launch: read key+value, write key+value
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--log2-pairs", type=int, default=28, help="pairs per GPU per step (log2)")
+    p.add_argument("--cpu-sample-log2", type=int, default=26)
+    p.add_argument("--no-side-metrics", action="store_true", help="skip scan/reduce/e2e/cpu legs (tuning runs)")
+    return p.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu_index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx = float(parts[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+
+def run_reference(args):
+    """The reference's own CPU path for this metric: the std::stable_sort of (key,value) pairs its test-suite
+    oracle prescribes (test/radix_sort_tests.cpp:20-51 strengthened per north_star; oracle/glu_oracle.cpp),
+    on all host threads (__gnu_parallel::stable_sort).  The reference's GPU path is GLSL on an OpenGL 4.6
+    context and cannot run on this box (no GL/X11), so oracle/_ref does not exist — kind = "port".
+    One step = one sort of a bounded 2^cpu_sample_log2-pair sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+
+    import oracle
+
+    oracle.build()
+    n = 1 << args.cpu_sample_log2
+    threads = oracle.max_threads()
+    keys = oracle.mt19937_u32(1, n)
+    vals = np.arange(n, dtype=np.uint32)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    budget_s = 150.0
+    t_begin = time.time()
+    for _ in range(min(warmup, 1)):
+        oracle.time_stable_sort_pairs(keys, vals, threads)
+    times = []
+    for _ in range(steps):
+        times.append(oracle.time_stable_sort_pairs(keys, vals, threads))
+        if time.time() - t_begin > budget_s:
+            break
+    total = sum(times)
+    value = n * len(times) / total / 1e9
+    line = {
+        "impl": "reference", "metric": "radix_sort_u32_key_value_throughput", "value": value, "unit": "Gpairs/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": min(warmup, 1), "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"std::stable_sort of (uint32 key, uint32 value) pairs on the host, each step a "
+                               f"2^{args.cpu_sample_log2}-pair uniform-random (mt19937) sample of the 2^28-pair sort"},
+        "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": threads, "kind": "port",
+                         "sample": f"2^{args.cpu_sample_log2} pairs per step, __gnu_parallel::stable_sort, "
+                                   f"{threads} threads"},
+        "e2e": {"value": value, "unit": "Gpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+
+def cpu_baseline(args):
+    import numpy as np
+
+    import oracle
+
+    oracle.build()
+    n = 1 << args.cpu_sample_log2
+    threads = oracle.max_threads()
+    keys = oracle.mt19937_u32(1, n)
+    vals = np.arange(n, dtype=np.uint32)
+    t = oracle.time_stable_sort_pairs(keys, vals, threads)
+    return {"value": n / t / 1e9, "unit": "Gpairs/s", "cores": threads, "kind": "port",
+            "sample": f"one __gnu_parallel::stable_sort of the first 2^{args.cpu_sample_log2} pairs "
+                      f"(mt19937 keys, index values), {threads} threads, {t:.2f} s"}
+
+
+def pinned_u32(glu, n):
+    """A pinned host uint32 array of n elements (cudaMallocHost through the C ABI)."""
+    import numpy as np
+
+    ptr = ctypes.c_void_p()
+    glu.check(glu.lib.glu_malloc_host(ctypes.byref(ptr), 4 * n), "glu_malloc_host")
+    buf = (ctypes.c_uint32 * n).from_address(ptr.value)
+    return np.frombuffer(buf, dtype=np.uint32), ptr
+
+
+def side_metrics(glu, torch, dev, n, peak):
+    """BASELINE config 2: Reduce(Uint, Sum) and BlellochScan(Uint) over 2^28 uint32, GB/s vs HBM."""
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(7)
+    data0 = torch.randint(0, 100, (n,), dtype=torch.int32, device=dev, generator=g)
+    data = data0.clone()
+    for name, op, kid, bytes_per_elem in (("scan", glu.BlellochScan(glu.DataType_Uint), glu.KERNEL_SCAN, 8),
+                                          ("reduce", glu.Reduce(glu.DataType_Uint, glu.ReduceOperator_Sum),
+                                           glu.KERNEL_REDUCE, 4)):
+        for _ in range(3):
+            data.copy_(data0)
+            op(data, n)
+        torch.cuda.synchronize()
+        glu.profile_collect(kid)
+        reps = 10
+        for _ in range(reps):
+            data.copy_(data0)  # also evicts the previous result from L2 (2 GiB of traffic > 126 MB L2)
+            op(data, n)
+        torch.cuda.synchronize()
+        ms, launches = glu.profile_collect(kid)
+        gbs = bytes_per_elem * n * launches / ms / 1e6
+        out[name] = {"n": n, "ms": ms / launches, "GB/s": gbs, "frac_of_hbm_peak": gbs / peak,
+                     "bytes_per_elem": bytes_per_elem}
+    return out
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+
+    glu = entry.load_package()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = 1 << args.log2_pairs
+    steps, warmup = args.steps, max(3, args.warmup)
+    peak, peak_src = measured_peaks()
+
+    # ---- inputs: one independent unsorted (keys, vals) pair per step, resident in HBM before timing starts
+    total_inputs = steps + warmup
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+    inputs = []
+    for _ in range(total_inputs):
+        k = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int32, device=dev, generator=gen)
+        v = torch.arange(n, dtype=torch.int32, device=dev)
+        inputs.append((k, v))
+
+    if world > 1:
+        dsort = entry.load_package().distributed.DistributedRadixSort(n)
+        step_fn = lambda k, v: dsort(k, v)  # noqa: E731
+        parallelism = f"msd-split x{world} (NVLink all-to-all) + local onesweep"
+    else:
+        sorter = glu.RadixSort()
+        sorter.prepare_internal_buffers(n)  # as the reference's benchmark does (test/radix_sort_tests.cpp:187)
+        step_fn = lambda k, v: sorter(k, v, n)  # noqa: E731
+        parallelism = "single GPU"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step_fn(*inputs[i])
+    barrier()
+    glu.profile_enable(True)
+    glu.profile_collect(glu.KERNEL_SORT_ONESWEEP)
+    glu.profile_collect(glu.KERNEL_SORT_HISTOGRAM)
+    launches0 = glu.kernel_launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(steps):
+        step_fn(*inputs[warmup + i])
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    gpu_launches = glu.kernel_launch_count() - launches0
+    sweep_ms, sweep_launches = glu.profile_collect(glu.KERNEL_SORT_ONESWEEP)
+    hist_ms, hist_launches = glu.profile_collect(glu.KERNEL_SORT_HISTOGRAM)
+    glu.profile_enable(False)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+
+    # sanity: the last timed step really sorted its input
+    k_sorted = inputs[warmup + steps - 1][0]
+    k64 = k_sorted[: 1 << 24].to(torch.int64) & 0xFFFFFFFF
+    assert bool((k64[1:] >= k64[:-1]).all()), "bench output is not sorted"
+    del k64
+
+    value = world * n * steps / (ms_total * 1e-3) / 1e9
+    # roofline of the dominant kernel (onesweep pass): algorithmic 16 B per pair per launch
+    per_launch_ms = sweep_ms / max(1, sweep_launches)
+    pairs_per_launch = n  # single GPU: every launch sweeps the whole array
+    achieved = PASS_BYTES_PER_PAIR * pairs_per_launch / (per_launch_ms * 1e-3) / 1e9 if sweep_launches else None
+    roofline = {"bound": "hbm", "kernel": "onesweep_kernel (one 8-bit digit pass)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": None,
+                "peak_source": peak_src, "launches": sweep_launches, "ms_per_launch": per_launch_ms,
+                "algorithmic_bytes_per_launch": PASS_BYTES_PER_PAIR * pairs_per_launch,
+                "kernel_share_of_step": sweep_ms / ms_total,
+                "histogram_ms_per_launch": hist_ms / max(1, hist_launches),
+                "whole_sort": {"bytes_per_pair": SORT_BYTES_PER_PAIR,
+                               "achieved_GB/s": SORT_BYTES_PER_PAIR * world * n * steps / (ms_total * 1e-3) / 1e9 / world,
+                               "frac": SORT_BYTES_PER_PAIR * n * steps / (ms_total * 1e-3) / 1e9 / peak}}
+    traffic_file = os.path.join(ROOT, "profiles", "onesweep_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+
+    line = {
+        "metric": "radix_sort_u32_key_value_throughput", "value": value, "unit": "Gpairs/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"RadixSort of 2^{args.log2_pairs} uniform-random uint32 key/value pairs per GPU "
+                               f"(BASELINE.json configs[2]), values = input index, one fresh unsorted input per step",
+                   "pairs_per_gpu": n, "parallelism": parallelism,
+                   "cache": "inputs (2 GiB per step) are larger than the 126 MB L2; no flush needed"},
+        "roofline": roofline, "clocks": clocks, "gpu_launches": int(gpu_launches),
+        "published_reference": {"value": 0.05345, "unit": "Gpairs/s", "hardware": "RTX 2060 SUPER (README.md:133)",
+                                "note": "different hardware; not used for vs_baseline"},
+    }
+
+    if rank == 0 and world == 1 and not args.no_side_metrics:
+        del inputs[1:]
+        torch.cuda.empty_cache()
+        # ---- e2e: the same sort through the host-buffer C-ABI call, pinned host memory, copies inside
+        hk, hk_ptr = pinned_u32(glu, n)
+        hv, hv_ptr = pinned_u32(glu, n)
+        src_k = inputs[0][0]
+        e2e_steps = min(steps, 5)
+        e2e_t = 0.0
+        for i in range(e2e_steps + 1):
+            hk[:] = np.random.default_rng(100 + i).integers(0, 1 << 32, size=n, dtype=np.uint32)
+            hv[:] = np.arange(n, dtype=np.uint32)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            glu.radix_sort_u32kv_host(hk, hv, n)
+            t1 = time.perf_counter()
+            if i > 0:  # first call warms the allocation path
+                e2e_t += t1 - t0
+        assert bool(np.all(hk[:-1][: 1 << 22] <= hk[1:][: 1 << 22]))
+        line["e2e"] = {"value": n * e2e_steps / e2e_t / 1e9, "unit": "Gpairs/s", "h2d_bytes_per_step": 8 * n,
+                       "d2h_bytes_per_step": 8 * n, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_t / e2e_steps,
+                       "api": "glu_radix_sort_u32kv_host (pinned host buffers; H2D + sort + D2H inside the call)"}
+        glu.lib.glu_free_host(hk_ptr)
+        glu.lib.glu_free_host(hv_ptr)
+        del src_k
+        glu.profile_enable(True)
+        line["side_metrics"] = side_metrics(glu, torch, dev, 1 << 28, peak)
+        glu.profile_enable(False)
+        line["cpu_baseline"] = cpu_baseline(args)
+    elif rank == 0:
+        line["e2e"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

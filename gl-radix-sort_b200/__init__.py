@@ -43,6 +43,8 @@ ABI = {
     "glu_last_cuda_error": (ctypes.c_char_p, []),
     "glu_data_type_size": (_sz, [_int]),
     "glu_kernel_launch_count": (ctypes.c_uint64, []),
+    "glu_profile_enable": (_int, [_int]),
+    "glu_profile_collect": (_int, [_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
     "glu_reduce_tmp_bytes": (_sz, [_sz, _int]),
     "glu_reduce": (_int, [_vp, _sz, _int, _int, _vp, _sz, _vp]),
     "glu_scan_exclusive_tmp_bytes": (_sz, [_sz, _sz, _int]),
@@ -131,6 +133,21 @@ def check(status: int, where: str) -> None:
 
 def kernel_launch_count() -> int:
     return int(_lib.glu_kernel_launch_count())
+
+
+KERNEL_REDUCE, KERNEL_SCAN, KERNEL_SORT_HISTOGRAM, KERNEL_SORT_ONESWEEP = 0, 1, 2, 3
+
+
+def profile_enable(on: bool) -> None:
+    """Bracket every hot-path kernel launch with CUDA events on its stream (bench.py's roofline)."""
+    check(_lib.glu_profile_enable(1 if on else 0), "profile_enable")
+
+
+def profile_collect(kernel_id: int):
+    """(total_ms, launches) of one kernel family since the last collect."""
+    ms, n = ctypes.c_double(0), ctypes.c_uint64(0)
+    check(_lib.glu_profile_collect(kernel_id, ctypes.byref(ms), ctypes.byref(n)), "profile_collect")
+    return float(ms.value), int(n.value)
 
 
 def data_type_size(data_type: int) -> int:

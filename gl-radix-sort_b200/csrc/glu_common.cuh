@@ -38,6 +38,28 @@ namespace glu_b200
         GLU_CUDA_TRY(cudaGetLastError());                                                                              \
     } while (0)
 
+    // Optional event bracketing of a launch (glu_profile_enable): construct before <<<>>>, destroyed after.
+    extern std::atomic<int> g_profile_on;
+    void profile_begin(int kernel_id, cudaStream_t s);
+    void profile_end(int kernel_id, cudaStream_t s);
+    struct ScopedKernelProfile
+    {
+        int id;
+        cudaStream_t s;
+        bool on;
+        ScopedKernelProfile(int kernel_id, cudaStream_t stream)
+            : id(kernel_id), s(stream), on(g_profile_on.load(std::memory_order_relaxed) != 0)
+        {
+            if (on)
+                profile_begin(id, s);
+        }
+        ~ScopedKernelProfile()
+        {
+            if (on)
+                profile_end(id, s);
+        }
+    };
+
     constexpr size_t k_tmp_align = 256;
     inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

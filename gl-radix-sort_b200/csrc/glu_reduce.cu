@@ -306,6 +306,7 @@ namespace glu_b200
             S* partials = reinterpret_cast<S*>(reinterpret_cast<char*>(d_tmp) + k_tmp_align);
             if (grid > 1)
                 GLU_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), stream));
+            ScopedKernelProfile prof(GLU_KERNEL_REDUCE, stream);
             reduce_kernel<S, NCOMP, OP, k_threads, k_unroll>
                 <<<grid, k_threads, 0, stream>>>(reinterpret_cast<S*>(d_data), n_scalars, head, n_units, partials, ticket);
             GLU_LAUNCH_CHECK();

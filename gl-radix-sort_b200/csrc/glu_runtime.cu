@@ -3,6 +3,8 @@
 // glu/gl_utils.hpp:146-265) and the host-buffer entry points used for end-to-end measurements.
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "glu_common.cuh"
 
@@ -10,6 +12,51 @@ namespace glu_b200
 {
     std::atomic<uint64_t> g_kernel_launches{0};
     thread_local cudaError_t t_last_cuda_error = cudaSuccess;
+
+    std::atomic<int> g_profile_on{0};
+    namespace
+    {
+        struct ProfileSpan
+        {
+            int id;
+            cudaEvent_t start, stop;
+        };
+        std::mutex g_profile_mutex;
+        std::vector<ProfileSpan> g_profile_spans;
+        std::vector<cudaEvent_t> g_profile_free_events;
+
+        cudaEvent_t profile_event()
+        {
+            if (!g_profile_free_events.empty())
+            {
+                cudaEvent_t e = g_profile_free_events.back();
+                g_profile_free_events.pop_back();
+                return e;
+            }
+            cudaEvent_t e = nullptr;
+            cudaEventCreate(&e);
+            return e;
+        }
+    } // namespace
+
+    void profile_begin(int kernel_id, cudaStream_t s)
+    {
+        std::lock_guard<std::mutex> lock(g_profile_mutex);
+        ProfileSpan span{kernel_id, profile_event(), profile_event()};
+        cudaEventRecord(span.start, s);
+        g_profile_spans.push_back(span);
+    }
+
+    void profile_end(int kernel_id, cudaStream_t s)
+    {
+        std::lock_guard<std::mutex> lock(g_profile_mutex);
+        for (size_t i = g_profile_spans.size(); i-- > 0;)
+            if (g_profile_spans[i].id == kernel_id)
+            {
+                cudaEventRecord(g_profile_spans[i].stop, s);
+                break;
+            }
+    }
 
     int current_sm_count()
     {
@@ -49,14 +96,14 @@ namespace glu_b200
 
 using namespace glu_b200;
 
-namespace
+namespace glu_b200
 {
     __global__ void fill_u32_kernel(uint32_t* dst, uint32_t value, size_t count)
     {
         for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x)
             dst[i] = value;
     }
-} // namespace
+} // namespace glu_b200
 
 extern "C"
 {
@@ -89,6 +136,41 @@ extern "C"
     }
 
     uint64_t glu_kernel_launch_count(void) { return g_kernel_launches.load(std::memory_order_relaxed); }
+
+    int glu_profile_enable(int on)
+    {
+        g_profile_on.store(on ? 1 : 0, std::memory_order_relaxed);
+        return GLU_SUCCESS;
+    }
+
+    int glu_profile_collect(int kernel_id, double* total_ms, uint64_t* launches)
+    {
+        if (kernel_id < 0 || kernel_id >= GLU_KERNEL_COUNT_ || !total_ms || !launches)
+            return GLU_ERROR_INVALID_ARGUMENT;
+        std::lock_guard<std::mutex> lock(g_profile_mutex);
+        double ms_sum = 0;
+        uint64_t n = 0;
+        std::vector<ProfileSpan> keep;
+        for (const ProfileSpan& span : g_profile_spans)
+        {
+            if (span.id != kernel_id)
+            {
+                keep.push_back(span);
+                continue;
+            }
+            float ms = 0;
+            GLU_CUDA_TRY(cudaEventSynchronize(span.stop));
+            GLU_CUDA_TRY(cudaEventElapsedTime(&ms, span.start, span.stop));
+            ms_sum += ms;
+            n++;
+            g_profile_free_events.push_back(span.start);
+            g_profile_free_events.push_back(span.stop);
+        }
+        g_profile_spans.swap(keep);
+        *total_ms = ms_sum;
+        *launches = n;
+        return GLU_SUCCESS;
+    }
 
     // ------------------------------------------------------------------------------------------ plumbing
 
@@ -265,15 +347,42 @@ extern "C"
 
     namespace
     {
-        struct DeviceScratch // RAII for the synchronous host variants
+        // Grow-only device buffers reused by the synchronous host-buffer entry points, one set per
+        // device (the role of the ShaderStorageBuffer objects a caller of the reference keeps alive).
+        struct HostPathBuffers
         {
-            void* p = nullptr;
-            ~DeviceScratch()
-            {
-                if (p)
-                    cudaFree(p);
-            }
+            void* p[3] = {nullptr, nullptr, nullptr};
+            size_t cap[3] = {0, 0, 0};
         };
+        std::mutex g_host_path_mutex;
+        HostPathBuffers g_host_path[64];
+
+        int host_path_ensure(int slot, size_t bytes, void** out)
+        {
+            int dev = 0;
+            GLU_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev < 0 || dev >= 64)
+                return GLU_ERROR_INVALID_ARGUMENT;
+            HostPathBuffers& b = g_host_path[dev];
+            if (b.cap[slot] < bytes)
+            {
+                if (b.p[slot])
+                    GLU_CUDA_TRY(cudaFree(b.p[slot]));
+                b.p[slot] = nullptr;
+                b.cap[slot] = 0;
+                GLU_CUDA_TRY(cudaMalloc(&b.p[slot], bytes));
+                b.cap[slot] = bytes;
+            }
+            *out = b.p[slot];
+            return GLU_SUCCESS;
+        }
+#define GLU_TRY(expr)                                                                                                  \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        int rc__ = (expr);                                                                                             \
+        if (rc__ != GLU_SUCCESS)                                                                                       \
+            return rc__;                                                                                               \
+    } while (0)
     } // namespace
 
     int glu_reduce_host(void* h_data, size_t count, int data_type, int op)
@@ -283,15 +392,14 @@ extern "C"
             return GLU_ERROR_INVALID_DATA_TYPE;
         if (!h_data || count == 0)
             return GLU_ERROR_INVALID_ARGUMENT;
-        DeviceScratch data, tmp;
+        std::lock_guard<std::mutex> lock(g_host_path_mutex);
+        void *data = nullptr, *tmp = nullptr;
         size_t tmp_bytes = glu_reduce_tmp_bytes(count, data_type);
-        GLU_CUDA_TRY(cudaMalloc(&data.p, count * esz));
-        GLU_CUDA_TRY(cudaMalloc(&tmp.p, tmp_bytes));
-        GLU_CUDA_TRY(cudaMemcpyAsync(data.p, h_data, count * esz, cudaMemcpyHostToDevice, 0));
-        int rc = glu_reduce(data.p, count, data_type, op, tmp.p, tmp_bytes, nullptr);
-        if (rc != GLU_SUCCESS)
-            return rc;
-        GLU_CUDA_TRY(cudaMemcpyAsync(h_data, data.p, esz, cudaMemcpyDeviceToHost, 0));
+        GLU_TRY(host_path_ensure(0, count * esz, &data));
+        GLU_TRY(host_path_ensure(2, tmp_bytes, &tmp));
+        GLU_CUDA_TRY(cudaMemcpyAsync(data, h_data, count * esz, cudaMemcpyHostToDevice, 0));
+        GLU_TRY(glu_reduce(data, count, data_type, op, tmp, tmp_bytes, nullptr));
+        GLU_CUDA_TRY(cudaMemcpyAsync(h_data, data, esz, cudaMemcpyDeviceToHost, 0));
         GLU_CUDA_TRY(cudaStreamSynchronize(0));
         return GLU_SUCCESS;
     }
@@ -303,16 +411,15 @@ extern "C"
             return GLU_ERROR_INVALID_DATA_TYPE;
         if (!h_data || count == 0 || num_partitions == 0)
             return GLU_ERROR_INVALID_ARGUMENT;
-        DeviceScratch data, tmp;
+        std::lock_guard<std::mutex> lock(g_host_path_mutex);
+        void *data = nullptr, *tmp = nullptr;
         size_t bytes = count * num_partitions * esz;
         size_t tmp_bytes = glu_scan_exclusive_tmp_bytes(count, num_partitions, data_type);
-        GLU_CUDA_TRY(cudaMalloc(&data.p, bytes));
-        GLU_CUDA_TRY(cudaMalloc(&tmp.p, tmp_bytes));
-        GLU_CUDA_TRY(cudaMemcpyAsync(data.p, h_data, bytes, cudaMemcpyHostToDevice, 0));
-        int rc = glu_scan_exclusive(data.p, count, num_partitions, data_type, tmp.p, tmp_bytes, nullptr);
-        if (rc != GLU_SUCCESS)
-            return rc;
-        GLU_CUDA_TRY(cudaMemcpyAsync(h_data, data.p, bytes, cudaMemcpyDeviceToHost, 0));
+        GLU_TRY(host_path_ensure(0, bytes, &data));
+        GLU_TRY(host_path_ensure(2, tmp_bytes, &tmp));
+        GLU_CUDA_TRY(cudaMemcpyAsync(data, h_data, bytes, cudaMemcpyHostToDevice, 0));
+        GLU_TRY(glu_scan_exclusive(data, count, num_partitions, data_type, tmp, tmp_bytes, nullptr));
+        GLU_CUDA_TRY(cudaMemcpyAsync(h_data, data, bytes, cudaMemcpyDeviceToHost, 0));
         GLU_CUDA_TRY(cudaStreamSynchronize(0));
         return GLU_SUCCESS;
     }
@@ -323,22 +430,21 @@ extern "C"
             return GLU_ERROR_INVALID_ARGUMENT;
         if (count <= 1)
             return GLU_SUCCESS;
-        DeviceScratch keys, vals, tmp;
         size_t bytes = count * sizeof(uint32_t);
         size_t tmp_bytes = glu_radix_sort_u32kv_tmp_bytes(count);
         if (tmp_bytes == 0)
             return GLU_ERROR_COUNT_TOO_LARGE;
-        GLU_CUDA_TRY(cudaMalloc(&keys.p, bytes));
-        GLU_CUDA_TRY(cudaMalloc(&vals.p, bytes));
-        GLU_CUDA_TRY(cudaMalloc(&tmp.p, tmp_bytes));
-        GLU_CUDA_TRY(cudaMemcpyAsync(keys.p, h_keys, bytes, cudaMemcpyHostToDevice, 0));
-        GLU_CUDA_TRY(cudaMemcpyAsync(vals.p, h_vals, bytes, cudaMemcpyHostToDevice, 0));
-        int rc = glu_radix_sort_u32kv(static_cast<uint32_t*>(keys.p), static_cast<uint32_t*>(vals.p), count, num_steps,
-                                      tmp.p, tmp_bytes, nullptr);
-        if (rc != GLU_SUCCESS)
-            return rc;
-        GLU_CUDA_TRY(cudaMemcpyAsync(h_keys, keys.p, bytes, cudaMemcpyDeviceToHost, 0));
-        GLU_CUDA_TRY(cudaMemcpyAsync(h_vals, vals.p, bytes, cudaMemcpyDeviceToHost, 0));
+        std::lock_guard<std::mutex> lock(g_host_path_mutex);
+        void *keys = nullptr, *vals = nullptr, *tmp = nullptr;
+        GLU_TRY(host_path_ensure(0, bytes, &keys));
+        GLU_TRY(host_path_ensure(1, bytes, &vals));
+        GLU_TRY(host_path_ensure(2, tmp_bytes, &tmp));
+        GLU_CUDA_TRY(cudaMemcpyAsync(keys, h_keys, bytes, cudaMemcpyHostToDevice, 0));
+        GLU_CUDA_TRY(cudaMemcpyAsync(vals, h_vals, bytes, cudaMemcpyHostToDevice, 0));
+        GLU_TRY(glu_radix_sort_u32kv(static_cast<uint32_t*>(keys), static_cast<uint32_t*>(vals), count, num_steps, tmp,
+                                     tmp_bytes, nullptr));
+        GLU_CUDA_TRY(cudaMemcpyAsync(h_keys, keys, bytes, cudaMemcpyDeviceToHost, 0));
+        GLU_CUDA_TRY(cudaMemcpyAsync(h_vals, vals, bytes, cudaMemcpyDeviceToHost, 0));
         GLU_CUDA_TRY(cudaStreamSynchronize(0));
         return GLU_SUCCESS;
     }

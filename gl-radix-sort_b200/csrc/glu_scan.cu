@@ -493,6 +493,7 @@ namespace glu_b200
             uint32_t* ticket = static_cast<uint32_t*>(d_tmp);
             uint64_t* state = reinterpret_cast<uint64_t*>(static_cast<char*>(d_tmp) + k_tmp_align);
             GLU_CUDA_TRY(cudaMemsetAsync(d_tmp, 0, k_tmp_align + state_bytes(p, 4), s));
+            ScopedKernelProfile prof(GLU_KERNEL_SCAN, s);
             if (p.variant == 0)
                 scan_b32_kernel<T, k_big_threads, k_big_vpt><<<unsigned(p.total_tiles), k_big_threads, 0, s>>>(
                     static_cast<T*>(d_data), count, p.tiles_per_part, ticket, state);
@@ -515,6 +516,7 @@ namespace glu_b200
             E* aggregates = reinterpret_cast<E*>(base + k_tmp_align + flag_bytes);
             E* inclusives = reinterpret_cast<E*>(base + k_tmp_align + flag_bytes + val_bytes);
             GLU_CUDA_TRY(cudaMemsetAsync(d_tmp, 0, k_tmp_align + flag_bytes, s));
+            ScopedKernelProfile prof(GLU_KERNEL_SCAN, s);
             if (p.variant == 0)
                 scan_wide_kernel<S, NC, k_wide_threads, k_wide_ipt><<<unsigned(p.total_tiles), k_wide_threads, 0, s>>>(
                     static_cast<E*>(d_data), count, p.tiles_per_part, ticket, flags, aggregates, inclusives);

@@ -93,6 +93,21 @@ GLU_API size_t glu_data_type_size(int data_type);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 GLU_API uint64_t glu_kernel_launch_count(void);
 
+/* Per-kernel device timing for bench.py's roofline (the measure_gl_elapsed_time role, glu/gl_utils.hpp:249-265).
+ * While enabled, every kernel launch of the hot path is bracketed by a pair of CUDA events on its own
+ * stream.  glu_profile_collect() synchronises, sums the elapsed time and the launch count of one kernel
+ * family since the last collect, and clears them.  Off by default (no events, no overhead). */
+typedef enum glu_kernel_id
+{
+    GLU_KERNEL_REDUCE = 0,
+    GLU_KERNEL_SCAN = 1,
+    GLU_KERNEL_SORT_HISTOGRAM = 2,
+    GLU_KERNEL_SORT_ONESWEEP = 3,
+    GLU_KERNEL_COUNT_ = 4
+} glu_kernel_id;
+GLU_API int glu_profile_enable(int on);
+GLU_API int glu_profile_collect(int kernel_id, double* total_ms, uint64_t* launches);
+
 /* ---------------------------------------------------------------------------------------------- hot path */
 
 /* Replaces glu::Reduce::operator() (glu/Reduce.hpp:111-135).

@@ -160,7 +160,7 @@ def test_sort_without_tma_path_matches(glu, cuda_device, oracle):
         "ek, ev = oracle.stable_sort_pairs(k, v)\n"
         "assert np.array_equal(dk.cpu().numpy().view(np.uint32), ek) and np.array_equal(dv.cpu().numpy().view(np.uint32), ev)\n"
         "print('ok')\n")
-    for env_extra in ({"GLU_SORT_TMA": "0"}, {"GLU_SORT_RANK": "1"}, {"GLU_SORT_CONFIG": "0"}, {"GLU_SORT_CONFIG": "4"}):
+    for env_extra in ({"GLU_SORT_TMA": "0"}, {"GLU_SORT_RANK": "0"}, {"GLU_SORT_CONFIG": "0"}, {"GLU_SORT_CONFIG": "4"}):
         env = dict(os.environ, **env_extra)
         r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True)
         assert r.returncode == 0 and "ok" in r.stdout, (env_extra, r.stdout, r.stderr)
