@@ -34,11 +34,11 @@ PASS_BYTES_PER_PAIR = 16  # one onesweep launch: read key+value, write key+value
 def parse_args():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--log2-pairs", type=int, default=28, help="pairs per GPU per step (log2)")
-    p.add_argument("--cpu-sample-log2", type=int, default=26)
+    p.add_argument("--cpu-sample-log2", type=int, default=28)
     p.add_argument("--no-side-metrics", action="store_true", help="skip scan/reduce/e2e/cpu legs (tuning runs)")
     return p.parse_args()
 
@@ -66,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu_index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.gpu_index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:

@@ -32,6 +32,7 @@ namespace glu_b200
         constexpr uint32_t k_lb_inclusive = 2u << 30; // inclusive prefix over tiles 0..t published
         constexpr uint32_t k_lb_value_mask = (1u << 30) - 1u;
         constexpr size_t k_max_count = size_t(1) << 30;
+        constexpr int k_lb_unroll = 8; // look-back rows in flight per digit thread
 
         struct PassPlan
         {
@@ -61,38 +62,30 @@ namespace glu_b200
         constexpr int k_hist_threads = 512;
         constexpr int k_hist_unroll = 4;
         constexpr int k_hist_blocks_per_sm = 2;
-
-        // One key's contribution to the shared histogram of one digit place.  When at least a quarter of
-        // the warp shares lane 0's digit the warp aggregates equal digits (match.any) so that a
-        // constant or heavily skewed digit costs one atomic instead of a 32-way bank conflict.
-        __device__ __forceinline__ void hist_add(uint32_t* s_bins, uint32_t digit, bool ok)
-        {
-            const uint32_t d0 = __shfl_sync(k_full_mask, digit, 0);
-            const uint32_t same0 = __ballot_sync(k_full_mask, ok && digit == d0);
-            if (__popc(same0) >= 8)
-            {
-                const uint32_t peers = __match_any_sync(k_full_mask, ok ? digit : 0xffffffffu);
-                if (ok && (peers & lanemask_lt()) == 0)
-                    atomicAdd(&s_bins[digit], uint32_t(__popc(peers)));
-            }
-            else if (ok)
-                atomicAdd(&s_bins[digit], 1u);
-        }
+        constexpr int k_hist_copies = 8; // bank-interleaved private copies of every bin: lane l uses copy l & 7
 
         // hist: [k_max_passes][256] zero-initialised; on exit hist holds EXCLUSIVE digit offsets.
+        //
+        // Shared-memory atomics are the cost here (4 per key), so every bin has 8 copies laid out in
+        // consecutive banks: lanes of a warp only collide inside their own group of 4.  When at least
+        // half of a warp holds the same digit (constant or heavily skewed digit places) the warp
+        // switches to __match_any_sync aggregation: one atomic per distinct digit instead of a
+        // serialised same-address pile-up.
         __global__ void __launch_bounds__(k_hist_threads)
             histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t head, uint32_t n_units,
                              int num_passes, uint32_t key_mask, uint32_t* hist, uint32_t* ticket)
         {
-            __shared__ uint32_t s_hist[k_max_passes][k_radix];
+            __shared__ uint32_t s_hist[k_max_passes][k_radix][k_hist_copies];
             __shared__ uint32_t s_scan[k_hist_threads / 32];
             __shared__ bool s_is_last;
 
-            for (int i = threadIdx.x; i < k_max_passes * k_radix; i += k_hist_threads)
-                (&s_hist[0][0])[i] = 0;
+            for (int i = threadIdx.x; i < k_max_passes * k_radix * k_hist_copies; i += k_hist_threads)
+                (&s_hist[0][0][0])[i] = 0;
             __syncthreads();
 
             const unsigned lane = threadIdx.x & 31;
+            const unsigned copy = lane & (k_hist_copies - 1);
+            const uint32_t lt = lanemask_lt();
             const uint4* body = reinterpret_cast<const uint4*>(keys + head);
             const uint32_t stride = gridDim.x * k_hist_threads;
             // warp-uniform loop bounds: the match/ballot collectives need every lane of the warp
@@ -116,9 +109,31 @@ namespace glu_b200
                     const uint32_t kk[4] = {k[u].x & key_mask, k[u].y & key_mask, k[u].z & key_mask,
                                             k[u].w & key_mask};
                     for (int p = 0; p < num_passes; p++)
+                    {
+                        uint32_t d[4];
 #pragma unroll
                         for (int c = 0; c < 4; c++)
-                            hist_add(s_hist[p], (kk[c] >> (8 * p)) & 0xffu, ok[u]);
+                            d[c] = (kk[c] >> (8 * p)) & 0xffu;
+                        // skew probe on one of the four keys (cheap: 1 shuffle + 1 ballot per 4 atomics)
+                        const uint32_t d0 = __shfl_sync(k_full_mask, d[0], 0);
+                        const uint32_t same0 = __ballot_sync(k_full_mask, ok[u] && d[0] == d0);
+                        if (__popc(same0) >= 16)
+                        {
+#pragma unroll
+                            for (int c = 0; c < 4; c++)
+                            {
+                                const uint32_t peers = __match_any_sync(k_full_mask, ok[u] ? d[c] : 0xffffffffu);
+                                if (ok[u] && (peers & lt) == 0)
+                                    atomicAdd(&s_hist[p][d[c]][copy], uint32_t(__popc(peers)));
+                            }
+                        }
+                        else if (ok[u])
+                        {
+#pragma unroll
+                            for (int c = 0; c < 4; c++)
+                                atomicAdd(&s_hist[p][d[c]][copy], 1u);
+                        }
+                    }
                 }
             }
             // unaligned head and sub-vector tail (at most 3 keys each)
@@ -126,15 +141,19 @@ namespace glu_b200
             {
                 const uint32_t tail_begin = head + n_units * 4;
                 const uint32_t idx = lane < head ? lane : tail_begin + (lane - head);
-                const bool ok = idx < n && (lane < head || idx >= tail_begin) && lane < head + 3;
+                const bool ok = idx < n && lane < head + 3;
                 const uint32_t key = ok ? (keys[idx] & key_mask) : 0;
-                for (int p = 0; p < num_passes; p++)
-                    hist_add(s_hist[p], (key >> (8 * p)) & 0xffu, ok);
+                if (ok)
+                    for (int p = 0; p < num_passes; p++)
+                        atomicAdd(&s_hist[p][(key >> (8 * p)) & 0xffu][copy], 1u);
             }
             __syncthreads();
             for (int i = threadIdx.x; i < num_passes * k_radix; i += k_hist_threads)
             {
-                const uint32_t c = (&s_hist[0][0])[i];
+                uint32_t c = 0;
+#pragma unroll
+                for (int j = 0; j < k_hist_copies; j++)
+                    c += (&s_hist[0][0][0])[i * k_hist_copies + j];
                 if (c)
                     atomicAdd(&hist[i], c);
             }
@@ -380,16 +399,29 @@ namespace glu_b200
                 uint32_t exclusive = 0;
                 if (tile > 0)
                 {
-                    const uint32_t* p = lookback + size_t(tile - 1) * k_radix + tid;
-                    while (true)
+                    // k_lb_unroll predecessors are fetched per round trip (independent loads), then folded in
+                    // order; rows before tile 0 read as "inclusive 0" and end the walk
+                    int t = int(tile) - 1;
+                    bool done = false;
+                    while (!done)
                     {
-                        const uint32_t w = ld_relaxed_u32(p);
-                        if ((w & ~k_lb_value_mask) == 0)
-                            continue; // predecessor has not published yet
-                        exclusive += w & k_lb_value_mask;
-                        if (w & k_lb_inclusive)
-                            break;
-                        p -= k_radix;
+                        uint32_t w[k_lb_unroll];
+#pragma unroll
+                        for (int j = 0; j < k_lb_unroll; j++)
+                            w[j] = t - j >= 0 ? ld_relaxed_u32(lookback + size_t(t - j) * k_radix + tid) : k_lb_inclusive;
+#pragma unroll
+                        for (int j = 0; j < k_lb_unroll; j++)
+                        {
+                            if (!done)
+                            {
+                                uint32_t x = w[j];
+                                while ((x & ~k_lb_value_mask) == 0) // predecessor has not published yet
+                                    x = ld_relaxed_u32(lookback + size_t(t - j) * k_radix + tid);
+                                exclusive += x & k_lb_value_mask;
+                                done = (x & k_lb_inclusive) != 0;
+                            }
+                        }
+                        t -= k_lb_unroll;
                     }
                     st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid],
                                    k_lb_inclusive | ((exclusive + count_valid) & k_lb_value_mask));
@@ -435,6 +467,10 @@ namespace glu_b200
             {3, 512, 12}, // 6144, 2 CTAs/SM
             {4, 384, 22}, // 8448, 2 CTAs/SM
             {5, 256, 8},  // 2048 (small inputs: more CTAs)
+            {6, 512, 22}, // 11264, 2 CTAs/SM
+            {7, 512, 20}, // 10240, 2 CTAs/SM
+            {8, 1024, 12}, // 12288, 1 CTA/SM
+            {9, 768, 14}, // 10752, 1 CTA/SM... 
         };
         constexpr int k_num_configs = int(sizeof(k_configs) / sizeof(k_configs[0]));
 
@@ -527,6 +563,10 @@ namespace glu_b200
             case 2: return launch_sweep<256, 16, 4, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
             case 3: return launch_sweep<512, 12, 2, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
             case 4: return launch_sweep<384, 22, 2, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+            case 6: return launch_sweep<512, 22, 2, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+            case 7: return launch_sweep<512, 20, 2, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+            case 8: return launch_sweep<1024, 12, 1, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+            case 9: return launch_sweep<768, 14, 1, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
             default: return launch_sweep<256, 8, 4, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
             }
         }

@@ -19,6 +19,8 @@
 // Element types wider than 4 bytes (double, vecN, dvecN, ...) use the same structure with one
 // element per lane per item and a {flag, aggregate, inclusive} record published with release /
 // acquire ordering.
+#include <cstdlib>
+
 #include "glu_common.cuh"
 
 namespace glu_b200
@@ -72,8 +74,12 @@ namespace glu_b200
         // ------------------------------------------------------------------------ 4-byte element types
         //
         // T = uint32_t (also serves Int: two's-complement addition is the same bit pattern) or float.
-        template<typename T, int THREADS, int VPT>
-        __global__ void __launch_bounds__(THREADS)
+        //
+        // TICKET = true : tile id from an atomic ticket (forward progress guaranteed by construction);
+        // TICKET = false: tile id = blockIdx.x (relies on the in-order CTA dispatch of the hardware, like
+        //                 CUB's DeviceScan; saves one L2 round trip and one barrier per tile).
+        template<typename T, int THREADS, int VPT, int MIN_BLOCKS, bool TICKET>
+        __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             scan_b32_kernel(T* __restrict__ data, size_t count, uint32_t tiles_per_part, uint32_t* ticket,
                             uint64_t* state)
         {
@@ -89,10 +95,14 @@ namespace glu_b200
 
             const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-            if (threadIdx.x == 0)
-                s_tile = atomicAdd(ticket, 1u);
-            __syncthreads();
-            const uint32_t tile = s_tile;
+            uint32_t tile = blockIdx.x;
+            if (TICKET)
+            {
+                if (threadIdx.x == 0)
+                    s_tile = atomicAdd(ticket, 1u);
+                __syncthreads();
+                tile = s_tile;
+            }
             const uint32_t part = tile / tiles_per_part;
             const uint32_t tp = tile - part * tiles_per_part; // tile index inside its partition
             const size_t in_part = size_t(tp) * TILE;
@@ -458,22 +468,46 @@ namespace glu_b200
             uint32_t tile;           // elements per tile
             uint32_t tiles_per_part; // ceil(count / tile)
             uint64_t total_tiles;
-            int variant;             // 0 = large tile, 1 = small tile
+            int variant;             // index into the tile-shape table of the element class
         };
 
-        constexpr int k_big_threads = 256, k_big_vpt = 4;     // 4096-element tiles (16 KiB in, 16 KiB out)
-        constexpr int k_small_threads = 64, k_small_vpt = 2;  // 512-element tiles for short segments
-        constexpr int k_wide_threads = 256, k_wide_ipt = 4;   // 1024-element tiles
+        struct ScanShape
+        {
+            int threads, per_thread; // per_thread: 16-byte vectors (4-byte types) or elements (wide types)
+        };
+        // 4-byte element types: {threads, vectors per thread}; tile = threads * vpt * 4 elements
+        constexpr ScanShape k_b32_shapes[] = {{256, 4}, {64, 2}, {512, 4}, {512, 8}, {1024, 4}, {256, 8}};
+        constexpr int k_b32_default = 0, k_b32_small = 1, k_num_b32_shapes = 6;
+        constexpr int k_wide_threads = 256, k_wide_ipt = 4; // 1024-element tiles
         constexpr int k_wide_small_threads = 64, k_wide_small_ipt = 2;
+
+        int scan_env_int(const char* name, int fallback)
+        {
+            const char* v = std::getenv(name);
+            return v && *v ? std::atoi(v) : fallback;
+        }
 
         ScanPlan make_plan(size_t count, size_t num_partitions, bool wide)
         {
+            static const int forced = scan_env_int("GLU_SCAN_CONFIG", -1); // tuning sweeps only
             ScanPlan p;
-            const uint32_t big = wide ? k_wide_threads * k_wide_ipt : k_big_threads * k_big_vpt * 4;
-            const uint32_t small = wide ? k_wide_small_threads * k_wide_small_ipt : k_small_threads * k_small_vpt * 4;
+            uint32_t big, small;
+            int big_variant = 0;
+            if (wide)
+            {
+                big = k_wide_threads * k_wide_ipt;
+                small = k_wide_small_threads * k_wide_small_ipt;
+            }
+            else
+            {
+                big_variant = (forced >= 0 && forced < k_num_b32_shapes && forced != k_b32_small) ? forced : k_b32_default;
+                big = k_b32_shapes[big_variant].threads * k_b32_shapes[big_variant].per_thread * 4;
+                small = k_b32_shapes[k_b32_small].threads * k_b32_shapes[k_b32_small].per_thread * 4;
+            }
             // short segments: a big tile would be mostly padding
-            p.variant = (num_partitions > 1 && count <= big / 2) ? 1 : 0;
-            p.tile = p.variant ? small : big;
+            const bool use_small = num_partitions > 1 && count <= big / 2;
+            p.variant = use_small ? 1 : big_variant;
+            p.tile = use_small ? small : big;
             p.tiles_per_part = uint32_t((count + p.tile - 1) / p.tile);
             p.total_tiles = uint64_t(p.tiles_per_part) * num_partitions;
             return p;
@@ -487,21 +521,37 @@ namespace glu_b200
                    2 * align_up(p.total_tiles * elem_size, k_tmp_align);
         }
 
+        template<typename T, int THREADS, int VPT, int MIN_BLOCKS>
+        int launch_b32_shape(T* data, size_t count, const ScanPlan& p, uint32_t* ticket, uint64_t* state, cudaStream_t s)
+        {
+            static const bool use_ticket = scan_env_int("GLU_SCAN_TICKET", 1) != 0;
+            ScopedKernelProfile prof(GLU_KERNEL_SCAN, s);
+            if (use_ticket)
+                scan_b32_kernel<T, THREADS, VPT, MIN_BLOCKS, true>
+                    <<<unsigned(p.total_tiles), THREADS, 0, s>>>(data, count, p.tiles_per_part, ticket, state);
+            else
+                scan_b32_kernel<T, THREADS, VPT, MIN_BLOCKS, false>
+                    <<<unsigned(p.total_tiles), THREADS, 0, s>>>(data, count, p.tiles_per_part, ticket, state);
+            GLU_LAUNCH_CHECK();
+            return GLU_SUCCESS;
+        }
+
         template<typename T>
         int launch_b32(void* d_data, size_t count, const ScanPlan& p, void* d_tmp, cudaStream_t s)
         {
             uint32_t* ticket = static_cast<uint32_t*>(d_tmp);
             uint64_t* state = reinterpret_cast<uint64_t*>(static_cast<char*>(d_tmp) + k_tmp_align);
+            T* data = static_cast<T*>(d_data);
             GLU_CUDA_TRY(cudaMemsetAsync(d_tmp, 0, k_tmp_align + state_bytes(p, 4), s));
-            ScopedKernelProfile prof(GLU_KERNEL_SCAN, s);
-            if (p.variant == 0)
-                scan_b32_kernel<T, k_big_threads, k_big_vpt><<<unsigned(p.total_tiles), k_big_threads, 0, s>>>(
-                    static_cast<T*>(d_data), count, p.tiles_per_part, ticket, state);
-            else
-                scan_b32_kernel<T, k_small_threads, k_small_vpt><<<unsigned(p.total_tiles), k_small_threads, 0, s>>>(
-                    static_cast<T*>(d_data), count, p.tiles_per_part, ticket, state);
-            GLU_LAUNCH_CHECK();
-            return GLU_SUCCESS;
+            switch (p.variant)
+            {
+            case 0: return launch_b32_shape<T, 256, 4, 1>(data, count, p, ticket, state, s);
+            case 1: return launch_b32_shape<T, 64, 2, 1>(data, count, p, ticket, state, s);
+            case 2: return launch_b32_shape<T, 512, 4, 1>(data, count, p, ticket, state, s);
+            case 3: return launch_b32_shape<T, 512, 8, 2>(data, count, p, ticket, state, s);
+            case 4: return launch_b32_shape<T, 1024, 4, 2>(data, count, p, ticket, state, s);
+            default: return launch_b32_shape<T, 256, 8, 4>(data, count, p, ticket, state, s);
+            }
         }
 
         template<typename S, int NC>

@@ -30,6 +30,10 @@ except Exception:
     dem = names
 for r, d in zip(rows, dem):
     d = re.sub(r"glu_b200::\(anonymous namespace\)::", "", d)
-    d = re.sub(r"\(.*$", "", d)
     d = re.sub(r"^void ", "", d)
+    d = re.sub(r"\((int|bool)\)", "", d)
+    d = re.sub(r"<unnamed>::", "", d)
+    d = re.sub(r"glu_b200::", "", d)
+    d = re.sub(r">\(.*$", ">", d)
+    d = re.sub(r"^(\w+)\(.*$", r"\1", d)
     print(f"{d:70s} regs={r.get('regs','?'):>3s} stack={r.get('stack','0'):>4s} spill(st/ld)={r['spill']:>7s} smem={r.get('smem','0')}")
