@@ -32,7 +32,7 @@ namespace glu_b200
         constexpr uint32_t k_lb_inclusive = 2u << 30; // inclusive prefix over tiles 0..t published
         constexpr uint32_t k_lb_value_mask = (1u << 30) - 1u;
         constexpr size_t k_max_count = size_t(1) << 30;
-        constexpr int k_lb_unroll = 8; // look-back rows in flight per digit thread
+        constexpr int k_lb_rows = 2;   // look-back rows in flight (x 8 digits per lane of the look-back warp)
 
         struct PassPlan
         {
@@ -220,45 +220,60 @@ namespace glu_b200
             return peers;
         }
 
-        template<int THREADS, int IPT> struct SweepSmem
+        constexpr int k_lb_threads = 32; // one dedicated look-back warp per CTA, 8 digits per lane
+
+        template<int RANK_THREADS, int IPT> struct SweepSmem
         {
-            static constexpr int WARPS = THREADS / 32;
-            static constexpr int TILE = THREADS * IPT;
+            static constexpr int WARPS = RANK_THREADS / 32; // ranking warps
+            static constexpr int TILE = RANK_THREADS * IPT;
             alignas(128) uint32_t keys[TILE];   // TMA destination (input order), then tile-sorted keys
             alignas(128) uint32_t vals[TILE];   // TMA destination (input order), then tile-sorted values
-            uint32_t warp_hist[WARPS][k_radix]; // per-warp digit counters, then per-warp digit offsets
+            uint32_t warp_hist[WARPS][k_radix]; // per-warp digit counts, then per-warp running slot offsets
             uint32_t gbase[k_radix];            // global index of tile-sorted slot 0, per digit
+            uint32_t tile_count[k_radix];       // this tile's digit counts (real keys only)
+            uint32_t tile_start[k_radix];       // first tile-sorted slot of each digit
             uint32_t scan[8];
             alignas(8) uint64_t bar_keys;       // mbarriers completed by the bulk copies
             alignas(8) uint64_t bar_vals;
             uint32_t tile;
         };
 
+        __device__ __forceinline__ void named_barrier_sync(int id, int threads)
+        {
+            asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+        }
+
         // One tile per CTA.  digit(key) = (key >> shift) & mask; keys with equal digits keep their order.
+        // A CTA is RANK_THREADS "ranking" threads plus one dedicated look-back warp.
         //
         //   1. ticket -> tile id; one thread issues two cp.async.bulk (TMA) copies: the tile's keys and
         //      values land in shared memory asynchronously, completion on an mbarrier each (the last,
         //      partial tile and 16-byte-misaligned inputs take a cooperative ld/st path instead);
-        //   2. every thread takes IPT keys warp-striped (slot = warp*IPT*32 + i*32 + lane, i.e. input
-        //      order inside the warp) and ranks each against the warp's earlier equal digits:
-        //      peers = match(digit); rank = counter[warp][digit] + popc(peers below me);
-        //   3. one thread per digit: tile count -> published for look-back -> exclusive scan over the
-        //      256 digits and the warps -> per-(warp, digit) slot offsets;
-        //   4. keys are scattered to their tile-sorted slot IN PLACE, values are pulled out of their
-        //      staging buffer into registers; meanwhile the digit threads walk back over the earlier
-        //      tiles' published counts until they meet an inclusive prefix;
-        //   5. values are scattered in place; then slot p of both arrays goes to
-        //      global[gbase[digit(key_p)] + p] — neighbouring threads, neighbouring addresses.
-        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE>
-        __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
+        //   2. EARLY COUNTS: every ranking thread takes IPT keys warp-striped (slot = warp*IPT*32 + i*32
+        //      + lane, i.e. input order inside the warp) and bumps its warp's private digit counters;
+        //      one thread per digit then sums the warps, PUBLISHES the tile's digit count for look-back
+        //      right away (successor tiles need it long before this tile has ranked anything), scans the
+        //      256 counts and turns the counters into per-(warp, digit) running slot offsets;
+        //   3. ranking: peers = lanes of the warp holding the same digit (one ballot per digit bit);
+        //      slot = offset[warp][digit] + popc(peers below me); the key goes straight to its
+        //      tile-sorted slot (in place: every key is in registers by now);
+        //   4. MEANWHILE the look-back warp walks back over the earlier tiles' published counts (8 digits
+        //      per lane, several rows in flight) until it meets an inclusive prefix, publishes this
+        //      tile's inclusive prefix and leaves gbase[digit] = global index of tile-sorted slot 0;
+        //   5. values: staging buffer -> registers -> tile-sorted slot (in place); then slot p of both
+        //      arrays goes to global[gbase[digit(key_p)] + p] — neighbouring threads, neighbouring
+        //      addresses inside every digit run.
+        template<int RANK_THREADS, int IPT, int MIN_BLOCKS, int MODE>
+        __global__ void __launch_bounds__(RANK_THREADS + k_lb_threads, MIN_BLOCKS)
             onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                             uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
                             uint32_t shift, uint32_t mask, const uint32_t* __restrict__ digit_offset,
                             uint32_t* lookback, uint32_t* ticket, int allow_tma)
         {
-            static_assert(THREADS >= k_radix && THREADS % 32 == 0, "one thread per digit is required");
+            static_assert(RANK_THREADS >= k_radix && RANK_THREADS % 32 == 0, "one ranking thread per digit");
             static_assert(IPT % 2 == 0, "ranks are packed two per register");
-            using Smem = SweepSmem<THREADS, IPT>;
+            using Smem = SweepSmem<RANK_THREADS, IPT>;
+            constexpr int THREADS = RANK_THREADS + k_lb_threads;
             constexpr int WARPS = Smem::WARPS;
             constexpr int TILE = Smem::TILE;
             constexpr int WARP_ELEMS = IPT * 32;
@@ -267,6 +282,7 @@ namespace glu_b200
             Smem& s = *reinterpret_cast<Smem*>(smem_raw);
 
             const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+            const bool ranking = tid < RANK_THREADS; // warp-uniform
             if (tid == 0)
             {
                 s.tile = atomicAdd(ticket, 1u);
@@ -295,7 +311,6 @@ namespace glu_b200
                     mbarrier_arrive_expect_tx(&s.bar_vals, TILE * 4);
                     tma_load_1d(s.vals, vals_in + tile_base, TILE * 4, &s.bar_vals, policy);
                 }
-                mbarrier_wait(&s.bar_keys, 0);
             }
             else
             {
@@ -309,43 +324,44 @@ namespace glu_b200
                 __syncthreads();
             }
 
-            // ---- rank inside the warp: position among the warp's earlier keys with the same digit
+            // ---- early counts: the warp's digit histogram
             uint32_t key[IPT];
-#pragma unroll
-            for (int i = 0; i < IPT; i++)
-                key[i] = s.keys[my_off + i * 32];
-            uint32_t rank2[IPT / 2]; // two 16-bit ranks per register
-            uint32_t* wh = s.warp_hist[warp];
-            const uint32_t lt = lanemask_lt();
-#pragma unroll
-            for (int i = 0; i < IPT; i++)
+            uint32_t* wh = s.warp_hist[ranking ? warp : 0];
+            if (ranking)
             {
-                const uint32_t d = (key[i] >> shift) & mask;
-                const uint32_t peers = match_digit<MODE>(d);
-                const uint32_t before = wh[d];
-                __syncwarp();
-                if ((peers & lt) == 0)
-                    wh[d] = before + __popc(peers);
-                __syncwarp();
-                const uint32_t r = before + __popc(peers & lt);
-                if (i & 1)
-                    rank2[i / 2] |= r << 16;
-                else
-                    rank2[i / 2] = r;
+                if (use_tma)
+                    mbarrier_wait(&s.bar_keys, 0);
+#pragma unroll
+                for (int i = 0; i < IPT; i++)
+                    key[i] = s.keys[my_off + i * 32];
+#pragma unroll
+                for (int i = 0; i < IPT; i++)
+                {
+                    const uint32_t d = (key[i] >> shift) & mask;
+                    // a digit shared by the whole warp would be a 32-way same-address atomic: count it once
+                    if (__all_sync(k_full_mask, d == __shfl_sync(k_full_mask, d, 0)))
+                    {
+                        if (lane == 0)
+                            wh[d] += 32;
+                    }
+                    else
+                        atomicAdd(&wh[d], 1u);
+                }
             }
-            __syncthreads(); // every key is in registers; the counters are final
+            __syncthreads(); // every key is in registers; the counts are final
 
-            // ---- per-digit: tile count, offsets of each warp inside the tile, look-back publication
-            uint32_t total = 0, inc = 0, count_valid = 0;
+            // ---- per-digit: tile count -> look-back publication; slot offsets of each warp
+            uint32_t total = 0, inc = 0;
             if (tid < k_radix)
             {
 #pragma unroll
                 for (int w = 0; w < WARPS; w++)
                     total += s.warp_hist[w][tid];
                 // padding slots all carry digit `mask`
-                count_valid = total - (tid == mask ? uint32_t(TILE) - valid : 0u);
+                const uint32_t count_valid = total - (tid == mask ? uint32_t(TILE) - valid : 0u);
                 st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid],
                                (tile == 0 ? k_lb_inclusive : k_lb_local) | count_valid);
+                s.tile_count[tid] = count_valid;
                 inc = total;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1)
@@ -358,12 +374,12 @@ namespace glu_b200
                     s.scan[warp] = inc;
             }
             __syncthreads();
-            uint32_t tile_start = 0; // first tile-sorted slot of this thread's digit
             if (tid < k_radix)
             {
+                uint32_t tile_start = inc - total;
                 for (unsigned w = 0; w < warp; w++)
                     tile_start += s.scan[w];
-                tile_start += inc - total;
+                s.tile_start[tid] = tile_start;
                 uint32_t running = tile_start;
 #pragma unroll
                 for (int w = 0; w < WARPS; w++)
@@ -375,78 +391,111 @@ namespace glu_b200
             }
             __syncthreads();
 
-            // ---- keys -> tile-sorted slots (in place: all keys were read before the barrier above)
-#pragma unroll
-            for (int i = 0; i < IPT; i += 2)
+            uint32_t rank2[IPT / 2]; // two 16-bit tile-sorted slots per register
+            if (ranking)
             {
-                const uint32_t d0 = (key[i] >> shift) & mask;
-                const uint32_t d1 = (key[i + 1] >> shift) & mask;
-                rank2[i / 2] += wh[d0] | (wh[d1] << 16); // both sums stay below 2^16
-                s.keys[rank2[i / 2] & 0xffffu] = key[i];
-                s.keys[rank2[i / 2] >> 16] = key[i + 1];
-            }
-            // ---- values: staging buffer -> registers (the key registers are dead now)
-            if (use_tma)
-                mbarrier_wait(&s.bar_vals, 0);
-            uint32_t val[IPT];
+                // ---- rank + scatter keys (in place)
+                const uint32_t lt = lanemask_lt();
 #pragma unroll
-            for (int i = 0; i < IPT; i++)
-                val[i] = s.vals[my_off + i * 32];
-
-            // ---- decoupled look-back: digits' counts in all earlier tiles
-            if (tid < k_radix)
-            {
-                uint32_t exclusive = 0;
-                if (tile > 0)
+                for (int i = 0; i < IPT; i++)
                 {
-                    // k_lb_unroll predecessors are fetched per round trip (independent loads), then folded in
-                    // order; rows before tile 0 read as "inclusive 0" and end the walk
-                    int t = int(tile) - 1;
-                    bool done = false;
-                    while (!done)
-                    {
-                        uint32_t w[k_lb_unroll];
+                    const uint32_t d = (key[i] >> shift) & mask;
+                    const uint32_t peers = match_digit<MODE>(d);
+                    const uint32_t before = wh[d];
+                    __syncwarp();
+                    wh[d] = before + __popc(peers); // every peer stores the same value
+                    __syncwarp();
+                    const uint32_t r = before + __popc(peers & lt);
+                    s.keys[r] = key[i];
+                    if (i & 1)
+                        rank2[i / 2] |= r << 16;
+                    else
+                        rank2[i / 2] = r;
+                }
+                // ---- values: staging buffer -> registers (the key registers are dead now)
+                if (use_tma)
+                    mbarrier_wait(&s.bar_vals, 0);
+                uint32_t val[IPT];
 #pragma unroll
-                        for (int j = 0; j < k_lb_unroll; j++)
-                            w[j] = t - j >= 0 ? ld_relaxed_u32(lookback + size_t(t - j) * k_radix + tid) : k_lb_inclusive;
+                for (int i = 0; i < IPT; i++)
+                    val[i] = s.vals[my_off + i * 32];
+                named_barrier_sync(1, RANK_THREADS); // all values are in registers
 #pragma unroll
-                        for (int j = 0; j < k_lb_unroll; j++)
+                for (int i = 0; i < IPT; i += 2)
+                {
+                    s.vals[rank2[i / 2] & 0xffffu] = val[i];
+                    s.vals[rank2[i / 2] >> 16] = val[i + 1];
+                }
+            }
+            else
+            {
+                // ---- the look-back warp: digits lane, lane + 32, ... ; their counts in all earlier tiles.
+                // k_lb_rows predecessor rows are fetched per round trip (independent loads), then folded
+                // in order; rows before tile 0 read as "inclusive 0" and end the walk.
+                constexpr int DPL = k_radix / k_lb_threads; // digits per lane
+                uint32_t exclusive[DPL];
+                bool done[DPL];
+#pragma unroll
+                for (int k = 0; k < DPL; k++)
+                {
+                    exclusive[k] = 0;
+                    done[k] = tile == 0;
+                }
+                int t = int(tile) - 1;
+                while (true)
+                {
+                    bool all_done = true;
+#pragma unroll
+                    for (int k = 0; k < DPL; k++)
+                        all_done = all_done && done[k];
+                    if (all_done)
+                        break;
+                    uint32_t w[k_lb_rows][DPL];
+#pragma unroll
+                    for (int j = 0; j < k_lb_rows; j++)
+#pragma unroll
+                        for (int k = 0; k < DPL; k++)
+                            w[j][k] = (t - j >= 0 && !done[k])
+                                          ? ld_relaxed_u32(lookback + size_t(t - j) * k_radix + k * k_lb_threads + lane)
+                                          : k_lb_inclusive;
+#pragma unroll
+                    for (int j = 0; j < k_lb_rows; j++)
+#pragma unroll
+                        for (int k = 0; k < DPL; k++)
                         {
-                            if (!done)
+                            if (!done[k])
                             {
-                                uint32_t x = w[j];
+                                uint32_t x = w[j][k];
                                 while ((x & ~k_lb_value_mask) == 0) // predecessor has not published yet
-                                    x = ld_relaxed_u32(lookback + size_t(t - j) * k_radix + tid);
-                                exclusive += x & k_lb_value_mask;
-                                done = (x & k_lb_inclusive) != 0;
+                                    x = ld_relaxed_u32(lookback + size_t(t - j) * k_radix + k * k_lb_threads + lane);
+                                exclusive[k] += x & k_lb_value_mask;
+                                done[k] = (x & k_lb_inclusive) != 0;
                             }
                         }
-                        t -= k_lb_unroll;
-                    }
-                    st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid],
-                                   k_lb_inclusive | ((exclusive + count_valid) & k_lb_value_mask));
+                    t -= k_lb_rows;
                 }
-                s.gbase[tid] = digit_offset[tid] + exclusive - tile_start;
-            }
-            __syncthreads(); // all values are in registers; sorted keys and gbase are visible
 #pragma unroll
-            for (int i = 0; i < IPT; i += 2)
-            {
-                s.vals[rank2[i / 2] & 0xffffu] = val[i];
-                s.vals[rank2[i / 2] >> 16] = val[i + 1];
+                for (int k = 0; k < DPL; k++)
+                {
+                    const uint32_t d = k * k_lb_threads + lane;
+                    if (tile > 0)
+                        st_relaxed_u32(&lookback[size_t(tile) * k_radix + d],
+                                       k_lb_inclusive | ((exclusive[k] + s.tile_count[d]) & k_lb_value_mask));
+                    s.gbase[d] = digit_offset[d] + exclusive[k] - s.tile_start[d];
+                }
             }
-            __syncthreads();
+            __syncthreads(); // tile-sorted keys and values, gbase
 
             // ---- out: consecutive threads write consecutive addresses inside each digit run
 #pragma unroll
-            for (int k = 0; k < IPT; k++)
+            for (int k = 0; k < (TILE + THREADS - 1) / THREADS; k++)
             {
                 const uint32_t p = tid + k * THREADS;
-                const uint32_t kk = s.keys[p];
-                const uint32_t vv = s.vals[p];
-                const uint32_t dst = s.gbase[(kk >> shift) & mask] + p;
-                if (full || p < valid)
+                if (p < valid)
                 {
+                    const uint32_t kk = s.keys[p];
+                    const uint32_t vv = s.vals[p];
+                    const uint32_t dst = s.gbase[(kk >> shift) & mask] + p;
                     keys_out[dst] = kk;
                     vals_out[dst] = vv;
                 }
@@ -461,16 +510,15 @@ namespace glu_b200
             int threads, ipt;
         };
         constexpr SweepConfig k_configs[] = {
-            {0, 512, 16}, // 8192-pair tiles, 2 CTAs/SM
-            {1, 384, 18}, // 6912, 3 CTAs/SM
-            {2, 256, 16}, // 4096, 4 CTAs/SM
-            {3, 512, 12}, // 6144, 2 CTAs/SM
-            {4, 384, 22}, // 8448, 2 CTAs/SM
+            // {id, ranking threads, keys per thread}: tile = threads * ipt; +32 threads for the look-back warp
+            {0, 480, 16}, // 7680-pair tiles, 2 CTAs/SM
+            {1, 352, 18}, // 6336, 3 CTAs/SM
+            {2, 256, 16}, // 4096, 4 CTAs/SM (mid-size inputs)
+            {3, 352, 20}, // 7040, 3 CTAs/SM
+            {4, 480, 22}, // 10560, 2 CTAs/SM
             {5, 256, 8},  // 2048 (small inputs: more CTAs)
-            {6, 512, 22}, // 11264, 2 CTAs/SM
-            {7, 512, 20}, // 10240, 2 CTAs/SM
-            {8, 1024, 12}, // 12288, 1 CTA/SM
-            {9, 768, 14}, // 10752, 1 CTA/SM... 
+            {6, 352, 16}, // 5632, 3 CTAs/SM
+            {7, 288, 18}, // 5184, 4 CTAs/SM
         };
         constexpr int k_num_configs = int(sizeof(k_configs) / sizeof(k_configs[0]));
 
@@ -545,8 +593,8 @@ namespace glu_b200
                 configured[dev] = true;
             }
             ScopedKernelProfile prof(GLU_KERNEL_SORT_ONESWEEP, s);
-            kernel<<<tiles, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket,
-                                                allow_tma);
+            kernel<<<tiles, THREADS + k_lb_threads, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback,
+                                                               ticket, allow_tma);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
@@ -558,16 +606,17 @@ namespace glu_b200
         {
             switch (c.id)
             {
-            case 0: return launch_sweep<512, 16, 2, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
-            case 1: return launch_sweep<384, 18, 3, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
-            case 2: return launch_sweep<256, 16, 4, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
-            case 3: return launch_sweep<512, 12, 2, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
-            case 4: return launch_sweep<384, 22, 2, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
-            case 6: return launch_sweep<512, 22, 2, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
-            case 7: return launch_sweep<512, 20, 2, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
-            case 8: return launch_sweep<1024, 12, 1, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
-            case 9: return launch_sweep<768, 14, 1, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+#define GLU_SWEEP_CASE(ID, T, I, B)                                                                                    \
+    case ID: return launch_sweep<T, I, B, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+                GLU_SWEEP_CASE(0, 480, 16, 2)
+                GLU_SWEEP_CASE(1, 352, 18, 3)
+                GLU_SWEEP_CASE(2, 256, 16, 4)
+                GLU_SWEEP_CASE(3, 352, 20, 3)
+                GLU_SWEEP_CASE(4, 480, 22, 2)
+                GLU_SWEEP_CASE(6, 352, 16, 3)
+                GLU_SWEEP_CASE(7, 288, 18, 4)
             default: return launch_sweep<256, 8, 4, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+#undef GLU_SWEEP_CASE
             }
         }
     } // namespace
