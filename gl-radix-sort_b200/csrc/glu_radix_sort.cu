@@ -32,7 +32,7 @@ namespace glu_b200
         constexpr uint32_t k_lb_inclusive = 2u << 30; // inclusive prefix over tiles 0..t published
         constexpr uint32_t k_lb_value_mask = (1u << 30) - 1u;
         constexpr size_t k_max_count = size_t(1) << 30;
-        constexpr int k_lb_rows = 2;   // look-back rows in flight (x 8 digits per lane of the look-back warp)
+        constexpr int k_lb_rows = 8;   // look-back rows in flight per digit thread
 
         struct PassPlan
         {
@@ -205,22 +205,33 @@ namespace glu_b200
             Rank_Ballot = 1 // one ballot per digit bit
         };
 
+        // One step of the ballot match: lanes whose digit agrees with mine in bit BIT stay in `peers`.
+        // Hand-scheduled as ~3 SASS instructions per bit (R2P for 7 bits at once, VOTE, SEL, LOP3);
+        // the C++ formulation `peers &= bit ? vote : ~vote` compiles to 6-7.
+#define GLU_MATCH_BIT(BIT)                                                                                             \
+    "and.b32 t, %1, " #BIT ";\n"                                                                                       \
+    "setp.ne.u32 p, t, 0;\n"                                                                                           \
+    "vote.sync.ballot.b32 v, p, 0xffffffff;\n"                                                                         \
+    "selp.b32 m, 0xffffffff, 0, p;\n"                                                                                  \
+    "lop3.b32 %0, %0, v, m, 0x90;\n" /* peers & ~(v ^ m) */
+
         template<int MODE> __device__ __forceinline__ uint32_t match_digit(uint32_t d)
         {
             if (MODE == Rank_Match)
                 return __match_any_sync(k_full_mask, d);
-            uint32_t peers = k_full_mask;
-#pragma unroll
-            for (int b = 0; b < 8; b++)
-            {
-                const bool bit = (d >> b) & 1u;
-                const uint32_t vote = __ballot_sync(k_full_mask, bit);
-                peers &= bit ? vote : ~vote;
-            }
+            uint32_t peers;
+            asm volatile("{\n"
+                         ".reg .pred p;\n"
+                         ".reg .b32 v, t, m;\n"
+                         "mov.b32 %0, 0xffffffff;\n" GLU_MATCH_BIT(1) GLU_MATCH_BIT(2) GLU_MATCH_BIT(4) GLU_MATCH_BIT(8)
+                             GLU_MATCH_BIT(16) GLU_MATCH_BIT(32) GLU_MATCH_BIT(64) GLU_MATCH_BIT(128) "}\n"
+                         : "=&r"(peers)
+                         : "r"(d));
             return peers;
         }
+#undef GLU_MATCH_BIT
 
-        constexpr int k_lb_threads = 32; // one dedicated look-back warp per CTA, 8 digits per lane
+        constexpr int k_lb_threads = 0; // (dedicated look-back warps: tried, slower — the walk became the critical path)
 
         template<int RANK_THREADS, int IPT> struct SweepSmem
         {
@@ -237,11 +248,6 @@ namespace glu_b200
             alignas(8) uint64_t bar_vals;
             uint32_t tile;
         };
-
-        __device__ __forceinline__ void named_barrier_sync(int id, int threads)
-        {
-            asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-        }
 
         // One tile per CTA.  digit(key) = (key >> shift) & mask; keys with equal digits keep their order.
         // A CTA is RANK_THREADS "ranking" threads plus one dedicated look-back warp.
@@ -282,7 +288,6 @@ namespace glu_b200
             Smem& s = *reinterpret_cast<Smem*>(smem_raw);
 
             const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-            const bool ranking = tid < RANK_THREADS; // warp-uniform
             if (tid == 0)
             {
                 s.tile = atomicAdd(ticket, 1u);
@@ -326,8 +331,7 @@ namespace glu_b200
 
             // ---- early counts: the warp's digit histogram
             uint32_t key[IPT];
-            uint32_t* wh = s.warp_hist[ranking ? warp : 0];
-            if (ranking)
+            uint32_t* wh = s.warp_hist[warp];
             {
                 if (use_tma)
                     mbarrier_wait(&s.bar_keys, 0);
@@ -392,7 +396,6 @@ namespace glu_b200
             __syncthreads();
 
             uint32_t rank2[IPT / 2]; // two 16-bit tile-sorted slots per register
-            if (ranking)
             {
                 // ---- rank + scatter keys (in place)
                 const uint32_t lt = lanemask_lt();
@@ -419,69 +422,49 @@ namespace glu_b200
 #pragma unroll
                 for (int i = 0; i < IPT; i++)
                     val[i] = s.vals[my_off + i * 32];
-                named_barrier_sync(1, RANK_THREADS); // all values are in registers
+
+                // ---- decoupled look-back (one thread per digit): this digit's count in all earlier tiles.
+                // k_lb_rows predecessor rows are fetched per round trip (independent loads), then folded
+                // in order; rows before tile 0 read as "inclusive 0" and end the walk.
+                if (tid < k_radix)
+                {
+                    uint32_t exclusive = 0;
+                    if (tile > 0)
+                    {
+                        int t = int(tile) - 1;
+                        bool done = false;
+                        while (!done)
+                        {
+                            uint32_t w[k_lb_rows];
+#pragma unroll
+                            for (int j = 0; j < k_lb_rows; j++)
+                                w[j] = t - j >= 0 ? ld_relaxed_u32(lookback + size_t(t - j) * k_radix + tid)
+                                                  : k_lb_inclusive;
+#pragma unroll
+                            for (int j = 0; j < k_lb_rows; j++)
+                            {
+                                if (!done)
+                                {
+                                    uint32_t x = w[j];
+                                    while ((x & ~k_lb_value_mask) == 0) // predecessor has not published yet
+                                        x = ld_relaxed_u32(lookback + size_t(t - j) * k_radix + tid);
+                                    exclusive += x & k_lb_value_mask;
+                                    done = (x & k_lb_inclusive) != 0;
+                                }
+                            }
+                            t -= k_lb_rows;
+                        }
+                        st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid],
+                                       k_lb_inclusive | ((exclusive + s.tile_count[tid]) & k_lb_value_mask));
+                    }
+                    s.gbase[tid] = digit_offset[tid] + exclusive - s.tile_start[tid];
+                }
+                __syncthreads(); // all values are in registers
 #pragma unroll
                 for (int i = 0; i < IPT; i += 2)
                 {
                     s.vals[rank2[i / 2] & 0xffffu] = val[i];
                     s.vals[rank2[i / 2] >> 16] = val[i + 1];
-                }
-            }
-            else
-            {
-                // ---- the look-back warp: digits lane, lane + 32, ... ; their counts in all earlier tiles.
-                // k_lb_rows predecessor rows are fetched per round trip (independent loads), then folded
-                // in order; rows before tile 0 read as "inclusive 0" and end the walk.
-                constexpr int DPL = k_radix / k_lb_threads; // digits per lane
-                uint32_t exclusive[DPL];
-                bool done[DPL];
-#pragma unroll
-                for (int k = 0; k < DPL; k++)
-                {
-                    exclusive[k] = 0;
-                    done[k] = tile == 0;
-                }
-                int t = int(tile) - 1;
-                while (true)
-                {
-                    bool all_done = true;
-#pragma unroll
-                    for (int k = 0; k < DPL; k++)
-                        all_done = all_done && done[k];
-                    if (all_done)
-                        break;
-                    uint32_t w[k_lb_rows][DPL];
-#pragma unroll
-                    for (int j = 0; j < k_lb_rows; j++)
-#pragma unroll
-                        for (int k = 0; k < DPL; k++)
-                            w[j][k] = (t - j >= 0 && !done[k])
-                                          ? ld_relaxed_u32(lookback + size_t(t - j) * k_radix + k * k_lb_threads + lane)
-                                          : k_lb_inclusive;
-#pragma unroll
-                    for (int j = 0; j < k_lb_rows; j++)
-#pragma unroll
-                        for (int k = 0; k < DPL; k++)
-                        {
-                            if (!done[k])
-                            {
-                                uint32_t x = w[j][k];
-                                while ((x & ~k_lb_value_mask) == 0) // predecessor has not published yet
-                                    x = ld_relaxed_u32(lookback + size_t(t - j) * k_radix + k * k_lb_threads + lane);
-                                exclusive[k] += x & k_lb_value_mask;
-                                done[k] = (x & k_lb_inclusive) != 0;
-                            }
-                        }
-                    t -= k_lb_rows;
-                }
-#pragma unroll
-                for (int k = 0; k < DPL; k++)
-                {
-                    const uint32_t d = k * k_lb_threads + lane;
-                    if (tile > 0)
-                        st_relaxed_u32(&lookback[size_t(tile) * k_radix + d],
-                                       k_lb_inclusive | ((exclusive[k] + s.tile_count[d]) & k_lb_value_mask));
-                    s.gbase[d] = digit_offset[d] + exclusive[k] - s.tile_start[d];
                 }
             }
             __syncthreads(); // tile-sorted keys and values, gbase
@@ -510,15 +493,15 @@ namespace glu_b200
             int threads, ipt;
         };
         constexpr SweepConfig k_configs[] = {
-            // {id, ranking threads, keys per thread}: tile = threads * ipt; +32 threads for the look-back warp
-            {0, 480, 16}, // 7680-pair tiles, 2 CTAs/SM
-            {1, 352, 18}, // 6336, 3 CTAs/SM
+            // {id, threads, keys per thread}: tile = threads * ipt
+            {0, 512, 16}, // 8192-pair tiles, 2 CTAs/SM
+            {1, 384, 18}, // 6912, 3 CTAs/SM
             {2, 256, 16}, // 4096, 4 CTAs/SM (mid-size inputs)
-            {3, 352, 20}, // 7040, 3 CTAs/SM
-            {4, 480, 22}, // 10560, 2 CTAs/SM
+            {3, 384, 20}, // 7680, 3 CTAs/SM
+            {4, 512, 22}, // 11264, 2 CTAs/SM
             {5, 256, 8},  // 2048 (small inputs: more CTAs)
-            {6, 352, 16}, // 5632, 3 CTAs/SM
-            {7, 288, 18}, // 5184, 4 CTAs/SM
+            {6, 384, 16}, // 6144, 3 CTAs/SM
+            {7, 320, 18}, // 5760, 4 CTAs/SM
         };
         constexpr int k_num_configs = int(sizeof(k_configs) / sizeof(k_configs[0]));
 
@@ -608,13 +591,13 @@ namespace glu_b200
             {
 #define GLU_SWEEP_CASE(ID, T, I, B)                                                                                    \
     case ID: return launch_sweep<T, I, B, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
-                GLU_SWEEP_CASE(0, 480, 16, 2)
-                GLU_SWEEP_CASE(1, 352, 18, 3)
+                GLU_SWEEP_CASE(0, 512, 16, 2)
+                GLU_SWEEP_CASE(1, 384, 18, 3)
                 GLU_SWEEP_CASE(2, 256, 16, 4)
-                GLU_SWEEP_CASE(3, 352, 20, 3)
-                GLU_SWEEP_CASE(4, 480, 22, 2)
-                GLU_SWEEP_CASE(6, 352, 16, 3)
-                GLU_SWEEP_CASE(7, 288, 18, 4)
+                GLU_SWEEP_CASE(3, 384, 20, 3)
+                GLU_SWEEP_CASE(4, 512, 22, 2)
+                GLU_SWEEP_CASE(6, 384, 16, 3)
+                GLU_SWEEP_CASE(7, 320, 18, 4)
             default: return launch_sweep<256, 8, 4, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
 #undef GLU_SWEEP_CASE
             }
