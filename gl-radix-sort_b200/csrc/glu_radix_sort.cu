@@ -32,7 +32,7 @@ namespace glu_b200
         constexpr uint32_t k_lb_inclusive = 2u << 30; // inclusive prefix over tiles 0..t published
         constexpr uint32_t k_lb_value_mask = (1u << 30) - 1u;
         constexpr size_t k_max_count = size_t(1) << 30;
-        constexpr int k_lb_rows = 8;   // look-back rows in flight per digit thread
+        constexpr int k_lb_rows = 16;  // look-back rows in flight per digit thread
 
         struct PassPlan
         {
@@ -239,7 +239,7 @@ namespace glu_b200
             static constexpr int TILE = RANK_THREADS * IPT;
             alignas(128) uint32_t keys[TILE];   // TMA destination (input order), then tile-sorted keys
             alignas(128) uint32_t vals[TILE];   // TMA destination (input order), then tile-sorted values
-            uint32_t warp_hist[WARPS][k_radix]; // per-warp digit counts, then per-warp running slot offsets
+            alignas(16) uint32_t warp_hist[WARPS][k_radix]; // per-warp digit counts, then running slot offsets
             uint32_t gbase[k_radix];            // global index of tile-sorted slot 0, per digit
             uint32_t tile_count[k_radix];       // this tile's digit counts (real keys only)
             uint32_t tile_start[k_radix];       // first tile-sorted slot of each digit
@@ -295,8 +295,8 @@ namespace glu_b200
                 mbarrier_init(&s.bar_vals, 1);
                 mbarrier_init_fence();
             }
-            for (int i = tid; i < WARPS * k_radix; i += THREADS)
-                (&s.warp_hist[0][0])[i] = 0;
+            for (int i = tid; i < WARPS * k_radix / 4; i += THREADS)
+                reinterpret_cast<uint4*>(&s.warp_hist[0][0])[i] = make_uint4(0, 0, 0, 0);
             __syncthreads();
             const uint32_t tile = s.tile;
             const uint32_t tile_base = tile * uint32_t(TILE);
@@ -338,18 +338,29 @@ namespace glu_b200
 #pragma unroll
                 for (int i = 0; i < IPT; i++)
                     key[i] = s.keys[my_off + i * 32];
-#pragma unroll
-                for (int i = 0; i < IPT; i++)
+                // A digit shared by the whole warp would be a 32-way same-address atomic.  Probe the first
+                // key: a warp that looks skewed checks every key and counts warp-uniform digits once.
+                const uint32_t d_first = (key[0] >> shift) & mask;
+                if (__all_sync(k_full_mask, d_first == __shfl_sync(k_full_mask, d_first, 0)))
                 {
-                    const uint32_t d = (key[i] >> shift) & mask;
-                    // a digit shared by the whole warp would be a 32-way same-address atomic: count it once
-                    if (__all_sync(k_full_mask, d == __shfl_sync(k_full_mask, d, 0)))
+#pragma unroll
+                    for (int i = 0; i < IPT; i++)
                     {
-                        if (lane == 0)
-                            wh[d] += 32;
+                        const uint32_t d = (key[i] >> shift) & mask;
+                        if (__all_sync(k_full_mask, d == __shfl_sync(k_full_mask, d, 0)))
+                        {
+                            if (lane == 0)
+                                wh[d] += 32;
+                        }
+                        else
+                            atomicAdd(&wh[d], 1u);
                     }
-                    else
-                        atomicAdd(&wh[d], 1u);
+                }
+                else
+                {
+#pragma unroll
+                    for (int i = 0; i < IPT; i++)
+                        atomicAdd(&wh[(key[i] >> shift) & mask], 1u);
                 }
             }
             __syncthreads(); // every key is in registers; the counts are final
@@ -397,35 +408,11 @@ namespace glu_b200
 
             uint32_t rank2[IPT / 2]; // two 16-bit tile-sorted slots per register
             {
-                // ---- rank + scatter keys (in place)
-                const uint32_t lt = lanemask_lt();
-#pragma unroll
-                for (int i = 0; i < IPT; i++)
-                {
-                    const uint32_t d = (key[i] >> shift) & mask;
-                    const uint32_t peers = match_digit<MODE>(d);
-                    const uint32_t before = wh[d];
-                    __syncwarp();
-                    wh[d] = before + __popc(peers); // every peer stores the same value
-                    __syncwarp();
-                    const uint32_t r = before + __popc(peers & lt);
-                    s.keys[r] = key[i];
-                    if (i & 1)
-                        rank2[i / 2] |= r << 16;
-                    else
-                        rank2[i / 2] = r;
-                }
-                // ---- values: staging buffer -> registers (the key registers are dead now)
-                if (use_tma)
-                    mbarrier_wait(&s.bar_vals, 0);
-                uint32_t val[IPT];
-#pragma unroll
-                for (int i = 0; i < IPT; i++)
-                    val[i] = s.vals[my_off + i * 32];
-
                 // ---- decoupled look-back (one thread per digit): this digit's count in all earlier tiles.
-                // k_lb_rows predecessor rows are fetched per round trip (independent loads), then folded
-                // in order; rows before tile 0 read as "inclusive 0" and end the walk.
+                // Done EARLY — right after this tile's own count went out and before any ranking — so the
+                // inclusive prefix of every tile follows its count by one short walk; that keeps everyone's
+                // walk short.  k_lb_rows predecessor rows are fetched per round trip (independent loads),
+                // then folded in order; rows before tile 0 read as "inclusive 0" and end the walk.
                 if (tid < k_radix)
                 {
                     uint32_t exclusive = 0;
@@ -459,6 +446,32 @@ namespace glu_b200
                     }
                     s.gbase[tid] = digit_offset[tid] + exclusive - s.tile_start[tid];
                 }
+                // ---- rank + scatter keys (in place)
+                const uint32_t lt = lanemask_lt();
+#pragma unroll
+                for (int i = 0; i < IPT; i++)
+                {
+                    const uint32_t d = (key[i] >> shift) & mask;
+                    const uint32_t peers = match_digit<MODE>(d);
+                    const uint32_t before = wh[d];
+                    __syncwarp();
+                    wh[d] = before + __popc(peers); // every peer stores the same value
+                    __syncwarp();
+                    const uint32_t r = before + __popc(peers & lt);
+                    s.keys[r] = key[i];
+                    if (i & 1)
+                        rank2[i / 2] |= r << 16;
+                    else
+                        rank2[i / 2] = r;
+                }
+                // ---- values: staging buffer -> registers (the key registers are dead now)
+                if (use_tma)
+                    mbarrier_wait(&s.bar_vals, 0);
+                uint32_t val[IPT];
+#pragma unroll
+                for (int i = 0; i < IPT; i++)
+                    val[i] = s.vals[my_off + i * 32];
+
                 __syncthreads(); // all values are in registers
 #pragma unroll
                 for (int i = 0; i < IPT; i += 2)
@@ -470,17 +483,27 @@ namespace glu_b200
             __syncthreads(); // tile-sorted keys and values, gbase
 
             // ---- out: consecutive threads write consecutive addresses inside each digit run
-#pragma unroll
-            for (int k = 0; k < (TILE + THREADS - 1) / THREADS; k++)
+            if (full)
             {
-                const uint32_t p = tid + k * THREADS;
-                if (p < valid)
+#pragma unroll
+                for (int k = 0; k < IPT; k++)
                 {
+                    const uint32_t p = tid + k * THREADS;
                     const uint32_t kk = s.keys[p];
                     const uint32_t vv = s.vals[p];
                     const uint32_t dst = s.gbase[(kk >> shift) & mask] + p;
                     keys_out[dst] = kk;
                     vals_out[dst] = vv;
+                }
+            }
+            else
+            {
+                for (uint32_t p = tid; p < valid; p += THREADS)
+                {
+                    const uint32_t kk = s.keys[p];
+                    const uint32_t dst = s.gbase[(kk >> shift) & mask] + p;
+                    keys_out[dst] = kk;
+                    vals_out[dst] = s.vals[p];
                 }
             }
         }
