@@ -32,7 +32,7 @@ namespace glu_b200
         constexpr uint32_t k_lb_inclusive = 2u << 30; // inclusive prefix over tiles 0..t published
         constexpr uint32_t k_lb_value_mask = (1u << 30) - 1u;
         constexpr size_t k_max_count = size_t(1) << 30;
-        constexpr int k_lb_rows = 4;   // look-back rows requested per ranking iteration per digit thread
+        constexpr int k_lb_rows = 8;   // look-back rows in flight per digit thread
 
         struct PassPlan
         {
@@ -408,57 +408,11 @@ namespace glu_b200
 
             uint32_t rank2[IPT / 2]; // two 16-bit tile-sorted slots per register
             {
-                // ---- decoupled look-back (one thread per digit): this digit's count in all earlier tiles,
-                // INTERLEAVED with the ranking loop below.  Every iteration the digit threads fold the
-                // k_lb_rows predecessor rows they requested one iteration earlier and request the next
-                // ones, so the L2 round trips of the walk hide behind ranking work; a row that is not
-                // published yet simply ends the round (it is requested again), nothing spins until the
-                // loop is over.  Rows before tile 0 read as "inclusive 0" and end the walk.
-                const bool lb_thread = tid < k_radix;
-                uint32_t exclusive = 0;
-                int lb_row = int(tile) - 1; // next predecessor row to fold
-                bool lb_done = !lb_thread || tile == 0;
-                uint32_t lb_w[k_lb_rows];
-                const uint32_t* lb_col = lookback + tid;
-#pragma unroll
-                for (int j = 0; j < k_lb_rows; j++)
-                    lb_w[j] = 0;
-
                 // ---- rank + scatter keys (in place)
                 const uint32_t lt = lanemask_lt();
 #pragma unroll
                 for (int i = 0; i < IPT; i++)
                 {
-                    if (warp < k_radix / 32) // warp-uniform: the digit threads' warps
-                    {
-                        if (i > 0 && !lb_done)
-                        {
-                            bool blocked = false;
-#pragma unroll
-                            for (int j = 0; j < k_lb_rows; j++)
-                            {
-                                const uint32_t x = lb_w[j];
-                                if (!lb_done && !blocked)
-                                {
-                                    if ((x & ~k_lb_value_mask) == 0)
-                                        blocked = true; // not published yet: ask again next round
-                                    else
-                                    {
-                                        exclusive += x & k_lb_value_mask;
-                                        lb_done = (x & k_lb_inclusive) != 0;
-                                        lb_row--;
-                                    }
-                                }
-                            }
-                        }
-                        if (!lb_done)
-                        {
-#pragma unroll
-                            for (int j = 0; j < k_lb_rows; j++)
-                                lb_w[j] = lb_row - j >= 0 ? ld_relaxed_u32(lb_col + size_t(lb_row - j) * k_radix)
-                                                          : k_lb_inclusive;
-                        }
-                    }
                     const uint32_t d = (key[i] >> shift) & mask;
                     const uint32_t peers = match_digit<MODE>(d);
                     const uint32_t before = wh[d];
@@ -480,36 +434,38 @@ namespace glu_b200
                 for (int i = 0; i < IPT; i++)
                     val[i] = s.vals[my_off + i * 32];
 
-                // ---- finish the walk (the last requested rows are still pending), now blocking
-                if (lb_thread)
+                // ---- decoupled look-back (one thread per digit): this digit's count in all earlier tiles.
+                // k_lb_rows predecessor rows are fetched per round trip (independent loads), then folded
+                // in order; rows before tile 0 read as "inclusive 0" and end the walk.  (Placement and
+                // shape were measured: walking right after the count went out, a dedicated look-back
+                // warp, and a walk interleaved with the ranking loop were all slower — DESIGN.md.)
+                if (tid < k_radix)
                 {
+                    uint32_t exclusive = 0;
                     if (tile > 0)
                     {
-                        bool first = true;
-                        while (!lb_done)
+                        const uint32_t* col = lookback + tid;
+                        int t = int(tile) - 1;
+                        bool done = false;
+                        while (!done)
                         {
-                            if (!first)
-                            {
+                            uint32_t w[k_lb_rows];
 #pragma unroll
-                                for (int j = 0; j < k_lb_rows; j++)
-                                    lb_w[j] = lb_row - j >= 0 ? ld_relaxed_u32(lb_col + size_t(lb_row - j) * k_radix)
-                                                              : k_lb_inclusive;
-                            }
-                            first = false;
-                            const int base_row = lb_row;
+                            for (int j = 0; j < k_lb_rows; j++)
+                                w[j] = t - j >= 0 ? ld_relaxed_u32(col + size_t(t - j) * k_radix) : k_lb_inclusive;
 #pragma unroll
                             for (int j = 0; j < k_lb_rows; j++)
                             {
-                                if (!lb_done)
+                                if (!done)
                                 {
-                                    uint32_t x = lb_w[j];
+                                    uint32_t x = w[j];
                                     while ((x & ~k_lb_value_mask) == 0) // predecessor has not published yet
-                                        x = ld_relaxed_u32(lb_col + size_t(base_row - j) * k_radix);
+                                        x = ld_relaxed_u32(col + size_t(t - j) * k_radix);
                                     exclusive += x & k_lb_value_mask;
-                                    lb_done = (x & k_lb_inclusive) != 0;
-                                    lb_row--;
+                                    done = (x & k_lb_inclusive) != 0;
                                 }
                             }
+                            t -= k_lb_rows;
                         }
                         st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid],
                                        k_lb_inclusive | ((exclusive + s.tile_count[tid]) & k_lb_value_mask));
