@@ -171,6 +171,14 @@ namespace glu_b200
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                      : "memory");
     }
+    __device__ __forceinline__ void mbarrier_arrive(uint64_t* bar)
+    {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    }
+    __device__ __forceinline__ void named_barrier_sync(int id, int threads)
+    {
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+    }
     __device__ __forceinline__ void mbarrier_wait(uint64_t* bar, uint32_t parity)
     {
         asm volatile("{\n"

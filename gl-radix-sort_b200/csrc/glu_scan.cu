@@ -265,6 +265,255 @@ namespace glu_b200
             }
         }
 
+        // ------------------------------------------------------- 4-byte element types, persistent + TMA
+        //
+        // The one-tile-per-CTA kernel above is latency bound on B200: while a CTA waits for its
+        // predecessors (look-back) it has no loads in flight, and two resident CTAs per SM cannot cover
+        // that.  This variant keeps HBM busy regardless: a grid of resident CTAs, each with a producer
+        // warp that takes tile tickets and streams whole tiles into a ring of shared-memory stages with
+        // cp.async.bulk (TMA), completion signalled on mbarriers; the consumer warps pull a stage into
+        // registers (LDS.128), hand the stage back, scan, look back, and store straight from registers.
+        // Loads of the next STAGES-1 tiles are always in flight while the consumers sit in a look-back.
+        // Tiles are consumed by a CTA in ticket order, so forward progress holds as before.  Partial or
+        // 16-byte-misaligned tiles bypass the ring (guarded loads from global memory).
+        template<typename T, int THREADS, int VPT, int STAGES>
+        __global__ void __launch_bounds__(THREADS + 32)
+            scan_b32_tma_kernel(T* __restrict__ data, size_t count, uint32_t tiles_per_part, uint32_t total_tiles,
+                                uint32_t* ticket, uint64_t* state)
+        {
+            constexpr int TILE = THREADS * VPT * 4;
+            constexpr int WARPS = THREADS / 32; // consumer warps; warp WARPS is the producer
+            constexpr int WARP_ELEMS = VPT * 128;
+            static_assert(WARPS <= 32, "one warp scans the warp totals");
+
+            extern __shared__ __align__(128) unsigned char smem_raw[];
+            T* ring = reinterpret_cast<T*>(smem_raw); // [STAGES][TILE]
+            __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
+            __shared__ uint32_t s_stage_tile[STAGES], s_stage_staged[STAGES];
+            __shared__ T s_warp_total[WARPS];
+            __shared__ T s_warp_prefix[WARPS];
+            __shared__ T s_tile_prefix;
+
+            const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            if (threadIdx.x == 0)
+            {
+                for (int i = 0; i < STAGES; i++)
+                {
+                    mbarrier_init(&full_bar[i], 1);
+                    mbarrier_init(&empty_bar[i], WARPS);
+                }
+                mbarrier_init_fence();
+            }
+            __syncthreads();
+
+            if (warp == WARPS)
+            {
+                // ---- producer: one lane
+                if (lane == 0)
+                {
+                    const uint64_t policy = l2_policy_evict_first();
+                    for (uint32_t it = 0;; it++)
+                    {
+                        const uint32_t stage = it % STAGES;
+                        if (it >= STAGES)
+                            mbarrier_wait(&empty_bar[stage], ((it / STAGES) & 1) ^ 1);
+                        const uint32_t tile = atomicAdd(ticket, 1u);
+                        s_stage_tile[stage] = tile;
+                        if (tile >= total_tiles)
+                        {
+                            mbarrier_arrive(&full_bar[stage]);
+                            break;
+                        }
+                        const uint32_t part = tile / tiles_per_part;
+                        const uint32_t tp = tile - part * tiles_per_part;
+                        const size_t in_part = size_t(tp) * TILE;
+                        const size_t base = size_t(part) * count + in_part;
+                        const bool staged =
+                            count - in_part >= size_t(TILE) && (reinterpret_cast<uintptr_t>(data + base) & 15) == 0;
+                        s_stage_staged[stage] = staged ? 1u : 0u;
+                        if (staged)
+                        {
+                            mbarrier_arrive_expect_tx(&full_bar[stage], TILE * 4);
+                            tma_load_1d(ring + size_t(stage) * TILE, data + base, TILE * 4, &full_bar[stage], policy);
+                        }
+                        else
+                            mbarrier_arrive(&full_bar[stage]);
+                    }
+                }
+                return;
+            }
+
+            // ---- consumers
+            for (uint32_t it = 0;; it++)
+            {
+                const uint32_t stage = it % STAGES;
+                mbarrier_wait(&full_bar[stage], (it / STAGES) & 1);
+                const uint32_t tile = s_stage_tile[stage];
+                if (tile >= total_tiles)
+                    break;
+                const bool staged = s_stage_staged[stage] != 0;
+                const uint32_t part = tile / tiles_per_part;
+                const uint32_t tp = tile - part * tiles_per_part;
+                const size_t in_part = size_t(tp) * TILE;
+                const size_t base = size_t(part) * count + in_part;
+                const uint32_t valid = uint32_t(count - in_part < size_t(TILE) ? count - in_part : size_t(TILE));
+                const uint32_t my_off = warp * WARP_ELEMS + lane * 4; // + j * 128
+
+                T x[VPT][4];
+                if (staged)
+                {
+                    const T* src = ring + size_t(stage) * TILE + my_off;
+#pragma unroll
+                    for (int j = 0; j < VPT; j++)
+                    {
+                        const uint4 r = *reinterpret_cast<const uint4*>(src + j * 128);
+                        x[j][0] = from_bits<T>(r.x);
+                        x[j][1] = from_bits<T>(r.y);
+                        x[j][2] = from_bits<T>(r.z);
+                        x[j][3] = from_bits<T>(r.w);
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int j = 0; j < VPT; j++)
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+                        {
+                            const uint32_t idx = my_off + j * 128 + c;
+                            x[j][c] = idx < valid ? data[base + idx] : T(0);
+                        }
+                }
+                __syncwarp();
+                if (lane == 0)
+                    mbarrier_arrive(&empty_bar[stage]); // this warp no longer needs the stage
+
+                T sum4[VPT], inc[VPT], ex[VPT];
+#pragma unroll
+                for (int j = 0; j < VPT; j++)
+                    inc[j] = sum4[j] = x[j][0] + x[j][1] + x[j][2] + x[j][3];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+                    for (int j = 0; j < VPT; j++)
+                    {
+                        T t = __shfl_up_sync(k_full_mask, inc[j], o);
+                        if (lane >= unsigned(o))
+                            inc[j] += t;
+                    }
+                T chunk_base = T(0);
+#pragma unroll
+                for (int j = 0; j < VPT; j++)
+                {
+                    T total = __shfl_sync(k_full_mask, inc[j], 31);
+                    T lane_ex;
+                    if (is_float_type<T>::value)
+                    {
+                        lane_ex = __shfl_up_sync(k_full_mask, inc[j], 1);
+                        if (lane == 0)
+                            lane_ex = T(0);
+                    }
+                    else
+                        lane_ex = inc[j] - sum4[j];
+                    ex[j] = chunk_base + lane_ex;
+                    chunk_base += total;
+                }
+                if (lane == 0)
+                    s_warp_total[warp] = chunk_base;
+                named_barrier_sync(1, THREADS);
+
+                if (warp == 0)
+                {
+                    T wt = lane < WARPS ? s_warp_total[lane] : T(0);
+                    T winc = warp_inclusive_scan(wt, lane);
+                    T wex = __shfl_up_sync(k_full_mask, winc, 1);
+                    if (lane == 0)
+                        wex = T(0);
+                    if (lane < WARPS)
+                        s_warp_prefix[lane] = wex;
+                    const T aggregate = __shfl_sync(k_full_mask, winc, 31);
+
+                    T exclusive = T(0);
+                    if (tp == 0)
+                    {
+                        if (lane == 0)
+                            st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(aggregate));
+                    }
+                    else
+                    {
+                        if (lane == 0)
+                            st_relaxed_u64(&state[tile], k_flag_aggregate | to_bits<T>(aggregate));
+                        uint32_t remaining = tp;
+                        uint32_t pred = tile - 1;
+                        while (true)
+                        {
+                            const bool in_range = lane < remaining;
+                            uint64_t w;
+                            uint32_t inclusive_mask;
+                            while (true)
+                            {
+                                w = in_range ? ld_relaxed_u64(&state[pred - lane]) : k_flag_inclusive;
+                                const uint32_t flag = uint32_t(w >> 32);
+                                const uint32_t empty_mask = __ballot_sync(k_full_mask, flag == 0);
+                                inclusive_mask = __ballot_sync(k_full_mask, flag == 2);
+                                const uint32_t need =
+                                    inclusive_mask ? ((2u << (__ffs(inclusive_mask) - 1)) - 1u) : k_full_mask;
+                                if ((empty_mask & need) == 0)
+                                    break;
+                            }
+                            const uint32_t first = inclusive_mask ? uint32_t(__ffs(inclusive_mask) - 1) : 31u;
+                            T contrib = lane <= first ? from_bits<T>(uint32_t(w)) : T(0);
+                            exclusive += warp_sum(contrib);
+                            if (inclusive_mask)
+                                break;
+                            pred -= 32;
+                            remaining -= 32;
+                        }
+                        if (lane == 0)
+                            st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(exclusive + aggregate));
+                    }
+                    if (lane == 0)
+                        s_tile_prefix = exclusive;
+                }
+                named_barrier_sync(1, THREADS);
+
+                const T prefix = s_tile_prefix + s_warp_prefix[warp];
+                if (staged)
+                {
+#pragma unroll
+                    for (int j = 0; j < VPT; j++)
+                    {
+                        T b = prefix + ex[j];
+                        uint4 r;
+                        r.x = to_bits<T>(b);
+                        b += x[j][0];
+                        r.y = to_bits<T>(b);
+                        b += x[j][1];
+                        r.z = to_bits<T>(b);
+                        b += x[j][2];
+                        r.w = to_bits<T>(b);
+                        st_stream_v4(data + base + my_off + j * 128, r);
+                    }
+                }
+                else
+                {
+#pragma unroll
+                    for (int j = 0; j < VPT; j++)
+                    {
+                        T b = prefix + ex[j];
+#pragma unroll
+                        for (int c = 0; c < 4; c++)
+                        {
+                            const uint32_t idx = my_off + j * 128 + c;
+                            if (idx < valid)
+                                data[base + idx] = b;
+                            b += x[j][c];
+                        }
+                    }
+                }
+            }
+        }
+
         // ------------------------------------------------------------------------ wide element types
         template<typename S, int NC> struct alignas(sizeof(S) * NC) Elem
         {
@@ -476,8 +725,12 @@ namespace glu_b200
             int threads, per_thread; // per_thread: 16-byte vectors (4-byte types) or elements (wide types)
         };
         // 4-byte element types: {threads, vectors per thread}; tile = threads * vpt * 4 elements
-        constexpr ScanShape k_b32_shapes[] = {{256, 4}, {64, 2}, {512, 4}, {512, 8}, {1024, 4}, {256, 8}};
-        constexpr int k_b32_default = 0, k_b32_small = 1, k_num_b32_shapes = 6;
+        // ids 0..5: one tile per CTA;  ids 6..: persistent TMA-pipelined kernel (threads exclude the producer warp)
+        constexpr ScanShape k_b32_shapes[] = {{256, 4}, {64, 2},  {512, 4}, {512, 8}, {1024, 4}, {256, 8},
+                                              {256, 8}, {512, 8}, {256, 8}, {512, 4}, {256, 4},  {512, 8}};
+        constexpr int k_b32_stages[] = {0, 0, 0, 0, 0, 0, 3, 3, 2, 3, 4, 2};
+        constexpr int k_b32_default = 3, k_b32_small = 1, k_num_b32_shapes = 12;
+        constexpr size_t k_persistent_min_elems = size_t(1) << 22; // below this the simple kernel is as good
         constexpr int k_wide_threads = 256, k_wide_ipt = 4; // 1024-element tiles
         constexpr int k_wide_small_threads = 64, k_wide_small_ipt = 2;
 
@@ -501,6 +754,10 @@ namespace glu_b200
             else
             {
                 big_variant = (forced >= 0 && forced < k_num_b32_shapes && forced != k_b32_small) ? forced : k_b32_default;
+                static const size_t persistent_min =
+                    size_t(scan_env_int("GLU_SCAN_PERSISTENT_MIN", int(k_persistent_min_elems)));
+                if (k_b32_stages[big_variant] > 0 && count * num_partitions < persistent_min)
+                    big_variant = 3;
                 big = k_b32_shapes[big_variant].threads * k_b32_shapes[big_variant].per_thread * 4;
                 small = k_b32_shapes[k_b32_small].threads * k_b32_shapes[k_b32_small].per_thread * 4;
             }
@@ -536,6 +793,31 @@ namespace glu_b200
             return GLU_SUCCESS;
         }
 
+        template<typename T, int THREADS, int VPT, int STAGES>
+        int launch_b32_tma(T* data, size_t count, const ScanPlan& p, uint32_t* ticket, uint64_t* state, cudaStream_t s)
+        {
+            auto kernel = scan_b32_tma_kernel<T, THREADS, VPT, STAGES>;
+            constexpr size_t smem = size_t(STAGES) * THREADS * VPT * 16;
+            static bool configured[64] = {};
+            static int ctas_per_sm[64] = {};
+            int dev = 0;
+            GLU_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev >= 64)
+                return GLU_ERROR_INVALID_ARGUMENT;
+            if (!configured[dev])
+            {
+                GLU_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+                GLU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[dev], kernel, THREADS + 32, smem));
+                configured[dev] = true;
+            }
+            const uint64_t resident = uint64_t(current_sm_count()) * uint64_t(ctas_per_sm[dev] > 0 ? ctas_per_sm[dev] : 1);
+            const unsigned grid = unsigned(p.total_tiles < resident ? p.total_tiles : resident);
+            ScopedKernelProfile prof(GLU_KERNEL_SCAN, s);
+            kernel<<<grid, THREADS + 32, smem, s>>>(data, count, p.tiles_per_part, uint32_t(p.total_tiles), ticket, state);
+            GLU_LAUNCH_CHECK();
+            return GLU_SUCCESS;
+        }
+
         template<typename T>
         int launch_b32(void* d_data, size_t count, const ScanPlan& p, void* d_tmp, cudaStream_t s)
         {
@@ -550,7 +832,13 @@ namespace glu_b200
             case 2: return launch_b32_shape<T, 512, 4, 1>(data, count, p, ticket, state, s);
             case 3: return launch_b32_shape<T, 512, 8, 2>(data, count, p, ticket, state, s);
             case 4: return launch_b32_shape<T, 1024, 4, 2>(data, count, p, ticket, state, s);
-            default: return launch_b32_shape<T, 256, 8, 4>(data, count, p, ticket, state, s);
+            case 5: return launch_b32_shape<T, 256, 8, 4>(data, count, p, ticket, state, s);
+            case 6: return launch_b32_tma<T, 256, 8, 3>(data, count, p, ticket, state, s);
+            case 7: return launch_b32_tma<T, 512, 8, 3>(data, count, p, ticket, state, s);
+            case 8: return launch_b32_tma<T, 256, 8, 2>(data, count, p, ticket, state, s);
+            case 9: return launch_b32_tma<T, 512, 4, 3>(data, count, p, ticket, state, s);
+            case 10: return launch_b32_tma<T, 256, 4, 4>(data, count, p, ticket, state, s);
+            default: return launch_b32_tma<T, 512, 8, 2>(data, count, p, ticket, state, s);
             }
         }
 
