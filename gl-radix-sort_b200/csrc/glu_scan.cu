@@ -81,7 +81,7 @@ namespace glu_b200
         template<typename T, int THREADS, int VPT, int MIN_BLOCKS, bool TICKET>
         __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             scan_b32_kernel(T* __restrict__ data, size_t count, uint32_t tiles_per_part, uint32_t* ticket,
-                            uint64_t* state)
+                            uint64_t* state, int debug_no_lookback)
         {
             constexpr int TILE = THREADS * VPT * 4;
             constexpr int WARPS = THREADS / 32;
@@ -183,7 +183,7 @@ namespace glu_b200
                 const T aggregate = __shfl_sync(k_full_mask, winc, 31);
 
                 T exclusive = T(0);
-                if (tp == 0)
+                if (tp == 0 || debug_no_lookback) // debug_no_lookback: timing experiments only (wrong results)
                 {
                     if (lane == 0)
                         st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(aggregate));
@@ -265,34 +265,77 @@ namespace glu_b200
             }
         }
 
-        // ------------------------------------------------------- 4-byte element types, persistent + TMA
+        // Decoupled look-back over `state`, one warp: returns the sum of all earlier tiles of the
+        // partition (tp of them), 32 predecessors per round trip; lanes past the partition start act as
+        // an inclusive prefix of 0, which ends the walk.
+        template<typename T>
+        __device__ __forceinline__ T lookback_walk(const uint64_t* state, uint32_t tile, uint32_t tp, unsigned lane)
+        {
+            T exclusive = T(0);
+            uint32_t remaining = tp;
+            uint32_t pred = tile - 1;
+            while (true)
+            {
+                const bool in_range = lane < remaining;
+                uint64_t w;
+                uint32_t inclusive_mask;
+                while (true)
+                {
+                    w = in_range ? ld_relaxed_u64(&state[pred - lane]) : k_flag_inclusive;
+                    const uint32_t flag = uint32_t(w >> 32);
+                    const uint32_t empty_mask = __ballot_sync(k_full_mask, flag == 0);
+                    inclusive_mask = __ballot_sync(k_full_mask, flag == 2);
+                    // only the lanes up to the first inclusive prefix matter
+                    const uint32_t need = inclusive_mask ? ((2u << (__ffs(inclusive_mask) - 1)) - 1u) : k_full_mask;
+                    if ((empty_mask & need) == 0)
+                        break;
+                }
+                const uint32_t first = inclusive_mask ? uint32_t(__ffs(inclusive_mask) - 1) : 31u;
+                T contrib = lane <= first ? from_bits<T>(uint32_t(w)) : T(0);
+                exclusive += warp_sum(contrib);
+                if (inclusive_mask)
+                    break;
+                pred -= 32;
+                remaining -= 32;
+            }
+            return exclusive;
+        }
+
+        // ------------------------------------------- 4-byte element types: persistent, TMA, chain warps
         //
-        // The one-tile-per-CTA kernel above is latency bound on B200: while a CTA waits for its
-        // predecessors (look-back) it has no loads in flight, and two resident CTAs per SM cannot cover
-        // that.  This variant keeps HBM busy regardless: a grid of resident CTAs, each with a producer
-        // warp that takes tile tickets and streams whole tiles into a ring of shared-memory stages with
-        // cp.async.bulk (TMA), completion signalled on mbarriers; the consumer warps pull a stage into
-        // registers (LDS.128), hand the stage back, scan, look back, and store straight from registers.
-        // Loads of the next STAGES-1 tiles are always in flight while the consumers sit in a look-back.
-        // Tiles are consumed by a CTA in ticket order, so forward progress holds as before.  Partial or
-        // 16-byte-misaligned tiles bypass the ring (guarded loads from global memory).
+        // Measured on B200 the one-tile-per-CTA kernel above runs at 6.8 TB/s when the look-back
+        // dependency is cut (GLU_SCAN_DEBUG_NO_LOOKBACK) and at 3.6 TB/s with it: every CTA sits idle,
+        // with no loads in flight, while it waits for its predecessors.  This kernel takes the chain off
+        // the data path with warp specialisation inside resident CTAs:
+        //   * a PRODUCER lane takes tile tickets and streams whole tiles into a ring of shared-memory
+        //     stages with cp.async.bulk (TMA), completion on an mbarrier per stage;
+        //   * CHAIN warps (alternating tiles) reduce a stage the moment it lands, publish the tile
+        //     aggregate, run the look-back right away and publish the inclusive prefix — the whole
+        //     inter-tile chain advances at data-arrival time and never waits for the heavy work;
+        //   * SCANNER warps pull the stage into registers (LDS.128), scan it with shuffles, pick up the
+        //     tile's exclusive prefix from the chain warp and store straight from registers.
+        // Tiles are consumed by a CTA in ticket order, so forward progress holds as before.  A partial
+        // tile bypasses the ring (guarded loads from global memory).
         template<typename T, int THREADS, int VPT, int STAGES>
-        __global__ void __launch_bounds__(THREADS + 32)
+        __global__ void __launch_bounds__(THREADS + 96)
             scan_b32_tma_kernel(T* __restrict__ data, size_t count, uint32_t tiles_per_part, uint32_t total_tiles,
                                 uint32_t* ticket, uint64_t* state)
         {
             constexpr int TILE = THREADS * VPT * 4;
-            constexpr int WARPS = THREADS / 32; // consumer warps; warp WARPS is the producer
+            constexpr int WARPS = THREADS / 32; // scanner warps; then 1 producer warp, then 2 chain warps
+            constexpr int CHAIN_WARPS = 2;
             constexpr int WARP_ELEMS = VPT * 128;
             static_assert(WARPS <= 32, "one warp scans the warp totals");
 
             extern __shared__ __align__(128) unsigned char smem_raw[];
             T* ring = reinterpret_cast<T*>(smem_raw); // [STAGES][TILE]
-            __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
+            // The prefix hand-off uses 2*STAGES slots: the chain warp of tile it+STAGES may finish before the
+            // scanners have picked up tile it's prefix (it only waits for them to have READ the stage).
+            constexpr int PSLOTS = 2 * STAGES;
+            __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], chain_bar[PSLOTS];
             __shared__ uint32_t s_stage_tile[STAGES], s_stage_staged[STAGES];
-            __shared__ T s_warp_total[WARPS];
-            __shared__ T s_warp_prefix[WARPS];
-            __shared__ T s_tile_prefix;
+            __shared__ T s_slot_prefix[PSLOTS];
+            __shared__ T s_warp_total[2][WARPS];
 
             const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
             if (threadIdx.x == 0)
@@ -300,8 +343,10 @@ namespace glu_b200
                 for (int i = 0; i < STAGES; i++)
                 {
                     mbarrier_init(&full_bar[i], 1);
-                    mbarrier_init(&empty_bar[i], WARPS);
+                    mbarrier_init(&empty_bar[i], WARPS + 1);
                 }
+                for (int i = 0; i < PSLOTS; i++)
+                    mbarrier_init(&chain_bar[i], 1);
                 mbarrier_init_fence();
             }
             __syncthreads();
@@ -343,11 +388,78 @@ namespace glu_b200
                 return;
             }
 
-            // ---- consumers
+            if (warp > WARPS)
+            {
+                // ---- chain warps: aggregate -> publish -> look back -> publish inclusive, per tile
+                const unsigned me = warp - WARPS - 1;
+                for (uint32_t it = 0;; it++)
+                {
+                    const uint32_t stage = it % STAGES;
+                    mbarrier_wait(&full_bar[stage], (it / STAGES) & 1);
+                    const uint32_t tile = s_stage_tile[stage];
+                    if (tile >= total_tiles)
+                        break;
+                    if (it % CHAIN_WARPS != me)
+                        continue;
+                    const uint32_t part = tile / tiles_per_part;
+                    const uint32_t tp = tile - part * tiles_per_part;
+                    T acc = T(0);
+                    if (s_stage_staged[stage])
+                    {
+                        const uint4* src = reinterpret_cast<const uint4*>(ring + size_t(stage) * TILE) + lane;
+                        T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+#pragma unroll 8
+                        for (int k = 0; k < TILE / 128; k++)
+                        {
+                            const uint4 r = src[k * 32];
+                            a0 += from_bits<T>(r.x);
+                            a1 += from_bits<T>(r.y);
+                            a2 += from_bits<T>(r.z);
+                            a3 += from_bits<T>(r.w);
+                        }
+                        acc = (a0 + a1) + (a2 + a3);
+                    }
+                    else
+                    {
+                        const size_t in_part = size_t(tp) * TILE;
+                        const size_t base = size_t(part) * count + in_part;
+                        const uint32_t valid = uint32_t(count - in_part < size_t(TILE) ? count - in_part : size_t(TILE));
+                        for (uint32_t idx = lane; idx < valid; idx += 32)
+                            acc += data[base + idx];
+                    }
+                    const T aggregate = warp_sum(acc);
+                    __syncwarp();
+                    if (lane == 0)
+                        mbarrier_arrive(&empty_bar[stage]); // done reading the stage
+                    T exclusive = T(0);
+                    if (tp == 0)
+                    {
+                        if (lane == 0)
+                            st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(aggregate));
+                    }
+                    else
+                    {
+                        if (lane == 0)
+                            st_relaxed_u64(&state[tile], k_flag_aggregate | to_bits<T>(aggregate));
+                        exclusive = lookback_walk<T>(state, tile, tp, lane);
+                        if (lane == 0)
+                            st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(exclusive + aggregate));
+                    }
+                    if (lane == 0)
+                    {
+                        s_slot_prefix[it % PSLOTS] = exclusive;
+                        mbarrier_arrive(&chain_bar[it % PSLOTS]);
+                    }
+                }
+                return;
+            }
+
+            // ---- scanner warps
             for (uint32_t it = 0;; it++)
             {
                 const uint32_t stage = it % STAGES;
-                mbarrier_wait(&full_bar[stage], (it / STAGES) & 1);
+                const uint32_t parity = (it / STAGES) & 1;
+                mbarrier_wait(&full_bar[stage], parity);
                 const uint32_t tile = s_stage_tile[stage];
                 if (tile >= total_tiles)
                     break;
@@ -418,66 +530,16 @@ namespace glu_b200
                     ex[j] = chunk_base + lane_ex;
                     chunk_base += total;
                 }
+                T* totals = s_warp_total[it & 1]; // double-buffered: one barrier per tile is enough
                 if (lane == 0)
-                    s_warp_total[warp] = chunk_base;
+                    totals[warp] = chunk_base;
                 named_barrier_sync(1, THREADS);
+                // every warp derives its own prefix from the warp totals (no second barrier)
+                T wt = lane < warp ? totals[lane] : T(0);
+                const T warp_prefix = warp_sum(wt);
 
-                if (warp == 0)
-                {
-                    T wt = lane < WARPS ? s_warp_total[lane] : T(0);
-                    T winc = warp_inclusive_scan(wt, lane);
-                    T wex = __shfl_up_sync(k_full_mask, winc, 1);
-                    if (lane == 0)
-                        wex = T(0);
-                    if (lane < WARPS)
-                        s_warp_prefix[lane] = wex;
-                    const T aggregate = __shfl_sync(k_full_mask, winc, 31);
-
-                    T exclusive = T(0);
-                    if (tp == 0)
-                    {
-                        if (lane == 0)
-                            st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(aggregate));
-                    }
-                    else
-                    {
-                        if (lane == 0)
-                            st_relaxed_u64(&state[tile], k_flag_aggregate | to_bits<T>(aggregate));
-                        uint32_t remaining = tp;
-                        uint32_t pred = tile - 1;
-                        while (true)
-                        {
-                            const bool in_range = lane < remaining;
-                            uint64_t w;
-                            uint32_t inclusive_mask;
-                            while (true)
-                            {
-                                w = in_range ? ld_relaxed_u64(&state[pred - lane]) : k_flag_inclusive;
-                                const uint32_t flag = uint32_t(w >> 32);
-                                const uint32_t empty_mask = __ballot_sync(k_full_mask, flag == 0);
-                                inclusive_mask = __ballot_sync(k_full_mask, flag == 2);
-                                const uint32_t need =
-                                    inclusive_mask ? ((2u << (__ffs(inclusive_mask) - 1)) - 1u) : k_full_mask;
-                                if ((empty_mask & need) == 0)
-                                    break;
-                            }
-                            const uint32_t first = inclusive_mask ? uint32_t(__ffs(inclusive_mask) - 1) : 31u;
-                            T contrib = lane <= first ? from_bits<T>(uint32_t(w)) : T(0);
-                            exclusive += warp_sum(contrib);
-                            if (inclusive_mask)
-                                break;
-                            pred -= 32;
-                            remaining -= 32;
-                        }
-                        if (lane == 0)
-                            st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(exclusive + aggregate));
-                    }
-                    if (lane == 0)
-                        s_tile_prefix = exclusive;
-                }
-                named_barrier_sync(1, THREADS);
-
-                const T prefix = s_tile_prefix + s_warp_prefix[warp];
+                mbarrier_wait(&chain_bar[it % PSLOTS], (it / PSLOTS) & 1); // the chain warp has the tile's prefix
+                const T prefix = s_slot_prefix[it % PSLOTS] + warp_prefix;
                 if (staged)
                 {
 #pragma unroll
@@ -782,13 +844,14 @@ namespace glu_b200
         int launch_b32_shape(T* data, size_t count, const ScanPlan& p, uint32_t* ticket, uint64_t* state, cudaStream_t s)
         {
             static const bool use_ticket = scan_env_int("GLU_SCAN_TICKET", 1) != 0;
+            static const int debug_no_lookback = scan_env_int("GLU_SCAN_DEBUG_NO_LOOKBACK", 0);
             ScopedKernelProfile prof(GLU_KERNEL_SCAN, s);
             if (use_ticket)
-                scan_b32_kernel<T, THREADS, VPT, MIN_BLOCKS, true>
-                    <<<unsigned(p.total_tiles), THREADS, 0, s>>>(data, count, p.tiles_per_part, ticket, state);
+                scan_b32_kernel<T, THREADS, VPT, MIN_BLOCKS, true><<<unsigned(p.total_tiles), THREADS, 0, s>>>(
+                    data, count, p.tiles_per_part, ticket, state, debug_no_lookback);
             else
-                scan_b32_kernel<T, THREADS, VPT, MIN_BLOCKS, false>
-                    <<<unsigned(p.total_tiles), THREADS, 0, s>>>(data, count, p.tiles_per_part, ticket, state);
+                scan_b32_kernel<T, THREADS, VPT, MIN_BLOCKS, false><<<unsigned(p.total_tiles), THREADS, 0, s>>>(
+                    data, count, p.tiles_per_part, ticket, state, debug_no_lookback);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
@@ -807,13 +870,13 @@ namespace glu_b200
             if (!configured[dev])
             {
                 GLU_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-                GLU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[dev], kernel, THREADS + 32, smem));
+                GLU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[dev], kernel, THREADS + 96, smem));
                 configured[dev] = true;
             }
             const uint64_t resident = uint64_t(current_sm_count()) * uint64_t(ctas_per_sm[dev] > 0 ? ctas_per_sm[dev] : 1);
             const unsigned grid = unsigned(p.total_tiles < resident ? p.total_tiles : resident);
             ScopedKernelProfile prof(GLU_KERNEL_SCAN, s);
-            kernel<<<grid, THREADS + 32, smem, s>>>(data, count, p.tiles_per_part, uint32_t(p.total_tiles), ticket, state);
+            kernel<<<grid, THREADS + 96, smem, s>>>(data, count, p.tiles_per_part, uint32_t(p.total_tiles), ticket, state);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
