@@ -309,21 +309,23 @@ namespace glu_b200
         // the data path with warp specialisation inside resident CTAs:
         //   * a PRODUCER lane takes tile tickets and streams whole tiles into a ring of shared-memory
         //     stages with cp.async.bulk (TMA), completion on an mbarrier per stage;
-        //   * CHAIN warps (alternating tiles) reduce a stage the moment it lands, publish the tile
-        //     aggregate, run the look-back right away and publish the inclusive prefix — the whole
-        //     inter-tile chain advances at data-arrival time and never waits for the heavy work;
+        //   * AGGREGATOR warps (alternating tiles) reduce a stage the moment it lands and publish the tile
+        //     aggregate — they never wait on another tile; a CHAIN warp walks the tiles in order, looks
+        //     back over aggregates that are already out, publishes the inclusive prefix and hands the
+        //     exclusive prefix to the scanners: the inter-tile chain advances at data-arrival time and
+        //     never waits for the heavy work (nor the heavy work for the chain, unless it catches up);
         //   * SCANNER warps pull the stage into registers (LDS.128), scan it with shuffles, pick up the
         //     tile's exclusive prefix from the chain warp and store straight from registers.
         // Tiles are consumed by a CTA in ticket order, so forward progress holds as before.  A partial
         // tile bypasses the ring (guarded loads from global memory).
         template<typename T, int THREADS, int VPT, int STAGES>
-        __global__ void __launch_bounds__(THREADS + 96)
+        __global__ void __launch_bounds__(THREADS + 128)
             scan_b32_tma_kernel(T* __restrict__ data, size_t count, uint32_t tiles_per_part, uint32_t total_tiles,
                                 uint32_t* ticket, uint64_t* state)
         {
             constexpr int TILE = THREADS * VPT * 4;
-            constexpr int WARPS = THREADS / 32; // scanner warps; then 1 producer warp, then 2 chain warps
-            constexpr int CHAIN_WARPS = 2;
+            constexpr int WARPS = THREADS / 32; // scanner warps; then 1 producer, 2 aggregator, 1 chain warp
+            constexpr int AGG_WARPS = 2;
             constexpr int WARP_ELEMS = VPT * 128;
             static_assert(WARPS <= 32, "one warp scans the warp totals");
 
@@ -332,9 +334,9 @@ namespace glu_b200
             // The prefix hand-off uses 2*STAGES slots: the chain warp of tile it+STAGES may finish before the
             // scanners have picked up tile it's prefix (it only waits for them to have READ the stage).
             constexpr int PSLOTS = 2 * STAGES;
-            __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], chain_bar[PSLOTS];
+            __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], agg_bar[PSLOTS], chain_bar[PSLOTS];
             __shared__ uint32_t s_stage_tile[STAGES], s_stage_staged[STAGES];
-            __shared__ T s_slot_prefix[PSLOTS];
+            __shared__ T s_slot_agg[PSLOTS], s_slot_prefix[PSLOTS];
             __shared__ T s_warp_total[2][WARPS];
 
             const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -346,7 +348,10 @@ namespace glu_b200
                     mbarrier_init(&empty_bar[i], WARPS + 1);
                 }
                 for (int i = 0; i < PSLOTS; i++)
+                {
+                    mbarrier_init(&agg_bar[i], 1);
                     mbarrier_init(&chain_bar[i], 1);
+                }
                 mbarrier_init_fence();
             }
             __syncthreads();
@@ -388,9 +393,11 @@ namespace glu_b200
                 return;
             }
 
-            if (warp > WARPS)
+            if (warp > WARPS && warp <= WARPS + AGG_WARPS)
             {
-                // ---- chain warps: aggregate -> publish -> look back -> publish inclusive, per tile
+                // ---- aggregator warps (alternating tiles): reduce the stage the moment it lands and publish
+                // the tile aggregate.  They never wait on other tiles, so every tile in flight anywhere on
+                // the GPU has its aggregate out as soon as its data is on chip.
                 const unsigned me = warp - WARPS - 1;
                 for (uint32_t it = 0;; it++)
                 {
@@ -399,7 +406,7 @@ namespace glu_b200
                     const uint32_t tile = s_stage_tile[stage];
                     if (tile >= total_tiles)
                         break;
-                    if (it % CHAIN_WARPS != me)
+                    if (it % AGG_WARPS != me)
                         continue;
                     const uint32_t part = tile / tiles_per_part;
                     const uint32_t tp = tile - part * tiles_per_part;
@@ -430,20 +437,37 @@ namespace glu_b200
                     const T aggregate = warp_sum(acc);
                     __syncwarp();
                     if (lane == 0)
+                    {
                         mbarrier_arrive(&empty_bar[stage]); // done reading the stage
-                    T exclusive = T(0);
-                    if (tp == 0)
-                    {
-                        if (lane == 0)
-                            st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(aggregate));
+                        st_relaxed_u64(&state[tile], (tp == 0 ? k_flag_inclusive : k_flag_aggregate) | to_bits<T>(aggregate));
+                        s_slot_agg[it % PSLOTS] = aggregate;
+                        mbarrier_arrive(&agg_bar[it % PSLOTS]);
                     }
-                    else
+                }
+                return;
+            }
+
+            if (warp > WARPS + AGG_WARPS)
+            {
+                // ---- chain warp: in tile order, look back, publish the inclusive prefix, hand the exclusive
+                // prefix to the scanners.  Its predecessors' aggregates are out long before it asks.
+                for (uint32_t it = 0;; it++)
+                {
+                    const uint32_t stage = it % STAGES;
+                    mbarrier_wait(&full_bar[stage], (it / STAGES) & 1);
+                    const uint32_t tile = s_stage_tile[stage];
+                    if (tile >= total_tiles)
+                        break;
+                    const uint32_t part = tile / tiles_per_part;
+                    const uint32_t tp = tile - part * tiles_per_part;
+                    T exclusive = T(0);
+                    if (tp != 0)
                     {
-                        if (lane == 0)
-                            st_relaxed_u64(&state[tile], k_flag_aggregate | to_bits<T>(aggregate));
                         exclusive = lookback_walk<T>(state, tile, tp, lane);
+                        mbarrier_wait(&agg_bar[it % PSLOTS], (it / PSLOTS) & 1);
                         if (lane == 0)
-                            st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(exclusive + aggregate));
+                            st_relaxed_u64(&state[tile],
+                                           k_flag_inclusive | to_bits<T>(exclusive + s_slot_agg[it % PSLOTS]));
                     }
                     if (lane == 0)
                     {
@@ -870,13 +894,13 @@ namespace glu_b200
             if (!configured[dev])
             {
                 GLU_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-                GLU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[dev], kernel, THREADS + 96, smem));
+                GLU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[dev], kernel, THREADS + 128, smem));
                 configured[dev] = true;
             }
             const uint64_t resident = uint64_t(current_sm_count()) * uint64_t(ctas_per_sm[dev] > 0 ? ctas_per_sm[dev] : 1);
             const unsigned grid = unsigned(p.total_tiles < resident ? p.total_tiles : resident);
             ScopedKernelProfile prof(GLU_KERNEL_SCAN, s);
-            kernel<<<grid, THREADS + 96, smem, s>>>(data, count, p.tiles_per_part, uint32_t(p.total_tiles), ticket, state);
+            kernel<<<grid, THREADS + 128, smem, s>>>(data, count, p.tiles_per_part, uint32_t(p.total_tiles), ticket, state);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
