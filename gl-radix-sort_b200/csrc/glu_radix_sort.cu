@@ -28,11 +28,11 @@ namespace glu_b200
     {
         constexpr int k_radix = 256;
         constexpr int k_max_passes = 4;
-        constexpr uint32_t k_lb_local = 1u << 30;     // tile-local digit count published
-        constexpr uint32_t k_lb_inclusive = 2u << 30; // inclusive prefix over tiles 0..t published
+        constexpr uint32_t k_lb_local = 1u << 30;     // counts row: tile-local digit count published (bits 0..29)
+        constexpr uint32_t k_lb_inclusive = 1u << 31; // prefix row: inclusive count over tiles 0..t (bits 0..30)
         constexpr uint32_t k_lb_value_mask = (1u << 30) - 1u;
         constexpr size_t k_max_count = size_t(1) << 30;
-        constexpr int k_lb_rows = 8;   // look-back rows in flight per digit thread
+        constexpr int k_chain_rows = 16; // count rows the chain CTA requests ahead
 
         struct PassPlan
         {
@@ -231,8 +231,7 @@ namespace glu_b200
         }
 #undef GLU_MATCH_BIT
 
-        constexpr int k_lb_threads = 0; // (dedicated look-back warps: tried, slower — the walk became the critical path)
-
+        
         template<int RANK_THREADS, int IPT> struct SweepSmem
         {
             static constexpr int WARPS = RANK_THREADS / 32; // ranking warps
@@ -241,7 +240,6 @@ namespace glu_b200
             alignas(128) uint32_t vals[TILE];   // TMA destination (input order), then tile-sorted values
             alignas(16) uint32_t warp_hist[WARPS][k_radix]; // per-warp digit counts, then running slot offsets
             uint32_t gbase[k_radix];            // global index of tile-sorted slot 0, per digit
-            uint32_t tile_count[k_radix];       // this tile's digit counts (real keys only)
             uint32_t tile_start[k_radix];       // first tile-sorted slot of each digit
             uint32_t scan[8];
             alignas(8) uint64_t bar_keys;       // mbarriers completed by the bulk copies
@@ -270,16 +268,16 @@ namespace glu_b200
         //      arrays goes to global[gbase[digit(key_p)] + p] — neighbouring threads, neighbouring
         //      addresses inside every digit run.
         template<int RANK_THREADS, int IPT, int MIN_BLOCKS, int MODE>
-        __global__ void __launch_bounds__(RANK_THREADS + k_lb_threads, MIN_BLOCKS)
+        __global__ void __launch_bounds__(RANK_THREADS, MIN_BLOCKS)
             onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                             uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
                             uint32_t shift, uint32_t mask, const uint32_t* __restrict__ digit_offset,
-                            uint32_t* lookback, uint32_t* ticket, int allow_tma)
+                            uint32_t* lookback, uint32_t* prefix, uint32_t* ticket, uint32_t num_tiles, int allow_tma)
         {
             static_assert(RANK_THREADS >= k_radix && RANK_THREADS % 32 == 0, "one ranking thread per digit");
             static_assert(IPT % 2 == 0, "ranks are packed two per register");
             using Smem = SweepSmem<RANK_THREADS, IPT>;
-            constexpr int THREADS = RANK_THREADS + k_lb_threads;
+            constexpr int THREADS = RANK_THREADS;
             constexpr int WARPS = Smem::WARPS;
             constexpr int TILE = Smem::TILE;
             constexpr int WARP_ELEMS = IPT * 32;
@@ -298,7 +296,38 @@ namespace glu_b200
             for (int i = tid; i < WARPS * k_radix / 4; i += THREADS)
                 reinterpret_cast<uint4*>(&s.warp_hist[0][0])[i] = make_uint4(0, 0, 0, 0);
             __syncthreads();
-            const uint32_t tile = s.tile;
+            if (s.tile == 0)
+            {
+                // ---- ticket 0 = the CHAIN CTA (the first CTA to run, hence resident before any tile exists).
+                // It turns the tiles' digit counts into running prefixes as a stream: one lane per digit,
+                // k_chain_rows rows requested ahead, rows folded strictly in tile order.  Tiles therefore
+                // never walk back over their predecessors: tile t reads ONE row, prefix[t - 1].
+                if (tid < k_radix)
+                {
+                    uint32_t running = 0;
+                    for (uint32_t t = 0; t < num_tiles; t += k_chain_rows)
+                    {
+                        uint32_t w[k_chain_rows];
+#pragma unroll
+                        for (int j = 0; j < k_chain_rows; j++)
+                            w[j] = t + j < num_tiles ? ld_relaxed_u32(lookback + size_t(t + j) * k_radix + tid) : 0u;
+#pragma unroll
+                        for (int j = 0; j < k_chain_rows; j++)
+                        {
+                            if (t + j < num_tiles)
+                            {
+                                uint32_t x = w[j];
+                                while ((x & k_lb_local) == 0) // tile t + j has not published its counts yet
+                                    x = ld_relaxed_u32(lookback + size_t(t + j) * k_radix + tid);
+                                running += x & k_lb_value_mask;
+                                st_relaxed_u32(prefix + size_t(t + j) * k_radix + tid, k_lb_inclusive | running);
+                            }
+                        }
+                    }
+                }
+                return;
+            }
+            const uint32_t tile = s.tile - 1;
             const uint32_t tile_base = tile * uint32_t(TILE);
             const uint32_t valid = n - tile_base < uint32_t(TILE) ? n - tile_base : uint32_t(TILE);
             const bool full = valid == uint32_t(TILE);
@@ -374,9 +403,7 @@ namespace glu_b200
                     total += s.warp_hist[w][tid];
                 // padding slots all carry digit `mask`
                 const uint32_t count_valid = total - (tid == mask ? uint32_t(TILE) - valid : 0u);
-                st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid],
-                               (tile == 0 ? k_lb_inclusive : k_lb_local) | count_valid);
-                s.tile_count[tid] = count_valid;
+                st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid], k_lb_local | count_valid);
                 inc = total;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1)
@@ -434,41 +461,17 @@ namespace glu_b200
                 for (int i = 0; i < IPT; i++)
                     val[i] = s.vals[my_off + i * 32];
 
-                // ---- decoupled look-back (one thread per digit): this digit's count in all earlier tiles.
-                // k_lb_rows predecessor rows are fetched per round trip (independent loads), then folded
-                // in order; rows before tile 0 read as "inclusive 0" and end the walk.  (Placement and
-                // shape were measured: walking right after the count went out, a dedicated look-back
-                // warp, and a walk interleaved with the ranking loop were all slower — DESIGN.md.)
+                // ---- this digit's count in all earlier tiles: one row, written by the chain CTA
                 if (tid < k_radix)
                 {
                     uint32_t exclusive = 0;
                     if (tile > 0)
                     {
-                        const uint32_t* col = lookback + tid;
-                        int t = int(tile) - 1;
-                        bool done = false;
-                        while (!done)
-                        {
-                            uint32_t w[k_lb_rows];
-#pragma unroll
-                            for (int j = 0; j < k_lb_rows; j++)
-                                w[j] = t - j >= 0 ? ld_relaxed_u32(col + size_t(t - j) * k_radix) : k_lb_inclusive;
-#pragma unroll
-                            for (int j = 0; j < k_lb_rows; j++)
-                            {
-                                if (!done)
-                                {
-                                    uint32_t x = w[j];
-                                    while ((x & ~k_lb_value_mask) == 0) // predecessor has not published yet
-                                        x = ld_relaxed_u32(col + size_t(t - j) * k_radix);
-                                    exclusive += x & k_lb_value_mask;
-                                    done = (x & k_lb_inclusive) != 0;
-                                }
-                            }
-                            t -= k_lb_rows;
-                        }
-                        st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid],
-                                       k_lb_inclusive | ((exclusive + s.tile_count[tid]) & k_lb_value_mask));
+                        const uint32_t* p = prefix + size_t(tile - 1) * k_radix + tid;
+                        uint32_t x = ld_relaxed_u32(p);
+                        while ((x & k_lb_inclusive) == 0)
+                            x = ld_relaxed_u32(p);
+                        exclusive = x & ~k_lb_inclusive;
                     }
                     s.gbase[tid] = digit_offset[tid] + exclusive - s.tile_start[tid];
                 }
@@ -573,7 +576,7 @@ namespace glu_b200
             l.tiles = (count + tile - 1) / tile;
             l.off_hist = k_tmp_align; // tickets live in [0, 256)
             l.off_lookback = l.off_hist + k_max_passes * k_radix * sizeof(uint32_t);
-            l.control_bytes = align_up(l.off_lookback + k_max_passes * l.tiles * k_radix * sizeof(uint32_t), k_tmp_align);
+            l.control_bytes = align_up(l.off_lookback + 2 * k_max_passes * l.tiles * k_radix * sizeof(uint32_t), k_tmp_align);
             l.off_keys = l.control_bytes;
             l.off_vals = l.off_keys + align_up(count * sizeof(uint32_t), k_tmp_align);
             l.total = l.off_vals + align_up(count * sizeof(uint32_t), k_tmp_align);
@@ -585,6 +588,8 @@ namespace glu_b200
                          uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback, uint32_t* ticket,
                          unsigned tiles, cudaStream_t s)
         {
+            // per pass: `tiles` count rows followed by `tiles` prefix rows; grid = tiles + the chain CTA
+            uint32_t* prefix = lookback + size_t(tiles) * k_radix;
             auto kernel = onesweep_kernel<THREADS, IPT, MIN_BLOCKS, MODE>;
             // TMA bulk copies need 16-byte aligned sources (tiles are multiples of 4 elements)
             const int allow_tma =
@@ -599,8 +604,8 @@ namespace glu_b200
                 configured[dev] = true;
             }
             ScopedKernelProfile prof(GLU_KERNEL_SORT_ONESWEEP, s);
-            kernel<<<tiles, THREADS + k_lb_threads, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback,
-                                                               ticket, allow_tma);
+            kernel<<<tiles + 1, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
+                                                    tiles, allow_tma);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
@@ -669,7 +674,7 @@ extern "C" int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t c
     const PassPlan plan = make_pass_plan(num_steps);
     const uint32_t n = uint32_t(count);
 
-    const size_t used_control = l.off_lookback + size_t(plan.num_passes) * l.tiles * k_radix * sizeof(uint32_t);
+    const size_t used_control = l.off_lookback + 2 * size_t(plan.num_passes) * l.tiles * k_radix * sizeof(uint32_t);
     GLU_CUDA_TRY(cudaMemsetAsync(tmp, 0, used_control, s));
 
     {
@@ -698,7 +703,7 @@ extern "C" int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t c
         const uint32_t* vi = vbuf[p & 1];
         uint32_t* ko = kbuf[(p + 1) & 1];
         uint32_t* vo = vbuf[(p + 1) & 1];
-        uint32_t* lb = lookback + size_t(p) * l.tiles * k_radix;
+        uint32_t* lb = lookback + 2 * size_t(p) * l.tiles * k_radix;
         int rc = mode == Rank_Ballot
                      ? dispatch_sweep<Rank_Ballot>(cfg, ki, vi, ko, vo, n, plan.shift[p], plan.mask[p],
                                                    hist + p * k_radix, lb, tickets + p, unsigned(l.tiles), s)

@@ -462,13 +462,12 @@ namespace glu_b200
                     const uint32_t tp = tile - part * tiles_per_part;
                     T exclusive = T(0);
                     if (tp != 0)
-                    {
                         exclusive = lookback_walk<T>(state, tile, tp, lane);
-                        mbarrier_wait(&agg_bar[it % PSLOTS], (it / PSLOTS) & 1);
-                        if (lane == 0)
-                            st_relaxed_u64(&state[tile],
-                                           k_flag_inclusive | to_bits<T>(exclusive + s_slot_agg[it % PSLOTS]));
-                    }
+                    // The aggregator must be done with the tile before the scanners may overwrite it in
+                    // global memory (an unstaged tile is reduced straight from global memory).
+                    mbarrier_wait(&agg_bar[it % PSLOTS], (it / PSLOTS) & 1);
+                    if (tp != 0 && lane == 0)
+                        st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(exclusive + s_slot_agg[it % PSLOTS]));
                     if (lane == 0)
                     {
                         s_slot_prefix[it % PSLOTS] = exclusive;
@@ -815,7 +814,7 @@ namespace glu_b200
         constexpr ScanShape k_b32_shapes[] = {{256, 4}, {64, 2},  {512, 4}, {512, 8}, {1024, 4}, {256, 8},
                                               {256, 8}, {512, 8}, {256, 8}, {512, 4}, {256, 4},  {512, 8}};
         constexpr int k_b32_stages[] = {0, 0, 0, 0, 0, 0, 3, 3, 2, 3, 4, 2};
-        constexpr int k_b32_default = 3, k_b32_small = 1, k_num_b32_shapes = 12;
+        constexpr int k_b32_default = 6, k_b32_simple = 3, k_b32_small = 1, k_num_b32_shapes = 12;
         constexpr size_t k_persistent_min_elems = size_t(1) << 22; // below this the simple kernel is as good
         constexpr int k_wide_threads = 256, k_wide_ipt = 4; // 1024-element tiles
         constexpr int k_wide_small_threads = 64, k_wide_small_ipt = 2;
@@ -826,9 +825,13 @@ namespace glu_b200
             return v && *v ? std::atoi(v) : fallback;
         }
 
-        ScanPlan make_plan(size_t count, size_t num_partitions, bool wide)
+        // `stageable`: the buffer is 16-byte aligned and so is every partition start, i.e. whole tiles can be
+        // TMA-staged.  Otherwise (and for small inputs) the one-tile-per-CTA kernel is used.
+        ScanPlan make_plan(size_t count, size_t num_partitions, bool wide, bool stageable)
         {
             static const int forced = scan_env_int("GLU_SCAN_CONFIG", -1); // tuning sweeps only
+            static const size_t persistent_min =
+                size_t(scan_env_int("GLU_SCAN_PERSISTENT_MIN", int(k_persistent_min_elems)));
             ScanPlan p;
             uint32_t big, small;
             int big_variant = 0;
@@ -840,10 +843,8 @@ namespace glu_b200
             else
             {
                 big_variant = (forced >= 0 && forced < k_num_b32_shapes && forced != k_b32_small) ? forced : k_b32_default;
-                static const size_t persistent_min =
-                    size_t(scan_env_int("GLU_SCAN_PERSISTENT_MIN", int(k_persistent_min_elems)));
-                if (k_b32_stages[big_variant] > 0 && count * num_partitions < persistent_min)
-                    big_variant = 3;
+                if (k_b32_stages[big_variant] > 0 && (!stageable || count * num_partitions < persistent_min))
+                    big_variant = k_b32_simple;
                 big = k_b32_shapes[big_variant].threads * k_b32_shapes[big_variant].per_thread * 4;
                 small = k_b32_shapes[k_b32_small].threads * k_b32_shapes[k_b32_small].per_thread * 4;
             }
@@ -963,8 +964,9 @@ extern "C" size_t glu_scan_exclusive_tmp_bytes(size_t count, size_t num_partitio
     if (!data_type_info(data_type, &info) || count == 0 || num_partitions == 0)
         return 0;
     size_t esz = info.scalar_size * info.ncomp;
-    ScanPlan p = make_plan(count, num_partitions, esz != 4);
-    return k_tmp_align + state_bytes(p, esz);
+    const size_t a = state_bytes(make_plan(count, num_partitions, esz != 4, true), esz);
+    const size_t b = state_bytes(make_plan(count, num_partitions, esz != 4, false), esz);
+    return k_tmp_align + (a > b ? a : b);
 }
 
 extern "C" int glu_scan_exclusive(void* d_data, size_t count, size_t num_partitions, int data_type, void* d_tmp,
@@ -980,7 +982,9 @@ extern "C" int glu_scan_exclusive(void* d_data, size_t count, size_t num_partiti
         return GLU_ERROR_MISALIGNED;
     if (count > (size_t(1) << 40) / esz / num_partitions)
         return GLU_ERROR_COUNT_TOO_LARGE;
-    ScanPlan p = make_plan(count, num_partitions, esz != 4);
+    const bool stageable =
+        reinterpret_cast<uintptr_t>(d_data) % 16 == 0 && (num_partitions == 1 || (count * esz) % 16 == 0);
+    ScanPlan p = make_plan(count, num_partitions, esz != 4, stageable);
     if (p.total_tiles >= (uint64_t(1) << 31))
         return GLU_ERROR_COUNT_TOO_LARGE;
     if (!d_tmp || tmp_bytes < k_tmp_align + state_bytes(p, esz))
