@@ -32,7 +32,8 @@ namespace glu_b200
         constexpr uint32_t k_lb_inclusive = 1u << 31; // prefix row: inclusive count over tiles 0..t (bits 0..30)
         constexpr uint32_t k_lb_value_mask = (1u << 30) - 1u;
         constexpr size_t k_max_count = size_t(1) << 30;
-        constexpr int k_chain_rows = 16; // count rows the chain CTA requests ahead
+        constexpr int k_chain_rows = 16; // count rows a chain lane requests at once
+        constexpr int k_chain_ctas = 4;  // 64 digits each
 
         struct PassPlan
         {
@@ -296,38 +297,60 @@ namespace glu_b200
             for (int i = tid; i < WARPS * k_radix / 4; i += THREADS)
                 reinterpret_cast<uint4*>(&s.warp_hist[0][0])[i] = make_uint4(0, 0, 0, 0);
             __syncthreads();
-            if (s.tile == 0)
+            if (s.tile < uint32_t(k_chain_ctas))
             {
-                // ---- ticket 0 = the CHAIN CTA (the first CTA to run, hence resident before any tile exists).
-                // It turns the tiles' digit counts into running prefixes as a stream: one lane per digit,
-                // k_chain_rows rows requested ahead, rows folded strictly in tile order.  Tiles therefore
-                // never walk back over their predecessors: tile t reads ONE row, prefix[t - 1].
-                if (tid < k_radix)
+                // ---- the first k_chain_ctas tickets = the CHAIN CTAs (the first CTAs to run, hence resident
+                // before any tile exists).  Chain CTA c turns the tiles' counts of digits [64c, 64c + 64)
+                // into running prefixes, as a stream of batches: a lane owns one digit and k_chain_rows
+                // consecutive rows of the batch (all requested at once), sums them, the warps of a digit
+                // group are combined through shared memory, and the batch's prefix rows go out together.
+                // Tiles therefore never walk back over their predecessors: tile t reads ONE row,
+                // prefix[t - 1], which trails the publication of count row t - 1 by about one batch.
+                constexpr int WPG = WARPS / 2;                 // warps per 32-digit group
+                constexpr int BATCH = WPG * k_chain_rows;      // rows per batch
+                uint32_t(*totals)[2][WPG][32] = reinterpret_cast<uint32_t(*)[2][WPG][32]>(&s.warp_hist[0][0]);
+                if (warp >= 2 * WPG)
+                    return;
+                const unsigned g = warp / WPG, w = warp % WPG;
+                const uint32_t d = s.tile * 64 + g * 32 + lane;
+                uint32_t base = 0;
+                unsigned parity = 0;
+                for (uint32_t t0 = 0; t0 < num_tiles; t0 += BATCH, parity ^= 1)
                 {
-                    uint32_t running = 0;
-                    for (uint32_t t = 0; t < num_tiles; t += k_chain_rows)
+                    const uint32_t r0 = t0 + w * k_chain_rows;
+                    uint32_t p[k_chain_rows];
+#pragma unroll
+                    for (int j = 0; j < k_chain_rows; j++)
+                        p[j] = r0 + j < num_tiles ? ld_relaxed_u32(lookback + size_t(r0 + j) * k_radix + d) : k_lb_local;
+                    uint32_t run = 0;
+#pragma unroll
+                    for (int j = 0; j < k_chain_rows; j++)
                     {
-                        uint32_t w[k_chain_rows];
-#pragma unroll
-                        for (int j = 0; j < k_chain_rows; j++)
-                            w[j] = t + j < num_tiles ? ld_relaxed_u32(lookback + size_t(t + j) * k_radix + tid) : 0u;
-#pragma unroll
-                        for (int j = 0; j < k_chain_rows; j++)
-                        {
-                            if (t + j < num_tiles)
-                            {
-                                uint32_t x = w[j];
-                                while ((x & k_lb_local) == 0) // tile t + j has not published its counts yet
-                                    x = ld_relaxed_u32(lookback + size_t(t + j) * k_radix + tid);
-                                running += x & k_lb_value_mask;
-                                st_relaxed_u32(prefix + size_t(t + j) * k_radix + tid, k_lb_inclusive | running);
-                            }
-                        }
+                        uint32_t x = p[j];
+                        while ((x & k_lb_local) == 0) // tile r0 + j has not published its counts yet
+                            x = ld_relaxed_u32(lookback + size_t(r0 + j) * k_radix + d);
+                        run += x & k_lb_value_mask;
+                        p[j] = run;
                     }
+                    totals[parity][g][w][lane] = run;
+                    named_barrier_sync(1, 2 * WPG * 32);
+                    uint32_t off = 0, batch_total = 0;
+#pragma unroll
+                    for (int ww = 0; ww < WPG; ww++)
+                    {
+                        const uint32_t tt = totals[parity][g][ww][lane];
+                        off += unsigned(ww) < w ? tt : 0u;
+                        batch_total += tt;
+                    }
+#pragma unroll
+                    for (int j = 0; j < k_chain_rows; j++)
+                        if (r0 + j < num_tiles)
+                            st_relaxed_u32(prefix + size_t(r0 + j) * k_radix + d, k_lb_inclusive | (base + off + p[j]));
+                    base += batch_total;
                 }
                 return;
             }
-            const uint32_t tile = s.tile - 1;
+            const uint32_t tile = s.tile - k_chain_ctas;
             const uint32_t tile_base = tile * uint32_t(TILE);
             const uint32_t valid = n - tile_base < uint32_t(TILE) ? n - tile_base : uint32_t(TILE);
             const bool full = valid == uint32_t(TILE);
@@ -588,7 +611,7 @@ namespace glu_b200
                          uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback, uint32_t* ticket,
                          unsigned tiles, cudaStream_t s)
         {
-            // per pass: `tiles` count rows followed by `tiles` prefix rows; grid = tiles + the chain CTA
+            // per pass: `tiles` count rows followed by `tiles` prefix rows; grid = tiles + the chain CTAs
             uint32_t* prefix = lookback + size_t(tiles) * k_radix;
             auto kernel = onesweep_kernel<THREADS, IPT, MIN_BLOCKS, MODE>;
             // TMA bulk copies need 16-byte aligned sources (tiles are multiples of 4 elements)
@@ -604,7 +627,7 @@ namespace glu_b200
                 configured[dev] = true;
             }
             ScopedKernelProfile prof(GLU_KERNEL_SORT_ONESWEEP, s);
-            kernel<<<tiles + 1, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
+            kernel<<<tiles + k_chain_ctas, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
                                                     tiles, allow_tma);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
