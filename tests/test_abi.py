@@ -79,7 +79,7 @@ def test_tmp_size_queries(glu):
     L = glu.lib
     assert L.glu_reduce_tmp_bytes(1 << 28, 3) >= 256
     assert L.glu_reduce_tmp_bytes(10, 99) == 0
-    assert L.glu_scan_exclusive_tmp_bytes(1 << 28, 1, 3) >= (1 << 28) // 4096 * 8
+    assert L.glu_scan_exclusive_tmp_bytes(1 << 28, 1, 3) >= (1 << 28) // 16384 * 8  # one 64-bit word per tile
     assert L.glu_scan_exclusive_tmp_bytes(0, 1, 3) == 0
     n = 1 << 20
     need = L.glu_radix_sort_u32kv_tmp_bytes(n)
