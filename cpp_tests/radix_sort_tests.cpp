@@ -1,0 +1,149 @@
+// radix_sort_tests.cpp — the reference's RadixSort cases (test/radix_sort_tests.cpp:54-193) against device
+// pointers.  The reference checks keys only (permutation + sortedness, all-zero values); every case here also
+// sorts values = input index and requires keys AND values to equal std::stable_sort of the pairs.
+#include <algorithm>
+#include <cstdint>
+#include <numeric>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "glu/RadixSort.hpp"
+#include "harness.hpp"
+#include "util/Random.hpp"
+#include "util/StopWatch.hpp"
+
+using namespace glu;
+
+namespace
+{
+    /// vector1 is a permutation of vector2 (multiset equality, test/radix_sort_tests.cpp:20-43)
+    template<typename T> void check_permutation(const std::vector<T>& vector1, const std::vector<T>& vector2)
+    {
+        CHECK(vector1.size() == vector2.size());
+        std::unordered_map<T, long> balance;
+        for (const T& v : vector1)
+            balance[v]++;
+        for (const T& v : vector2)
+            balance[v]--;
+        CHECK(std::all_of(balance.begin(), balance.end(), [](const auto& kv) { return kv.second == 0; }));
+    }
+
+    template<typename T> void check_sorted(const std::vector<T>& vector) { CHECK(std::is_sorted(vector.begin(), vector.end())); }
+
+    /// Sorts (keys, index) on the device and compares both arrays with std::stable_sort of the pairs.
+    void sort_and_check(const std::vector<uint32_t>& keys, size_t num_steps = 0)
+    {
+        const size_t n = keys.size();
+        std::vector<uint32_t> vals(n);
+        std::iota(vals.begin(), vals.end(), 0u);
+        DeviceBuffer key_buffer(keys), val_buffer(vals);
+        RadixSort radix_sort;
+        radix_sort(key_buffer.handle(), val_buffer.handle(), n, num_steps);
+        const std::vector<uint32_t> sorted_keys = key_buffer.get_data<uint32_t>();
+        const std::vector<uint32_t> sorted_vals = val_buffer.get_data<uint32_t>();
+
+        if (num_steps == 0)
+        { // the reference's own assertions
+            check_permutation(keys, sorted_keys);
+            check_sorted(sorted_keys);
+        }
+        const uint32_t mask = (num_steps == 0 || num_steps >= 8) ? 0xffffffffu : ((1u << (4 * num_steps)) - 1u);
+        std::vector<std::pair<uint32_t, uint32_t>> pairs(n);
+        for (size_t i = 0; i < n; i++)
+            pairs[i] = {keys[i], vals[i]};
+        std::stable_sort(pairs.begin(), pairs.end(),
+                         [mask](const auto& a, const auto& b) { return (a.first & mask) < (b.first & mask); });
+        bool equal = true;
+        for (size_t i = 0; i < n && equal; i++)
+            equal = pairs[i].first == sorted_keys[i] && pairs[i].second == sorted_vals[i];
+        CHECK(equal);
+    }
+} // namespace
+
+TEST_CASE("RadixSort-simple", "[.]")
+{
+    Random random(1);
+    const std::vector<uint32_t> keys = random.sample_int_vector<uint32_t>(10, 0, UINT32_MAX);
+    std::vector<uint32_t> vals(keys.size(), 0);
+    DeviceBuffer key_buffer(keys), val_buffer(vals);
+    RadixSort radix_sort;
+    radix_sort(key_buffer.handle(), val_buffer.handle(), keys.size());
+    print_buffer_hex(key_buffer);
+    const std::vector<uint32_t> sorted_keys = key_buffer.get_data<uint32_t>();
+    check_permutation(keys, sorted_keys);
+    check_sorted(sorted_keys);
+}
+
+TEST_CASE("RadixSort-128-256-512-1024", "")
+{
+    for (size_t k_num_elements : {128, 256, 512, 1024})
+    {
+        Random random(1);
+        sort_and_check(random.sample_int_vector<uint32_t>(k_num_elements, 0, UINT32_MAX));
+    }
+}
+
+TEST_CASE("RadixSort-2048", "")
+{
+    Random random(1);
+    sort_and_check(random.sample_int_vector<uint32_t>(2048, 0, 10)); // heavy duplicates: stability matters
+}
+
+TEST_CASE("RadixSort-multiple-sizes", "")
+{
+    for (size_t k_num_elements : {10993, 14978, 16243, 18985, 23857, 27865, 33363, 41298, 45821, 47487})
+    {
+        Random random(1);
+        sort_and_check(random.sample_int_vector<uint32_t>(k_num_elements, 0, UINT32_MAX));
+    }
+}
+
+// BASELINE.json configs[0]: 1,048,576 pairs — only a benchmark size in the reference, a checked case here;
+// once with the reference's 31-bit generator and once with true 32-bit keys (bit 31 set).
+TEST_CASE("RadixSort-1048576", "")
+{
+    Random random(1);
+    sort_and_check(random.sample_int_vector<uint32_t>(1048576, 0, UINT32_MAX));
+    std::mt19937 engine(1);
+    std::vector<uint32_t> keys(1048576);
+    for (uint32_t& k : keys)
+        k = engine();
+    sort_and_check(keys);
+}
+
+// num_steps is never exercised by the reference's tests: low 4*num_steps bits only, stable.
+TEST_CASE("RadixSort-num-steps", "")
+{
+    std::mt19937 engine(5);
+    std::vector<uint32_t> keys(50021);
+    for (uint32_t& k : keys)
+        k = engine();
+    for (size_t num_steps : {1, 2, 3, 4, 5, 7, 8, 9})
+        sort_and_check(keys, num_steps);
+}
+
+TEST_CASE("RadixSort-benchmark", "[.][benchmark]")
+{
+    for (size_t k_num_elements : {1024, 16384, 65536, 131072, 524288, 1048576, 2097152, 4194304, 8388608, 16777216,
+                                  33554432, 67108864, 134217728, 268435456})
+    {
+        // zero-filled like the reference's benchmark, and a uniform-random run beside it (all-equal keys put
+        // every pair in one digit bin, which is not what a sort usually sees)
+        std::vector<uint32_t> zeros(k_num_elements), vals(k_num_elements), uniform(k_num_elements);
+        std::mt19937 engine(1);
+        for (uint32_t& k : uniform)
+            k = engine();
+        DeviceBuffer key_buffer(zeros), val_buffer(vals);
+        RadixSort radix_sort;
+        radix_sort.prepare_internal_buffers(k_num_elements);
+        radix_sort(key_buffer.handle(), val_buffer.handle(), k_num_elements); // warm-up
+        const uint64_t ns_zero =
+            measure_elapsed_time([&]() { radix_sort(key_buffer.handle(), val_buffer.handle(), k_num_elements); });
+        key_buffer.write_data(uniform.data(), uniform.size() * sizeof(uint32_t));
+        const uint64_t ns_uniform =
+            measure_elapsed_time([&]() { radix_sort(key_buffer.handle(), val_buffer.handle(), k_num_elements); });
+        std::printf("Radix sort; Num elements: %zu, Elapsed: %s (uniform keys: %s)\n", k_num_elements,
+                    ns_to_human_string(ns_zero).c_str(), ns_to_human_string(ns_uniform).c_str());
+    }
+}

@@ -1,0 +1,58 @@
+// glu/RadixSort.hpp — glu::RadixSort for CUDA device buffers (reference: glu/RadixSort.hpp:186-354).
+//
+//     glu::RadixSort radix_sort;
+//     radix_sort.prepare_internal_buffers(count);          // optional pre-sizing, as the reference's benchmark does
+//     radix_sort(d_keys, d_vals, count);                   // stable, ascending, in place
+//
+// Keys and values are two separate dense uint32 arrays, as in the reference.  num_steps keeps the
+// reference's meaning (number of 4-bit steps, i.e. only the low 4*num_steps key bits take part; 0 = all).
+// Deviation: the result always ends up in the caller's buffers (the reference leaves an odd-num_steps
+// result in its internal scratch).
+#ifndef GLU_B200_RADIXSORT_HPP
+#define GLU_B200_RADIXSORT_HPP
+
+#include "BlellochScan.hpp"
+#include "device_utils.hpp"
+
+namespace glu
+{
+    class RadixSort
+    {
+    private:
+        /// Ping-pong key/value arrays, digit histograms, per-tile look-back words (glu_radix_sort_u32kv_tmp_bytes).
+        DeviceBuffer m_tmp;
+        glu_stream_t m_stream = nullptr;
+
+    public:
+        explicit RadixSort() = default;
+        ~RadixSort() = default;
+
+        void set_stream(glu_stream_t stream) { m_stream = stream; }
+
+        void prepare_internal_buffers(size_t count)
+        {
+            const size_t need = glu_radix_sort_u32kv_tmp_bytes(count);
+            GLU_CHECK_ARGUMENT(need != 0, "RadixSort: count %zu is too large", count);
+            if (m_tmp.size() < need)
+            {
+                m_tmp.resize(need, false);
+#ifdef GLU_VERBOSE
+                std::printf("[RadixSort] Scratch buffer reallocated to: %zu\n", need);
+#endif
+            }
+        }
+
+        void operator()(DevicePtr key_buffer, DevicePtr val_buffer, size_t count, size_t num_steps = 0)
+        {
+            GLU_CHECK_ARGUMENT(key_buffer, "Invalid key buffer");
+            GLU_CHECK_ARGUMENT(val_buffer, "Invalid value buffer");
+            if (count <= 1)
+                return;
+            prepare_internal_buffers(count);
+            GLU_CHECK_STATUS(glu_radix_sort_u32kv(static_cast<uint32_t*>(key_buffer), static_cast<uint32_t*>(val_buffer),
+                                                  count, num_steps, m_tmp.handle(), m_tmp.size(), m_stream));
+        }
+    };
+} // namespace glu
+
+#endif // GLU_B200_RADIXSORT_HPP
