@@ -32,8 +32,6 @@ namespace glu_b200
         constexpr uint32_t k_lb_inclusive = 1u << 31; // prefix row: inclusive count over tiles 0..t (bits 0..30)
         constexpr uint32_t k_lb_value_mask = (1u << 30) - 1u;
         constexpr size_t k_max_count = size_t(1) << 30;
-        constexpr int k_chain_rows = 16; // count rows a chain lane requests at once
-        constexpr int k_chain_ctas = 4;  // 64 digits each
 
         struct PassPlan
         {
@@ -248,6 +246,79 @@ namespace glu_b200
             uint32_t tile;
         };
 
+        // The CHAIN CTAs of a onesweep pass (see onesweep_kernel).  Chain CTA c turns the tiles' counts of
+        // digits [64c, 64c + 64) into running prefixes, as a stream of batches: a lane owns one digit and
+        // ROWS consecutive rows of the batch (all requested at once), sums them, the warps of a digit
+        // group are combined through shared memory, and the batch's prefix rows go out together.
+        template<int WARPS, int ROWS, int GROUPS>
+        __device__ __noinline__ void chain_cta(uint32_t* smem_totals, uint32_t chain_id, const uint32_t* lookback,
+                                               uint32_t* prefix, uint32_t num_tiles)
+        {
+            constexpr int WPG = WARPS / GROUPS; // warps per 32-digit group
+            constexpr int BATCH = WPG * ROWS;   // rows per batch
+            uint32_t(*totals)[GROUPS][WPG][32] = reinterpret_cast<uint32_t(*)[GROUPS][WPG][32]>(smem_totals);
+            const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            if (warp >= GROUPS * WPG)
+                return;
+            const unsigned g = warp / WPG, w = warp % WPG;
+            const uint32_t d = (chain_id * GROUPS + g) * 32 + lane;
+            const uint32_t* col = lookback + d;
+            uint32_t base = 0;
+            unsigned parity = 0;
+            uint32_t p[ROWS], q[ROWS];
+#pragma unroll
+            for (int j = 0; j < ROWS; j++)
+                q[j] = w * ROWS + j < num_tiles ? ld_relaxed_u32(col + size_t(w * ROWS + j) * k_radix) : k_lb_local;
+            for (uint32_t t0 = 0; t0 < num_tiles; t0 += BATCH, parity ^= 1)
+            {
+                const uint32_t r0 = t0 + w * ROWS;
+#pragma unroll
+                for (int j = 0; j < ROWS; j++)
+                    p[j] = q[j];
+                // rows that are not published yet are asked for again TOGETHER: one L2 round trip per
+                // polling round, however many rows are late
+                while (true)
+                {
+                    uint32_t all = k_lb_local;
+#pragma unroll
+                    for (int j = 0; j < ROWS; j++)
+                        all &= p[j];
+                    if (all & k_lb_local)
+                        break;
+#pragma unroll
+                    for (int j = 0; j < ROWS; j++)
+                        if ((p[j] & k_lb_local) == 0)
+                            p[j] = ld_relaxed_u32(col + size_t(r0 + j) * k_radix);
+                }
+                // the next batch's rows are in flight while this one is combined and written
+#pragma unroll
+                for (int j = 0; j < ROWS; j++)
+                    q[j] = r0 + BATCH + j < num_tiles ? ld_relaxed_u32(col + size_t(r0 + BATCH + j) * k_radix) : k_lb_local;
+                uint32_t run = 0;
+#pragma unroll
+                for (int j = 0; j < ROWS; j++)
+                {
+                    run += p[j] & k_lb_value_mask;
+                    p[j] = run;
+                }
+                totals[parity][g][w][lane] = run;
+                named_barrier_sync(1 + g, WPG * 32);
+                uint32_t off = 0, batch_total = 0;
+#pragma unroll
+                for (int ww = 0; ww < WPG; ww++)
+                {
+                    const uint32_t tt = totals[parity][g][ww][lane];
+                    off += unsigned(ww) < w ? tt : 0u;
+                    batch_total += tt;
+                }
+#pragma unroll
+                for (int j = 0; j < ROWS; j++)
+                    if (r0 + j < num_tiles)
+                        st_relaxed_u32(prefix + size_t(r0 + j) * k_radix + d, k_lb_inclusive | (base + off + p[j]));
+                base += batch_total;
+            }
+        }
+
         // One tile per CTA.  digit(key) = (key >> shift) & mask; keys with equal digits keep their order.
         // A CTA is RANK_THREADS "ranking" threads plus one dedicated look-back warp.
         //
@@ -273,7 +344,8 @@ namespace glu_b200
             onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                             uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
                             uint32_t shift, uint32_t mask, const uint32_t* __restrict__ digit_offset,
-                            uint32_t* lookback, uint32_t* prefix, uint32_t* ticket, uint32_t num_tiles, int allow_tma)
+                            uint32_t* lookback, uint32_t* prefix, uint32_t* ticket, uint32_t num_tiles, int allow_tma,
+                            int chain_rows, int debug_no_lookback)
         {
             static_assert(RANK_THREADS >= k_radix && RANK_THREADS % 32 == 0, "one ranking thread per digit");
             static_assert(IPT % 2 == 0, "ranks are packed two per register");
@@ -287,6 +359,7 @@ namespace glu_b200
             Smem& s = *reinterpret_cast<Smem*>(smem_raw);
 
             const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+            const uint32_t chain_ctas = chain_rows >= 100 ? 4u : 8u; // 64 or 32 digits per chain CTA
             if (tid == 0)
             {
                 s.tile = atomicAdd(ticket, 1u);
@@ -297,60 +370,24 @@ namespace glu_b200
             for (int i = tid; i < WARPS * k_radix / 4; i += THREADS)
                 reinterpret_cast<uint4*>(&s.warp_hist[0][0])[i] = make_uint4(0, 0, 0, 0);
             __syncthreads();
-            if (s.tile < uint32_t(k_chain_ctas))
+            if (s.tile < chain_ctas)
             {
-                // ---- the first k_chain_ctas tickets = the CHAIN CTAs (the first CTAs to run, hence resident
-                // before any tile exists).  Chain CTA c turns the tiles' counts of digits [64c, 64c + 64)
-                // into running prefixes, as a stream of batches: a lane owns one digit and k_chain_rows
-                // consecutive rows of the batch (all requested at once), sums them, the warps of a digit
-                // group are combined through shared memory, and the batch's prefix rows go out together.
-                // Tiles therefore never walk back over their predecessors: tile t reads ONE row,
-                // prefix[t - 1], which trails the publication of count row t - 1 by about one batch.
-                constexpr int WPG = WARPS / 2;                 // warps per 32-digit group
-                constexpr int BATCH = WPG * k_chain_rows;      // rows per batch
-                uint32_t(*totals)[2][WPG][32] = reinterpret_cast<uint32_t(*)[2][WPG][32]>(&s.warp_hist[0][0]);
-                if (warp >= 2 * WPG)
-                    return;
-                const unsigned g = warp / WPG, w = warp % WPG;
-                const uint32_t d = s.tile * 64 + g * 32 + lane;
-                uint32_t base = 0;
-                unsigned parity = 0;
-                for (uint32_t t0 = 0; t0 < num_tiles; t0 += BATCH, parity ^= 1)
+                // ---- the first tickets = the CHAIN CTAs (the first CTAs to run, hence resident before any
+                // tile exists): see chain_cta().  Tiles never walk back over their predecessors: tile t
+                // reads ONE row, prefix[t - 1], which trails the publication of count row t - 1 by about
+                // one batch.  chain_rows selects the batch shape (rows per lane; >= 100: 64 digits per CTA).
+                uint32_t* totals = reinterpret_cast<uint32_t*>(&s.warp_hist[0][0]);
+                switch (chain_rows)
                 {
-                    const uint32_t r0 = t0 + w * k_chain_rows;
-                    uint32_t p[k_chain_rows];
-#pragma unroll
-                    for (int j = 0; j < k_chain_rows; j++)
-                        p[j] = r0 + j < num_tiles ? ld_relaxed_u32(lookback + size_t(r0 + j) * k_radix + d) : k_lb_local;
-                    uint32_t run = 0;
-#pragma unroll
-                    for (int j = 0; j < k_chain_rows; j++)
-                    {
-                        uint32_t x = p[j];
-                        while ((x & k_lb_local) == 0) // tile r0 + j has not published its counts yet
-                            x = ld_relaxed_u32(lookback + size_t(r0 + j) * k_radix + d);
-                        run += x & k_lb_value_mask;
-                        p[j] = run;
-                    }
-                    totals[parity][g][w][lane] = run;
-                    named_barrier_sync(1, 2 * WPG * 32);
-                    uint32_t off = 0, batch_total = 0;
-#pragma unroll
-                    for (int ww = 0; ww < WPG; ww++)
-                    {
-                        const uint32_t tt = totals[parity][g][ww][lane];
-                        off += unsigned(ww) < w ? tt : 0u;
-                        batch_total += tt;
-                    }
-#pragma unroll
-                    for (int j = 0; j < k_chain_rows; j++)
-                        if (r0 + j < num_tiles)
-                            st_relaxed_u32(prefix + size_t(r0 + j) * k_radix + d, k_lb_inclusive | (base + off + p[j]));
-                    base += batch_total;
+                case 2: chain_cta<WARPS, 2, 1>(totals, s.tile, lookback, prefix, num_tiles); break;
+                case 4: chain_cta<WARPS, 4, 1>(totals, s.tile, lookback, prefix, num_tiles); break;
+                case 8: chain_cta<WARPS, 8, 1>(totals, s.tile, lookback, prefix, num_tiles); break;
+                case 104: chain_cta<WARPS, 4, 2>(totals, s.tile, lookback, prefix, num_tiles); break;
+                default: chain_cta<WARPS, 8, 2>(totals, s.tile, lookback, prefix, num_tiles); break;
                 }
                 return;
             }
-            const uint32_t tile = s.tile - k_chain_ctas;
+            const uint32_t tile = s.tile - chain_ctas;
             const uint32_t tile_base = tile * uint32_t(TILE);
             const uint32_t valid = n - tile_base < uint32_t(TILE) ? n - tile_base : uint32_t(TILE);
             const bool full = valid == uint32_t(TILE);
@@ -488,7 +525,7 @@ namespace glu_b200
                 if (tid < k_radix)
                 {
                     uint32_t exclusive = 0;
-                    if (tile > 0)
+                    if (tile > 0 && !debug_no_lookback) // debug_no_lookback: timing experiments only (wrong results)
                     {
                         const uint32_t* p = prefix + size_t(tile - 1) * k_radix + tid;
                         uint32_t x = ld_relaxed_u32(p);
@@ -569,7 +606,7 @@ namespace glu_b200
                 return k_configs[5];
             if (count <= (size_t(1) << 21))
                 return k_configs[2];
-            return k_configs[1];
+            return k_configs[3];
         }
 
         bool use_tma_env()
@@ -618,6 +655,8 @@ namespace glu_b200
             const int allow_tma =
                 ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
             constexpr size_t smem = sizeof(SweepSmem<THREADS, IPT>);
+            static const int chain_rows = env_int("GLU_SORT_CHAIN_ROWS", 4);
+            static const int debug_no_lookback = env_int("GLU_SORT_DEBUG_NO_LOOKBACK", 0);
             static bool configured[64] = {};
             int dev = 0;
             GLU_CUDA_TRY(cudaGetDevice(&dev));
@@ -627,8 +666,8 @@ namespace glu_b200
                 configured[dev] = true;
             }
             ScopedKernelProfile prof(GLU_KERNEL_SORT_ONESWEEP, s);
-            kernel<<<tiles + k_chain_ctas, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
-                                                    tiles, allow_tma);
+            kernel<<<tiles + (chain_rows >= 100 ? 4 : 8), THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
+                                                    tiles, allow_tma, chain_rows, debug_no_lookback);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }

@@ -1,0 +1,12 @@
+#!/bin/bash
+# Tuning sweep for the sort on the GPU box: each argument is a space-separated list of VAR=value settings.
+# usage: bash tools/exp_sort.sh tag "GLU_SORT_CONFIG=1" "GLU_SORT_CONFIG=1 GLU_SORT_CHAIN_ROWS=16" ...
+TAG=$1; shift
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+( timeout 600 python -m pytest tests/test_sort_gpu.py -m gpu -x -q 2>&1 | tail -5 ) > $OUT/pytest_sort.log
+cat $OUT/pytest_sort.log
+for cfg in "$@"; do
+  echo "== $cfg" | tee -a $OUT/sweep.log
+  ( env $cfg timeout 300 python tools/quick_bench.py --log2n ${LOG2N:-28} --what sort --reps ${REPS:-10} 2>&1 | tail -2 ) | tee -a $OUT/sweep.log
+done

@@ -60,9 +60,10 @@ if "sort" in args.what:
           f"{n / med / 1e6:.2f} Gpairs/s  {68 * n / med / 1e6:.0f} GB/s(68B/pair)  "
           f"cfg={os.environ.get('GLU_SORT_CONFIG', 'auto')} rank={os.environ.get('GLU_SORT_RANK', '0')} "
           f"tma={os.environ.get('GLU_SORT_TMA', '1')}")
-    k64 = keys.to(torch.int64) & 0xFFFFFFFF
-    assert bool((k64[1:] >= k64[:-1]).all()), "not sorted"
-    del k64
+    if not os.environ.get("GLU_SORT_DEBUG_NO_LOOKBACK"):
+        k64 = keys.to(torch.int64) & 0xFFFFFFFF
+        assert bool((k64[1:] >= k64[:-1]).all()), "not sorted"
+        del k64
 
 if "scan" in args.what:
     data0 = torch.randint(0, 100, (n,), dtype=torch.int32, device=dev, generator=g)
