@@ -51,6 +51,14 @@ ABI = {
     "glu_scan_exclusive": (_int, [_vp, _sz, _sz, _int, _vp, _sz, _vp]),
     "glu_radix_sort_u32kv_tmp_bytes": (_sz, [_sz]),
     "glu_radix_sort_u32kv": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _vp]),
+    "glu_reduce_into": (_int, [_vp, _sz, _int, _int, _vp, _vp, _sz, _vp]),
+    "glu_scan_exclusive_init": (_int, [_vp, _sz, _sz, _int, _vp, _vp, _sz, _vp]),
+    "glu_radix_histogram_u32": (_int, [_vp, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _vp]),
+    "glu_radix_partition_u32kv_tmp_bytes": (_sz, [_sz]),
+    "glu_radix_partition_u32kv": (_int, [_vp, _vp, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _vp, _sz, _vp]),
+    "glu_ipc_get_handle": (_int, [_vp, ctypes.c_char_p]),
+    "glu_ipc_open_handle": (_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
+    "glu_ipc_close_handle": (_int, [_vp]),
     "glu_reduce_host": (_int, [_vp, _sz, _int, _int]),
     "glu_scan_exclusive_host": (_int, [_vp, _sz, _sz, _int]),
     "glu_radix_sort_u32kv_host": (_int, [_vp, _vp, _sz, _sz]),
@@ -300,3 +308,7 @@ def radix_sort_u32kv_host(keys, vals, count: int | None = None, num_steps: int =
     if count is None:
         count = keys.size
     check(_lib.glu_radix_sort_u32kv_host(_np_ptr(keys), _np_ptr(vals), count, num_steps), "radix_sort_u32kv_host")
+
+
+from . import distributed  # noqa: E402  (multi-GPU composition; imports torch lazily)
+from .distributed import DistributedBlellochScan, DistributedRadixSort, DistributedReduce  # noqa: E402,F401

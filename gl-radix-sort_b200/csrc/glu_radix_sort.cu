@@ -72,7 +72,8 @@ namespace glu_b200
         // serialised same-address pile-up.
         __global__ void __launch_bounds__(k_hist_threads)
             histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t head, uint32_t n_units,
-                             int num_passes, uint32_t key_mask, uint32_t* hist, uint32_t* ticket)
+                             int num_passes, uint32_t pre_shift, uint32_t key_mask, uint32_t* hist, uint32_t* ticket,
+                             int make_offsets)
         {
             __shared__ uint32_t s_hist[k_max_passes][k_radix][k_hist_copies];
             __shared__ uint32_t s_scan[k_hist_threads / 32];
@@ -105,8 +106,8 @@ namespace glu_b200
                 {
                     if (__ballot_sync(k_full_mask, ok[u]) == 0)
                         continue;
-                    const uint32_t kk[4] = {k[u].x & key_mask, k[u].y & key_mask, k[u].z & key_mask,
-                                            k[u].w & key_mask};
+                    const uint32_t kk[4] = {(k[u].x >> pre_shift) & key_mask, (k[u].y >> pre_shift) & key_mask,
+                                            (k[u].z >> pre_shift) & key_mask, (k[u].w >> pre_shift) & key_mask};
                     for (int p = 0; p < num_passes; p++)
                     {
                         uint32_t d[4];
@@ -141,7 +142,7 @@ namespace glu_b200
                 const uint32_t tail_begin = head + n_units * 4;
                 const uint32_t idx = lane < head ? lane : tail_begin + (lane - head);
                 const bool ok = idx < n && lane < head + 3;
-                const uint32_t key = ok ? (keys[idx] & key_mask) : 0;
+                const uint32_t key = ok ? ((keys[idx] >> pre_shift) & key_mask) : 0;
                 if (ok)
                     for (int p = 0; p < num_passes; p++)
                         atomicAdd(&s_hist[p][(key >> (8 * p)) & 0xffu][copy], 1u);
@@ -157,6 +158,8 @@ namespace glu_b200
                     atomicAdd(&hist[i], c);
             }
 
+            if (!make_offsets) // glu_radix_histogram_u32: raw counts
+                return;
             // last CTA: counts -> exclusive offsets, one digit place at a time
             __threadfence();
             __syncthreads();
@@ -231,7 +234,18 @@ namespace glu_b200
 #undef GLU_MATCH_BIT
 
         
-        template<int RANK_THREADS, int IPT> struct SweepSmem
+        // PEER = true: every digit run goes to its own destination pointer (possibly in another GPU's memory,
+        // glu_radix_partition_u32kv) instead of one output array.
+        template<bool PEER> struct SweepDst
+        {
+        };
+        template<> struct SweepDst<true>
+        {
+            uint32_t* key[k_radix]; // address of tile-sorted slot 0, per digit
+            uint32_t* val[k_radix];
+        };
+
+        template<int RANK_THREADS, int IPT, bool PEER = false> struct SweepSmem
         {
             static constexpr int WARPS = RANK_THREADS / 32; // ranking warps
             static constexpr int TILE = RANK_THREADS * IPT;
@@ -241,6 +255,7 @@ namespace glu_b200
             uint32_t gbase[k_radix];            // global index of tile-sorted slot 0, per digit
             uint32_t tile_start[k_radix];       // first tile-sorted slot of each digit
             uint32_t scan[8];
+            SweepDst<PEER> dst;
             alignas(8) uint64_t bar_keys;       // mbarriers completed by the bulk copies
             alignas(8) uint64_t bar_vals;
             uint32_t tile;
@@ -339,17 +354,18 @@ namespace glu_b200
         //   5. values: staging buffer -> registers -> tile-sorted slot (in place); then slot p of both
         //      arrays goes to global[gbase[digit(key_p)] + p] — neighbouring threads, neighbouring
         //      addresses inside every digit run.
-        template<int RANK_THREADS, int IPT, int MIN_BLOCKS, int MODE>
+        template<int RANK_THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false>
         __global__ void __launch_bounds__(RANK_THREADS, MIN_BLOCKS)
             onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                             uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
                             uint32_t shift, uint32_t mask, const uint32_t* __restrict__ digit_offset,
                             uint32_t* lookback, uint32_t* prefix, uint32_t* ticket, uint32_t num_tiles, int allow_tma,
-                            int chain_rows, int debug_no_lookback)
+                            int chain_rows, int debug_no_lookback, uint32_t* const* key_dst = nullptr,
+                            uint32_t* const* val_dst = nullptr)
         {
             static_assert(RANK_THREADS >= k_radix && RANK_THREADS % 32 == 0, "one ranking thread per digit");
             static_assert(IPT % 2 == 0, "ranks are packed two per register");
-            using Smem = SweepSmem<RANK_THREADS, IPT>;
+            using Smem = SweepSmem<RANK_THREADS, IPT, PEER>;
             constexpr int THREADS = RANK_THREADS;
             constexpr int WARPS = Smem::WARPS;
             constexpr int TILE = Smem::TILE;
@@ -533,7 +549,14 @@ namespace glu_b200
                             x = ld_relaxed_u32(p);
                         exclusive = x & ~k_lb_inclusive;
                     }
-                    s.gbase[tid] = digit_offset[tid] + exclusive - s.tile_start[tid];
+                    if constexpr (PEER)
+                    {
+                        const ptrdiff_t off = ptrdiff_t(exclusive) - ptrdiff_t(s.tile_start[tid]);
+                        s.dst.key[tid] = key_dst[tid] + off;
+                        s.dst.val[tid] = val_dst[tid] + off;
+                    }
+                    else
+                        s.gbase[tid] = digit_offset[tid] + exclusive - s.tile_start[tid];
                 }
                 __syncthreads(); // all values are in registers
 #pragma unroll
@@ -554,9 +577,18 @@ namespace glu_b200
                     const uint32_t p = tid + k * THREADS;
                     const uint32_t kk = s.keys[p];
                     const uint32_t vv = s.vals[p];
-                    const uint32_t dst = s.gbase[(kk >> shift) & mask] + p;
-                    keys_out[dst] = kk;
-                    vals_out[dst] = vv;
+                    if constexpr (PEER)
+                    {
+                        const uint32_t d = (kk >> shift) & mask;
+                        s.dst.key[d][p] = kk;
+                        s.dst.val[d][p] = vv;
+                    }
+                    else
+                    {
+                        const uint32_t dst = s.gbase[(kk >> shift) & mask] + p;
+                        keys_out[dst] = kk;
+                        vals_out[dst] = vv;
+                    }
                 }
             }
             else
@@ -564,9 +596,18 @@ namespace glu_b200
                 for (uint32_t p = tid; p < valid; p += THREADS)
                 {
                     const uint32_t kk = s.keys[p];
-                    const uint32_t dst = s.gbase[(kk >> shift) & mask] + p;
-                    keys_out[dst] = kk;
-                    vals_out[dst] = s.vals[p];
+                    if constexpr (PEER)
+                    {
+                        const uint32_t d = (kk >> shift) & mask;
+                        s.dst.key[d][p] = kk;
+                        s.dst.val[d][p] = s.vals[p];
+                    }
+                    else
+                    {
+                        const uint32_t dst = s.gbase[(kk >> shift) & mask] + p;
+                        keys_out[dst] = kk;
+                        vals_out[dst] = s.vals[p];
+                    }
                 }
             }
         }
@@ -643,18 +684,19 @@ namespace glu_b200
             return l;
         }
 
-        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE>
+        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false>
         int launch_sweep(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint32_t n, uint32_t shift,
                          uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback, uint32_t* ticket,
-                         unsigned tiles, cudaStream_t s)
+                         unsigned tiles, cudaStream_t s, uint32_t* const* key_dst = nullptr,
+                         uint32_t* const* val_dst = nullptr)
         {
             // per pass: `tiles` count rows followed by `tiles` prefix rows; grid = tiles + the chain CTAs
             uint32_t* prefix = lookback + size_t(tiles) * k_radix;
-            auto kernel = onesweep_kernel<THREADS, IPT, MIN_BLOCKS, MODE>;
+            auto kernel = onesweep_kernel<THREADS, IPT, MIN_BLOCKS, MODE, PEER>;
             // TMA bulk copies need 16-byte aligned sources (tiles are multiples of 4 elements)
             const int allow_tma =
                 ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
-            constexpr size_t smem = sizeof(SweepSmem<THREADS, IPT>);
+            constexpr size_t smem = sizeof(SweepSmem<THREADS, IPT, PEER>);
             static const int chain_rows = env_int("GLU_SORT_CHAIN_ROWS", 4);
             static const int debug_no_lookback = env_int("GLU_SORT_DEBUG_NO_LOOKBACK", 0);
             static bool configured[64] = {};
@@ -667,7 +709,7 @@ namespace glu_b200
             }
             ScopedKernelProfile prof(GLU_KERNEL_SORT_ONESWEEP, s);
             kernel<<<tiles + (chain_rows >= 100 ? 4 : 8), THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
-                                                    tiles, allow_tma, chain_rows, debug_no_lookback);
+                                                    tiles, allow_tma, chain_rows, debug_no_lookback, key_dst, val_dst);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
@@ -696,6 +738,31 @@ namespace glu_b200
 } // namespace glu_b200
 
 using namespace glu_b200;
+
+namespace
+{
+    // the partition pass always uses the large-input tile shape
+    constexpr int k_part_threads = 384, k_part_ipt = 20, k_part_blocks = 3;
+
+    int launch_histogram(const uint32_t* d_keys, uint32_t n, int num_passes, uint32_t pre_shift, uint32_t key_mask,
+                         uint32_t* hist, uint32_t* ticket, int make_offsets, int sms, cudaStream_t s)
+    {
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(d_keys);
+        uint32_t head = uint32_t(((16 - (addr & 15)) & 15) / sizeof(uint32_t));
+        if (head > n)
+            head = n;
+        const uint32_t n_units = (n - head) / 4;
+        const size_t per_block = size_t(k_hist_threads) * k_hist_unroll;
+        size_t grid = (size_t(n_units) + per_block - 1) / per_block;
+        const size_t cap = size_t(sms) * k_hist_blocks_per_sm;
+        grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
+        ScopedKernelProfile prof(GLU_KERNEL_SORT_HISTOGRAM, s);
+        histogram_kernel<<<unsigned(grid), k_hist_threads, 0, s>>>(d_keys, n, head, n_units, num_passes, pre_shift, key_mask,
+                                                                    hist, ticket, make_offsets);
+        GLU_LAUNCH_CHECK();
+        return GLU_SUCCESS;
+    }
+} // namespace
 
 extern "C" size_t glu_radix_sort_u32kv_tmp_bytes(size_t count)
 {
@@ -740,19 +807,9 @@ extern "C" int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t c
     GLU_CUDA_TRY(cudaMemsetAsync(tmp, 0, used_control, s));
 
     {
-        const uintptr_t addr = reinterpret_cast<uintptr_t>(d_keys);
-        uint32_t head = uint32_t(((16 - (addr & 15)) & 15) / sizeof(uint32_t));
-        if (head > n)
-            head = n;
-        const uint32_t n_units = (n - head) / 4;
-        const size_t per_block = size_t(k_hist_threads) * k_hist_unroll;
-        size_t grid = (size_t(n_units) + per_block - 1) / per_block;
-        const size_t cap = size_t(sms) * k_hist_blocks_per_sm;
-        grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
-        ScopedKernelProfile prof(GLU_KERNEL_SORT_HISTOGRAM, s);
-        histogram_kernel<<<unsigned(grid), k_hist_threads, 0, s>>>(d_keys, n, head, n_units, plan.num_passes,
-                                                                    plan.key_mask, hist, tickets + 4);
-        GLU_LAUNCH_CHECK();
+        const int rc = launch_histogram(d_keys, n, plan.num_passes, 0u, plan.key_mask, hist, tickets + 4, 1, sms, s);
+        if (rc != GLU_SUCCESS)
+            return rc;
     }
 
     const SweepConfig& cfg = select_config(count);
@@ -782,4 +839,67 @@ extern "C" int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t c
         GLU_CUDA_TRY(cudaMemcpyAsync(d_vals, alt_vals, count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     }
     return GLU_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------ multi-GPU building blocks
+
+
+extern "C" int glu_radix_histogram_u32(const uint32_t* d_keys, size_t count, unsigned shift, unsigned bits,
+                                       uint32_t* d_hist, glu_stream_t stream)
+{
+    if (!d_keys || !d_hist || bits == 0 || bits > 8 || shift > 31)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    if (count > k_max_count)
+        return GLU_ERROR_COUNT_TOO_LARGE;
+    if (reinterpret_cast<uintptr_t>(d_keys) % sizeof(uint32_t) != 0 || reinterpret_cast<uintptr_t>(d_hist) % sizeof(uint32_t) != 0)
+        return GLU_ERROR_MISALIGNED;
+    const int sms = current_sm_count();
+    if (sms <= 0)
+        return GLU_ERROR_CUDA;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    GLU_CUDA_TRY(cudaMemsetAsync(d_hist, 0, k_radix * sizeof(uint32_t), s));
+    if (count == 0)
+        return GLU_SUCCESS;
+    return launch_histogram(d_keys, uint32_t(count), 1, shift, (1u << bits) - 1u, d_hist, nullptr, 0, sms, s);
+}
+
+extern "C" size_t glu_radix_partition_u32kv_tmp_bytes(size_t count)
+{
+    if (count > k_max_count)
+        return 0;
+    const size_t tile = size_t(k_part_threads) * k_part_ipt;
+    const size_t tiles = (count + tile - 1) / tile;
+    return k_tmp_align + align_up(2 * tiles * k_radix * sizeof(uint32_t), k_tmp_align);
+}
+
+extern "C" int glu_radix_partition_u32kv(const uint32_t* d_keys, const uint32_t* d_vals, size_t count, unsigned shift,
+                                         unsigned bits, uint32_t* const* d_key_dst, uint32_t* const* d_val_dst,
+                                         void* d_tmp, size_t tmp_bytes, glu_stream_t stream)
+{
+    if (!d_keys || !d_vals || !d_key_dst || !d_val_dst || bits == 0 || bits > 8 || shift > 31)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    if (count == 0)
+        return GLU_SUCCESS;
+    if (count > k_max_count)
+        return GLU_ERROR_COUNT_TOO_LARGE;
+    if ((reinterpret_cast<uintptr_t>(d_keys) | reinterpret_cast<uintptr_t>(d_vals)) % sizeof(uint32_t) != 0 ||
+        (reinterpret_cast<uintptr_t>(d_key_dst) | reinterpret_cast<uintptr_t>(d_val_dst)) % sizeof(void*) != 0)
+        return GLU_ERROR_MISALIGNED;
+    const size_t need = glu_radix_partition_u32kv_tmp_bytes(count);
+    if (!d_tmp || tmp_bytes < need)
+        return GLU_ERROR_TMP_TOO_SMALL;
+    if (reinterpret_cast<uintptr_t>(d_tmp) % k_tmp_align != 0)
+        return GLU_ERROR_MISALIGNED;
+    if (current_sm_count() <= 0)
+        return GLU_ERROR_CUDA;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t tile = size_t(k_part_threads) * k_part_ipt;
+    const unsigned tiles = unsigned((count + tile - 1) / tile);
+    char* tmp = static_cast<char*>(d_tmp);
+    GLU_CUDA_TRY(cudaMemsetAsync(tmp, 0, need, s));
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(tmp);
+    uint32_t* lookback = reinterpret_cast<uint32_t*>(tmp + k_tmp_align);
+    return launch_sweep<k_part_threads, k_part_ipt, k_part_blocks, Rank_Ballot, true>(
+        d_keys, d_vals, nullptr, nullptr, uint32_t(count), shift, (1u << bits) - 1u, nullptr, lookback, ticket, tiles, s,
+        d_key_dst, d_val_dst);
 }

@@ -163,13 +163,14 @@ namespace glu_b200
         }
 
         // data      : base pointer of the buffer (scalar view)
+        // out       : where the NCOMP result scalars go (data itself for the in-place glu_reduce)
         // head      : scalars before the first 16-byte aligned address (handled by CTA 0)
         // n_units   : number of whole 16-byte units after the head
         // n_scalars : count * NCOMP
         template<typename S, int NCOMP, int OP, int THREADS, int UNROLL>
         __global__ void __launch_bounds__(THREADS)
-            reduce_kernel(S* __restrict__ data, size_t n_scalars, unsigned head, size_t n_units, S* partials,
-                          unsigned* ticket)
+            reduce_kernel(const S* __restrict__ data, S* __restrict__ out, size_t n_scalars, unsigned head, size_t n_units,
+                          S* partials, unsigned* ticket)
         {
             using Opr = Operator<S, OP>;
             constexpr int L = Unit<S>::L;
@@ -243,7 +244,7 @@ namespace glu_b200
                 {
 #pragma unroll
                     for (int c = 0; c < NCOMP; c++)
-                        data[c] = r[c];
+                        out[c] = r[c];
                 }
                 return;
             }
@@ -277,7 +278,7 @@ namespace glu_b200
             {
 #pragma unroll
                 for (int c = 0; c < NCOMP; c++)
-                    data[c] = r[c];
+                    out[c] = r[c];
             }
         }
 
@@ -292,7 +293,7 @@ namespace glu_b200
         }
 
         template<typename S, int NCOMP, int OP>
-        int launch_reduce(void* d_data, size_t count, void* d_tmp, cudaStream_t stream)
+        int launch_reduce(const void* d_data, void* d_out, size_t count, void* d_tmp, cudaStream_t stream)
         {
             constexpr int L = Unit<S>::L;
             const size_t n_scalars = count * NCOMP;
@@ -308,30 +309,31 @@ namespace glu_b200
                 GLU_CUDA_TRY(cudaMemsetAsync(ticket, 0, sizeof(unsigned), stream));
             ScopedKernelProfile prof(GLU_KERNEL_REDUCE, stream);
             reduce_kernel<S, NCOMP, OP, k_threads, k_unroll>
-                <<<grid, k_threads, 0, stream>>>(reinterpret_cast<S*>(d_data), n_scalars, head, n_units, partials, ticket);
+                <<<grid, k_threads, 0, stream>>>(reinterpret_cast<const S*>(d_data), reinterpret_cast<S*>(d_out), n_scalars, head,
+                                                 n_units, partials, ticket);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
 
-        template<typename S, int NCOMP> int dispatch_op(void* d, size_t n, int op, void* tmp, cudaStream_t s)
+        template<typename S, int NCOMP> int dispatch_op(const void* d, void* o, size_t n, int op, void* tmp, cudaStream_t s)
         {
             switch (op)
             {
-            case GLU_REDUCE_OPERATOR_SUM: return launch_reduce<S, NCOMP, GLU_REDUCE_OPERATOR_SUM>(d, n, tmp, s);
-            case GLU_REDUCE_OPERATOR_MUL: return launch_reduce<S, NCOMP, GLU_REDUCE_OPERATOR_MUL>(d, n, tmp, s);
-            case GLU_REDUCE_OPERATOR_MIN: return launch_reduce<S, NCOMP, GLU_REDUCE_OPERATOR_MIN>(d, n, tmp, s);
-            case GLU_REDUCE_OPERATOR_MAX: return launch_reduce<S, NCOMP, GLU_REDUCE_OPERATOR_MAX>(d, n, tmp, s);
+            case GLU_REDUCE_OPERATOR_SUM: return launch_reduce<S, NCOMP, GLU_REDUCE_OPERATOR_SUM>(d, o, n, tmp, s);
+            case GLU_REDUCE_OPERATOR_MUL: return launch_reduce<S, NCOMP, GLU_REDUCE_OPERATOR_MUL>(d, o, n, tmp, s);
+            case GLU_REDUCE_OPERATOR_MIN: return launch_reduce<S, NCOMP, GLU_REDUCE_OPERATOR_MIN>(d, o, n, tmp, s);
+            case GLU_REDUCE_OPERATOR_MAX: return launch_reduce<S, NCOMP, GLU_REDUCE_OPERATOR_MAX>(d, o, n, tmp, s);
             default: return GLU_ERROR_INVALID_OPERATOR;
             }
         }
 
-        template<typename S> int dispatch_ncomp(void* d, size_t n, int ncomp, int op, void* tmp, cudaStream_t s)
+        template<typename S> int dispatch_ncomp(const void* d, void* o, size_t n, int ncomp, int op, void* tmp, cudaStream_t s)
         {
             switch (ncomp)
             {
-            case 1: return dispatch_op<S, 1>(d, n, op, tmp, s);
-            case 2: return dispatch_op<S, 2>(d, n, op, tmp, s);
-            default: return dispatch_op<S, 4>(d, n, op, tmp, s);
+            case 1: return dispatch_op<S, 1>(d, o, n, op, tmp, s);
+            case 2: return dispatch_op<S, 2>(d, o, n, op, tmp, s);
+            default: return dispatch_op<S, 4>(d, o, n, op, tmp, s);
             }
         }
     } // namespace
@@ -353,29 +355,39 @@ extern "C" size_t glu_reduce_tmp_bytes(size_t count, int data_type)
 extern "C" int glu_reduce(void* d_data, size_t count, int data_type, int op, void* d_tmp, size_t tmp_bytes,
                           glu_stream_t stream)
 {
+    return glu_reduce_into(d_data, count, data_type, op, d_data, d_tmp, tmp_bytes, stream);
+}
+
+extern "C" int glu_reduce_into(const void* d_data, size_t count, int data_type, int op, void* d_result, void* d_tmp,
+                               size_t tmp_bytes, glu_stream_t stream)
+{
     DataTypeInfo info;
     if (!data_type_info(data_type, &info))
         return GLU_ERROR_INVALID_DATA_TYPE;
     if (op < GLU_REDUCE_OPERATOR_SUM || op > GLU_REDUCE_OPERATOR_MAX)
         return GLU_ERROR_INVALID_OPERATOR;
-    if (!d_data || count == 0) // glu/Reduce.hpp:113-114
+    if (!d_data || !d_result || count == 0) // glu/Reduce.hpp:113-114
         return GLU_ERROR_INVALID_ARGUMENT;
-    if (reinterpret_cast<uintptr_t>(d_data) % info.scalar_size != 0)
+    if (reinterpret_cast<uintptr_t>(d_data) % info.scalar_size != 0 || reinterpret_cast<uintptr_t>(d_result) % info.scalar_size != 0)
         return GLU_ERROR_MISALIGNED;
-    if (count == 1) // glu/Reduce.hpp:124-125: zero dispatches, data[0] is already the result
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (count == 1)
+    {
+        if (d_result != d_data)
+            GLU_CUDA_TRY(cudaMemcpyAsync(d_result, d_data, info.scalar_size * info.ncomp, cudaMemcpyDeviceToDevice, s));
         return GLU_SUCCESS;
+    }
     if (!d_tmp || tmp_bytes < glu_reduce_tmp_bytes(count, data_type))
         return GLU_ERROR_TMP_TOO_SMALL;
     if (reinterpret_cast<uintptr_t>(d_tmp) % k_tmp_align != 0)
         return GLU_ERROR_MISALIGNED;
     if (current_sm_count() <= 0)
         return GLU_ERROR_CUDA;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     switch (info.scalar)
     {
-    case 0: return dispatch_ncomp<float>(d_data, count, info.ncomp, op, d_tmp, s);
-    case 1: return dispatch_ncomp<double>(d_data, count, info.ncomp, op, d_tmp, s);
-    case 2: return dispatch_ncomp<int32_t>(d_data, count, info.ncomp, op, d_tmp, s);
-    default: return dispatch_ncomp<uint32_t>(d_data, count, info.ncomp, op, d_tmp, s);
+    case 0: return dispatch_ncomp<float>(d_data, d_result, count, info.ncomp, op, d_tmp, s);
+    case 1: return dispatch_ncomp<double>(d_data, d_result, count, info.ncomp, op, d_tmp, s);
+    case 2: return dispatch_ncomp<int32_t>(d_data, d_result, count, info.ncomp, op, d_tmp, s);
+    default: return dispatch_ncomp<uint32_t>(d_data, d_result, count, info.ncomp, op, d_tmp, s);
     }
 }

@@ -449,3 +449,34 @@ extern "C"
         return GLU_SUCCESS;
     }
 }
+
+// ---- CUDA IPC (one process per GPU: map a peer rank's receive buffer into this process) ----------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == GLU_IPC_HANDLE_BYTES, "handle size");
+
+extern "C" int glu_ipc_get_handle(void* d_ptr, unsigned char handle[GLU_IPC_HANDLE_BYTES])
+{
+    if (!d_ptr || !handle)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    cudaIpcMemHandle_t h;
+    GLU_CUDA_TRY(cudaIpcGetMemHandle(&h, d_ptr));
+    std::memcpy(handle, &h, sizeof h);
+    return GLU_SUCCESS;
+}
+
+extern "C" int glu_ipc_open_handle(const unsigned char handle[GLU_IPC_HANDLE_BYTES], void** d_ptr)
+{
+    if (!handle || !d_ptr)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    GLU_CUDA_TRY(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return GLU_SUCCESS;
+}
+
+extern "C" int glu_ipc_close_handle(void* d_ptr)
+{
+    if (!d_ptr)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    GLU_CUDA_TRY(cudaIpcCloseMemHandle(d_ptr));
+    return GLU_SUCCESS;
+}

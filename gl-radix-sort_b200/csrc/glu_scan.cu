@@ -81,7 +81,7 @@ namespace glu_b200
         template<typename T, int THREADS, int VPT, int MIN_BLOCKS, bool TICKET>
         __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             scan_b32_kernel(T* __restrict__ data, size_t count, uint32_t tiles_per_part, uint32_t* ticket,
-                            uint64_t* state, int debug_no_lookback)
+                            uint64_t* state, int debug_no_lookback, const T* __restrict__ init)
         {
             constexpr int TILE = THREADS * VPT * 4;
             constexpr int WARPS = THREADS / 32;
@@ -182,11 +182,12 @@ namespace glu_b200
                     s_warp_prefix[lane] = wex;
                 const T aggregate = __shfl_sync(k_full_mask, winc, 31);
 
-                T exclusive = T(0);
+                // the first tile of a partition starts from `init` (std::exclusive_scan's init; 0 if absent)
+                T exclusive = (tp == 0 && init) ? *init : T(0);
                 if (tp == 0 || debug_no_lookback) // debug_no_lookback: timing experiments only (wrong results)
                 {
                     if (lane == 0)
-                        st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(aggregate));
+                        st_relaxed_u64(&state[tile], k_flag_inclusive | to_bits<T>(exclusive + aggregate));
                 }
                 else
                 {
@@ -321,7 +322,7 @@ namespace glu_b200
         template<typename T, int THREADS, int VPT, int STAGES>
         __global__ void __launch_bounds__(THREADS + 128)
             scan_b32_tma_kernel(T* __restrict__ data, size_t count, uint32_t tiles_per_part, uint32_t total_tiles,
-                                uint32_t* ticket, uint64_t* state)
+                                uint32_t* ticket, uint64_t* state, const T* __restrict__ init)
         {
             constexpr int TILE = THREADS * VPT * 4;
             constexpr int WARPS = THREADS / 32; // scanner warps; then 1 producer, 2 aggregator, 1 chain warp
@@ -399,6 +400,7 @@ namespace glu_b200
                 // the tile aggregate.  They never wait on other tiles, so every tile in flight anywhere on
                 // the GPU has its aggregate out as soon as its data is on chip.
                 const unsigned me = warp - WARPS - 1;
+                const T seed = init ? *init : T(0);
                 for (uint32_t it = 0;; it++)
                 {
                     const uint32_t stage = it % STAGES;
@@ -439,7 +441,8 @@ namespace glu_b200
                     if (lane == 0)
                     {
                         mbarrier_arrive(&empty_bar[stage]); // done reading the stage
-                        st_relaxed_u64(&state[tile], (tp == 0 ? k_flag_inclusive : k_flag_aggregate) | to_bits<T>(aggregate));
+                        st_relaxed_u64(&state[tile], tp == 0 ? (k_flag_inclusive | to_bits<T>(seed + aggregate))
+                                                             : (k_flag_aggregate | to_bits<T>(aggregate)));
                         s_slot_agg[it % PSLOTS] = aggregate;
                         mbarrier_arrive(&agg_bar[it % PSLOTS]);
                     }
@@ -451,6 +454,7 @@ namespace glu_b200
             {
                 // ---- chain warp: in tile order, look back, publish the inclusive prefix, hand the exclusive
                 // prefix to the scanners.  Its predecessors' aggregates are out long before it asks.
+                const T seed = init ? *init : T(0);
                 for (uint32_t it = 0;; it++)
                 {
                     const uint32_t stage = it % STAGES;
@@ -460,7 +464,7 @@ namespace glu_b200
                         break;
                     const uint32_t part = tile / tiles_per_part;
                     const uint32_t tp = tile - part * tiles_per_part;
-                    T exclusive = T(0);
+                    T exclusive = seed;
                     if (tp != 0)
                         exclusive = lookback_walk<T>(state, tile, tp, lane);
                     // The aggregator must be done with the tile before the scanners may overwrite it in
@@ -669,7 +673,8 @@ namespace glu_b200
         template<typename S, int NC, int THREADS, int IPT>
         __global__ void __launch_bounds__(THREADS)
             scan_wide_kernel(Elem<S, NC>* __restrict__ data, size_t count, uint32_t tiles_per_part, uint32_t* ticket,
-                             uint32_t* flags, Elem<S, NC>* aggregates, Elem<S, NC>* inclusives)
+                             uint32_t* flags, Elem<S, NC>* aggregates, Elem<S, NC>* inclusives,
+                             const Elem<S, NC>* __restrict__ init)
         {
             using E = Elem<S, NC>;
             constexpr int TILE = THREADS * IPT;
@@ -728,12 +733,14 @@ namespace glu_b200
                     s_warp_prefix[lane] = wex;
                 const E aggregate = elem_shfl(winc, 31);
 
-                E exclusive = elem_zero<S, NC>();
+                E exclusive = (tp == 0 && init) ? *init : elem_zero<S, NC>();
                 if (tp == 0)
                 {
                     if (lane == 0)
                     {
-                        inclusives[tile] = aggregate;
+                        E inclusive = exclusive;
+                        elem_add(inclusive, aggregate);
+                        inclusives[tile] = inclusive;
                         st_release_u32(&flags[tile], 2u);
                     }
                 }
@@ -866,23 +873,25 @@ namespace glu_b200
         }
 
         template<typename T, int THREADS, int VPT, int MIN_BLOCKS>
-        int launch_b32_shape(T* data, size_t count, const ScanPlan& p, uint32_t* ticket, uint64_t* state, cudaStream_t s)
+        int launch_b32_shape(T* data, size_t count, const ScanPlan& p, uint32_t* ticket, uint64_t* state, cudaStream_t s,
+                             const T* init)
         {
             static const bool use_ticket = scan_env_int("GLU_SCAN_TICKET", 1) != 0;
             static const int debug_no_lookback = scan_env_int("GLU_SCAN_DEBUG_NO_LOOKBACK", 0);
             ScopedKernelProfile prof(GLU_KERNEL_SCAN, s);
             if (use_ticket)
                 scan_b32_kernel<T, THREADS, VPT, MIN_BLOCKS, true><<<unsigned(p.total_tiles), THREADS, 0, s>>>(
-                    data, count, p.tiles_per_part, ticket, state, debug_no_lookback);
+                    data, count, p.tiles_per_part, ticket, state, debug_no_lookback, init);
             else
                 scan_b32_kernel<T, THREADS, VPT, MIN_BLOCKS, false><<<unsigned(p.total_tiles), THREADS, 0, s>>>(
-                    data, count, p.tiles_per_part, ticket, state, debug_no_lookback);
+                    data, count, p.tiles_per_part, ticket, state, debug_no_lookback, init);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
 
         template<typename T, int THREADS, int VPT, int STAGES>
-        int launch_b32_tma(T* data, size_t count, const ScanPlan& p, uint32_t* ticket, uint64_t* state, cudaStream_t s)
+        int launch_b32_tma(T* data, size_t count, const ScanPlan& p, uint32_t* ticket, uint64_t* state, cudaStream_t s,
+                           const T* init)
         {
             auto kernel = scan_b32_tma_kernel<T, THREADS, VPT, STAGES>;
             constexpr size_t smem = size_t(STAGES) * THREADS * VPT * 16;
@@ -901,37 +910,38 @@ namespace glu_b200
             const uint64_t resident = uint64_t(current_sm_count()) * uint64_t(ctas_per_sm[dev] > 0 ? ctas_per_sm[dev] : 1);
             const unsigned grid = unsigned(p.total_tiles < resident ? p.total_tiles : resident);
             ScopedKernelProfile prof(GLU_KERNEL_SCAN, s);
-            kernel<<<grid, THREADS + 128, smem, s>>>(data, count, p.tiles_per_part, uint32_t(p.total_tiles), ticket, state);
+            kernel<<<grid, THREADS + 128, smem, s>>>(data, count, p.tiles_per_part, uint32_t(p.total_tiles), ticket, state, init);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
 
         template<typename T>
-        int launch_b32(void* d_data, size_t count, const ScanPlan& p, void* d_tmp, cudaStream_t s)
+        int launch_b32(void* d_data, size_t count, const ScanPlan& p, void* d_tmp, cudaStream_t s, const void* d_init)
         {
+            const T* init = static_cast<const T*>(d_init);
             uint32_t* ticket = static_cast<uint32_t*>(d_tmp);
             uint64_t* state = reinterpret_cast<uint64_t*>(static_cast<char*>(d_tmp) + k_tmp_align);
             T* data = static_cast<T*>(d_data);
             GLU_CUDA_TRY(cudaMemsetAsync(d_tmp, 0, k_tmp_align + state_bytes(p, 4), s));
             switch (p.variant)
             {
-            case 0: return launch_b32_shape<T, 256, 4, 1>(data, count, p, ticket, state, s);
-            case 1: return launch_b32_shape<T, 64, 2, 1>(data, count, p, ticket, state, s);
-            case 2: return launch_b32_shape<T, 512, 4, 1>(data, count, p, ticket, state, s);
-            case 3: return launch_b32_shape<T, 512, 8, 2>(data, count, p, ticket, state, s);
-            case 4: return launch_b32_shape<T, 1024, 4, 2>(data, count, p, ticket, state, s);
-            case 5: return launch_b32_shape<T, 256, 8, 4>(data, count, p, ticket, state, s);
-            case 6: return launch_b32_tma<T, 256, 8, 3>(data, count, p, ticket, state, s);
-            case 7: return launch_b32_tma<T, 512, 8, 3>(data, count, p, ticket, state, s);
-            case 8: return launch_b32_tma<T, 256, 8, 2>(data, count, p, ticket, state, s);
-            case 9: return launch_b32_tma<T, 512, 4, 3>(data, count, p, ticket, state, s);
-            case 10: return launch_b32_tma<T, 256, 4, 4>(data, count, p, ticket, state, s);
-            default: return launch_b32_tma<T, 512, 8, 2>(data, count, p, ticket, state, s);
+            case 0: return launch_b32_shape<T, 256, 4, 1>(data, count, p, ticket, state, s, init);
+            case 1: return launch_b32_shape<T, 64, 2, 1>(data, count, p, ticket, state, s, init);
+            case 2: return launch_b32_shape<T, 512, 4, 1>(data, count, p, ticket, state, s, init);
+            case 3: return launch_b32_shape<T, 512, 8, 2>(data, count, p, ticket, state, s, init);
+            case 4: return launch_b32_shape<T, 1024, 4, 2>(data, count, p, ticket, state, s, init);
+            case 5: return launch_b32_shape<T, 256, 8, 4>(data, count, p, ticket, state, s, init);
+            case 6: return launch_b32_tma<T, 256, 8, 3>(data, count, p, ticket, state, s, init);
+            case 7: return launch_b32_tma<T, 512, 8, 3>(data, count, p, ticket, state, s, init);
+            case 8: return launch_b32_tma<T, 256, 8, 2>(data, count, p, ticket, state, s, init);
+            case 9: return launch_b32_tma<T, 512, 4, 3>(data, count, p, ticket, state, s, init);
+            case 10: return launch_b32_tma<T, 256, 4, 4>(data, count, p, ticket, state, s, init);
+            default: return launch_b32_tma<T, 512, 8, 2>(data, count, p, ticket, state, s, init);
             }
         }
 
         template<typename S, int NC>
-        int launch_wide(void* d_data, size_t count, const ScanPlan& p, void* d_tmp, cudaStream_t s)
+        int launch_wide(void* d_data, size_t count, const ScanPlan& p, void* d_tmp, cudaStream_t s, const void* d_init)
         {
             using E = Elem<S, NC>;
             char* base = static_cast<char*>(d_tmp);
@@ -945,11 +955,13 @@ namespace glu_b200
             ScopedKernelProfile prof(GLU_KERNEL_SCAN, s);
             if (p.variant == 0)
                 scan_wide_kernel<S, NC, k_wide_threads, k_wide_ipt><<<unsigned(p.total_tiles), k_wide_threads, 0, s>>>(
-                    static_cast<E*>(d_data), count, p.tiles_per_part, ticket, flags, aggregates, inclusives);
+                    static_cast<E*>(d_data), count, p.tiles_per_part, ticket, flags, aggregates, inclusives,
+                    static_cast<const E*>(d_init));
             else
                 scan_wide_kernel<S, NC, k_wide_small_threads, k_wide_small_ipt>
                     <<<unsigned(p.total_tiles), k_wide_small_threads, 0, s>>>(
-                        static_cast<E*>(d_data), count, p.tiles_per_part, ticket, flags, aggregates, inclusives);
+                        static_cast<E*>(d_data), count, p.tiles_per_part, ticket, flags, aggregates, inclusives,
+                    static_cast<const E*>(d_init));
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
@@ -972,13 +984,19 @@ extern "C" size_t glu_scan_exclusive_tmp_bytes(size_t count, size_t num_partitio
 extern "C" int glu_scan_exclusive(void* d_data, size_t count, size_t num_partitions, int data_type, void* d_tmp,
                                   size_t tmp_bytes, glu_stream_t stream)
 {
+    return glu_scan_exclusive_init(d_data, count, num_partitions, data_type, nullptr, d_tmp, tmp_bytes, stream);
+}
+
+extern "C" int glu_scan_exclusive_init(void* d_data, size_t count, size_t num_partitions, int data_type,
+                                       const void* d_init, void* d_tmp, size_t tmp_bytes, glu_stream_t stream)
+{
     DataTypeInfo info;
     if (!data_type_info(data_type, &info))
         return GLU_ERROR_INVALID_DATA_TYPE;
     if (!d_data || count == 0 || num_partitions == 0) // glu/BlellochScan.hpp:132-135
         return GLU_ERROR_INVALID_ARGUMENT;
     const size_t esz = info.scalar_size * info.ncomp;
-    if (reinterpret_cast<uintptr_t>(d_data) % esz != 0)
+    if (reinterpret_cast<uintptr_t>(d_data) % esz != 0 || reinterpret_cast<uintptr_t>(d_init) % esz != 0)
         return GLU_ERROR_MISALIGNED;
     if (count > (size_t(1) << 40) / esz / num_partitions)
         return GLU_ERROR_COUNT_TOO_LARGE;
@@ -995,15 +1013,15 @@ extern "C" int glu_scan_exclusive(void* d_data, size_t count, size_t num_partiti
     switch (data_type)
     {
     case GLU_DATA_TYPE_UINT:
-    case GLU_DATA_TYPE_INT: return launch_b32<uint32_t>(d_data, count, p, d_tmp, s);
-    case GLU_DATA_TYPE_FLOAT: return launch_b32<float>(d_data, count, p, d_tmp, s);
-    case GLU_DATA_TYPE_DOUBLE: return launch_wide<double, 1>(d_data, count, p, d_tmp, s);
-    case GLU_DATA_TYPE_VEC2: return launch_wide<float, 2>(d_data, count, p, d_tmp, s);
-    case GLU_DATA_TYPE_VEC4: return launch_wide<float, 4>(d_data, count, p, d_tmp, s);
-    case GLU_DATA_TYPE_DVEC2: return launch_wide<double, 2>(d_data, count, p, d_tmp, s);
-    case GLU_DATA_TYPE_DVEC4: return launch_wide<double, 4>(d_data, count, p, d_tmp, s);
+    case GLU_DATA_TYPE_INT: return launch_b32<uint32_t>(d_data, count, p, d_tmp, s, d_init);
+    case GLU_DATA_TYPE_FLOAT: return launch_b32<float>(d_data, count, p, d_tmp, s, d_init);
+    case GLU_DATA_TYPE_DOUBLE: return launch_wide<double, 1>(d_data, count, p, d_tmp, s, d_init);
+    case GLU_DATA_TYPE_VEC2: return launch_wide<float, 2>(d_data, count, p, d_tmp, s, d_init);
+    case GLU_DATA_TYPE_VEC4: return launch_wide<float, 4>(d_data, count, p, d_tmp, s, d_init);
+    case GLU_DATA_TYPE_DVEC2: return launch_wide<double, 2>(d_data, count, p, d_tmp, s, d_init);
+    case GLU_DATA_TYPE_DVEC4: return launch_wide<double, 4>(d_data, count, p, d_tmp, s, d_init);
     case GLU_DATA_TYPE_UVEC2:
-    case GLU_DATA_TYPE_IVEC2: return launch_wide<uint32_t, 2>(d_data, count, p, d_tmp, s);
-    default: return launch_wide<uint32_t, 4>(d_data, count, p, d_tmp, s);
+    case GLU_DATA_TYPE_IVEC2: return launch_wide<uint32_t, 2>(d_data, count, p, d_tmp, s, d_init);
+    default: return launch_wide<uint32_t, 4>(d_data, count, p, d_tmp, s, d_init);
     }
 }

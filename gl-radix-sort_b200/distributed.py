@@ -1,0 +1,364 @@
+"""Multi-GPU composition of the three primitives: one process per GPU, ``torch.distributed`` (NCCL) for the plumbing.
+
+The reference is single-GPU; this module is what BASELINE.json's north_star adds on top:
+
+* ``DistributedReduce`` / ``DistributedBlellochScan`` shard by contiguous ranges (rank r owns the r-th range).
+  Each rank reduces its shard with the local kernel, the per-rank partials are all-gathered (a few bytes over
+  NVLink) and combined on the device — no host synchronisation, no extra pass over the data: the scan feeds the
+  rank's base into the single-pass scan as its ``init`` (``glu_scan_exclusive_init``).
+* ``DistributedRadixSort`` is an MSD split followed by a local sort:
+    1. every rank builds the 256-bin histogram of the split digit of its keys (``glu_radix_histogram_u32``);
+    2. the histograms are all-gathered, so every rank knows ``counts[src][bucket]`` exactly;
+    3. buckets are assigned to GPUs by balanced prefix (contiguous bucket ranges, ``assign_buckets``);
+    4. ONE partition pass per GPU (``glu_radix_partition_u32kv``, a onesweep pass) scatters every pair straight
+       into its destination GPU's receive buffer through NVLink peer pointers — the partition and the all-to-all
+       are the same kernel (``exchange="p2p"``, CUDA IPC mappings of the peers' buffers).  Inside the destination
+       a bucket's pairs are ordered by source rank, then by source position, which keeps the global sort stable.
+       ``exchange="nccl"`` is the two-step variant: partition into a local staging buffer, then
+       ``all_to_all_single``;
+    5. every rank sorts what it received with the local onesweep sort.  The concatenation of the ranks' outputs
+       in rank order is the stable sort of the concatenation of the inputs.
+
+The host-side planning (``choose_split_shift``, ``assign_buckets``, ``plan_exchange``) is plain numpy so that it can be
+tested on CPU with the gloo backend (tests/test_distributed_cpu.py).  Everything that touches data runs in
+libglu_b200.so on the GPU; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+RADIX_BITS = 8
+RADIX = 1 << RADIX_BITS
+
+
+# ------------------------------------------------------------------------------------------------ host-side planning
+
+def choose_split_shift(key_min: int, key_max: int, bits: int = RADIX_BITS) -> int:
+    """Shift of the highest `bits`-wide digit in which the keys of [key_min, key_max] can differ.
+
+    All bits above the digit are equal in every key, so bucket order == key order.  Uniform 32-bit keys give
+    24 (the top byte, north_star's "top-8-bit histogram"); keys that only use their low 16 bits give 8."""
+    varying = (int(key_min) ^ int(key_max)).bit_length()
+    return max(0, varying - bits)
+
+
+def assign_buckets(global_counts: np.ndarray, world: int) -> np.ndarray:
+    """Destination rank of every bucket: contiguous, monotone bucket ranges with about total/world pairs each.
+
+    A bucket goes to the rank in whose share of the global order its midpoint falls."""
+    counts = np.asarray(global_counts, dtype=np.int64)
+    total = int(counts.sum())
+    if total == 0:
+        return np.zeros(counts.size, dtype=np.int64)
+    exclusive = np.cumsum(counts) - counts
+    dest = (2 * exclusive + counts) * world // (2 * total)
+    return np.minimum(dest, world - 1).astype(np.int64)
+
+
+@dataclass
+class ExchangePlan:
+    dest: np.ndarray          # [RADIX]        destination rank of each bucket
+    send_counts: np.ndarray   # [world, world] pairs rank s sends to rank g
+    recv_totals: np.ndarray   # [world]        pairs each rank ends up with
+    dst_offset: np.ndarray    # [world, RADIX] where rank s's run of bucket b starts in dest[b]'s receive buffer
+    src_offset: np.ndarray    # [world, RADIX] where bucket b starts in rank s's own bucket-major order
+
+
+def plan_exchange(hist_all: np.ndarray) -> ExchangePlan:
+    """From counts[src][bucket] (the all-gathered histograms) to the complete layout of the all-to-all.
+
+    Receive layout of rank g: its buckets in increasing order; inside a bucket the sources in rank order; inside a
+    source the pairs in source order.  Equal keys therefore stay in global input order (rank, then position)."""
+    counts = np.asarray(hist_all, dtype=np.int64)
+    world, radix = counts.shape
+    dest = assign_buckets(counts.sum(axis=0), world)
+    send_counts = np.zeros((world, world), dtype=np.int64)
+    for g in range(world):
+        send_counts[:, g] = counts[:, dest == g].sum(axis=1)
+    recv_totals = send_counts.sum(axis=0)
+    dst_offset = np.zeros((world, radix), dtype=np.int64)
+    fill = np.zeros(world, dtype=np.int64)
+    for b in range(radix):
+        g = int(dest[b])
+        within = np.cumsum(counts[:, b]) - counts[:, b]
+        dst_offset[:, b] = fill[g] + within
+        fill[g] += int(counts[:, b].sum())
+    src_offset = np.cumsum(counts, axis=1) - counts
+    return ExchangePlan(dest, send_counts, recv_totals, dst_offset, src_offset)
+
+
+# ------------------------------------------------------------------------------------------------------ GPU side
+
+def _glu():
+    import sys
+
+    return sys.modules[__name__.rsplit(".", 1)[0]]
+
+
+def _dist():
+    import torch.distributed as dist
+
+    if not dist.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised (launch with torchrun / init_process_group('nccl'))")
+    return dist
+
+
+class _DeviceArray:
+    """A glu_malloc'ed (cudaMalloc, hence CUDA-IPC exportable) int32 array viewed as a torch tensor."""
+
+    def __init__(self, n_elems: int, device):
+        import torch
+
+        glu = _glu()
+        self.ptr = ctypes.c_void_p()
+        self.n = int(n_elems)
+        glu.check(glu.lib.glu_malloc(ctypes.byref(self.ptr), 4 * max(self.n, 1)), "glu_malloc")
+        self.__cuda_array_interface__ = {"shape": (max(self.n, 1),), "typestr": "<i4", "data": (self.ptr.value, False),
+                                         "version": 2, "strides": None}
+        self.tensor = torch.as_tensor(self, device=device)
+
+    def free(self):
+        if self.ptr:
+            self.tensor = None
+            _glu().lib.glu_free(self.ptr)
+            self.ptr = ctypes.c_void_p()
+
+
+class DistributedReduce:
+    """Reduce over a buffer sharded by contiguous ranges: after the call element 0 of EVERY rank's shard holds the
+    global result (glu::Reduce leaves its result in element 0, glu/Reduce.hpp:111-135)."""
+
+    def __init__(self, data_type, operator_, group=None):
+        glu = _glu()
+        self._local = glu.Reduce(data_type, operator_)  # validates like the reference
+        self.data_type, self.operator, self.group = self._local.data_type, self._local.operator, group
+        self._esz = glu.data_type_size(self.data_type)
+        self._gathered = None
+
+    def __call__(self, buffer, count: int) -> None:
+        import torch
+
+        glu, dist = _glu(), _dist()
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if count <= 0:
+            raise glu.GluError(1, "Count must be greater than zero (every rank owns a non-empty range)")
+        ptr, dev = glu._ptr_and_device(buffer)
+        dev = glu._device_of(dev)
+        if self._gathered is None or self._gathered.device != dev:
+            self._gathered = torch.empty((world + 1) * self._esz, dtype=torch.uint8, device=dev)
+        gathered = self._gathered
+        partial = gathered[world * self._esz:]
+        need = int(glu.lib.glu_reduce_tmp_bytes(count, int(self.data_type)))
+        tmp, tmp_bytes = self._local._scratch.ensure(need, dev)
+        st = glu._current_stream(dev)
+        glu.check(glu.lib.glu_reduce_into(ptr, count, int(self.data_type), int(self.operator), partial.data_ptr(),
+                                          tmp, tmp_bytes, st), "DistributedReduce (local)")
+        dist.all_gather_into_tensor(gathered[: world * self._esz], partial, group=self.group)
+        glu.check(glu.lib.glu_reduce_into(gathered.data_ptr(), world, int(self.data_type), int(self.operator), ptr,
+                                          tmp, tmp_bytes, st), "DistributedReduce (combine)")
+
+
+class DistributedBlellochScan:
+    """Exclusive prefix sum of ONE sequence sharded by contiguous ranges in rank order.  12 B of HBM traffic per
+    4-byte element: a reduce pass for the rank totals (4 B), an all-gather of `world` elements, and the
+    single-pass scan seeded with the rank's base (8 B)."""
+
+    def __init__(self, data_type, group=None):
+        glu = _glu()
+        self._scan = glu.BlellochScan(data_type)
+        self._reduce = glu.Reduce(data_type, glu.ReduceOperator_Sum)
+        self.data_type, self.group = self._scan.data_type, group
+        self._esz = glu.data_type_size(self.data_type)
+        self._gathered = None
+        self._small = glu._Scratch()
+
+    def __call__(self, buffer, count: int) -> None:
+        import torch
+
+        glu, dist = _glu(), _dist()
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if count <= 0:
+            raise glu.GluError(1, "Count must be greater than zero (every rank owns a non-empty range)")
+        ptr, dev = glu._ptr_and_device(buffer)
+        dev = glu._device_of(dev)
+        dt, esz = int(self.data_type), self._esz
+        if self._gathered is None or self._gathered.device != dev:
+            self._gathered = torch.empty((world + 1) * esz, dtype=torch.uint8, device=dev)
+        gathered = self._gathered
+        total = gathered[world * esz:]
+        st = glu._current_stream(dev)
+        tmp, tmp_bytes = self._reduce._scratch.ensure(int(glu.lib.glu_reduce_tmp_bytes(count, dt)), dev)
+        glu.check(glu.lib.glu_reduce_into(ptr, count, dt, int(glu.ReduceOperator_Sum), total.data_ptr(), tmp, tmp_bytes,
+                                          st), "DistributedBlellochScan (rank total)")
+        dist.all_gather_into_tensor(gathered[: world * esz], total, group=self.group)
+        # exclusive scan of the `world` totals: element `rank` becomes this rank's base
+        stmp, stmp_bytes = self._small.ensure(int(glu.lib.glu_scan_exclusive_tmp_bytes(world, 1, dt)), dev)
+        glu.check(glu.lib.glu_scan_exclusive(gathered.data_ptr(), world, 1, dt, stmp, stmp_bytes, st),
+                  "DistributedBlellochScan (bases)")
+        need = int(glu.lib.glu_scan_exclusive_tmp_bytes(count, 1, dt))
+        tmp, tmp_bytes = self._scan._scratch.ensure(need, dev)
+        glu.check(glu.lib.glu_scan_exclusive_init(ptr, count, 1, dt, gathered.data_ptr() + rank * esz, tmp, tmp_bytes,
+                                                  st), "DistributedBlellochScan (seeded scan)")
+
+
+class DistributedRadixSort:
+    """Stable sort of uint32 (key, value) pairs spread over the ranks of `group` (MSD split + local sort).
+
+    ``sorter(keys, vals, count)`` takes this rank's `count` pairs (CUDA tensors or device pointers; not modified)
+    and returns ``(sorted_keys, sorted_vals, m)``: int32-typed tensor views (uint32 bit patterns) of this rank's
+    slice of the global result, valid until the next call.  Rank r's keys are <= rank r+1's."""
+
+    def __init__(self, max_count: int, group=None, capacity_factor: float = 1.25, exchange: str = "auto",
+                 split_shift: int | str = 32 - RADIX_BITS):
+        import torch
+
+        glu, dist = _glu(), _dist()
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.max_count = int(max_count)
+        self.capacity = int(max_count * capacity_factor) + 1024
+        self.split_shift = split_shift
+        if self.capacity > (1 << 30):
+            raise glu.GluError(6, "DistributedRadixSort: per-rank capacity exceeds 2^30 pairs")
+        self._recv_keys = _DeviceArray(self.capacity, self.device)
+        self._recv_vals = _DeviceArray(self.capacity, self.device)
+        self._sorter = glu.RadixSort()
+        self._sorter.prepare_internal_buffers(self.capacity, self.device)
+        self._part_tmp = torch.empty(int(glu.lib.glu_radix_partition_u32kv_tmp_bytes(self.max_count)), dtype=torch.uint8,
+                                     device=self.device)
+        self._hist = torch.zeros(RADIX, dtype=torch.int32, device=self.device)
+        self._hist_all = torch.zeros(self.world * RADIX, dtype=torch.int32, device=self.device)
+        self._tables = torch.zeros(2 * RADIX, dtype=torch.int64, device=self.device)
+        self._tables_host = torch.zeros(2 * RADIX, dtype=torch.int64).pin_memory()
+        self._minmax = None
+        self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._peer_keys = self._peer_vals = None
+        self._stage_keys = self._stage_vals = None
+        self.exchange = self._setup_exchange(exchange)
+        self.last_plan = None
+
+    # -- peer mappings (CUDA IPC): rank g's receive buffers mapped into this process
+    def _setup_exchange(self, exchange: str) -> str:
+        import torch
+
+        glu, dist = _glu(), _dist()
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError(exchange)
+        ok, err = True, ""
+        if exchange in ("auto", "p2p"):
+            try:
+                hk = ctypes.create_string_buffer(64)
+                hv = ctypes.create_string_buffer(64)
+                glu.check(glu.lib.glu_ipc_get_handle(self._recv_keys.ptr, hk), "glu_ipc_get_handle")
+                glu.check(glu.lib.glu_ipc_get_handle(self._recv_vals.ptr, hv), "glu_ipc_get_handle")
+                mine = (hk.raw, hv.raw)
+            except glu.GluError as e:  # pragma: no cover - depends on the box
+                mine, ok, err = None, False, str(e)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mine, group=self.group)
+            ok = ok and all(h is not None for h in handles)
+            peer_keys, peer_vals = [0] * self.world, [0] * self.world
+            if ok:
+                try:
+                    for g, h in enumerate(handles):
+                        if g == self.rank:
+                            peer_keys[g], peer_vals[g] = self._recv_keys.ptr.value, self._recv_vals.ptr.value
+                            continue
+                        pk, pv = ctypes.c_void_p(), ctypes.c_void_p()
+                        glu.check(glu.lib.glu_ipc_open_handle(h[0], ctypes.byref(pk)), "glu_ipc_open_handle")
+                        glu.check(glu.lib.glu_ipc_open_handle(h[1], ctypes.byref(pv)), "glu_ipc_open_handle")
+                        peer_keys[g], peer_vals[g] = pk.value, pv.value
+                except glu.GluError as e:  # pragma: no cover
+                    ok, err = False, str(e)
+            flags = [None] * self.world
+            dist.all_gather_object(flags, ok, group=self.group)
+            if all(flags):
+                self._peer_keys = np.array(peer_keys, dtype=np.int64)
+                self._peer_vals = np.array(peer_vals, dtype=np.int64)
+                return "p2p"
+            if exchange == "p2p":
+                raise glu.GluError(7, f"DistributedRadixSort: CUDA IPC peer mapping failed ({err})")
+        self._stage_keys = torch.empty(self.max_count, dtype=torch.int32, device=self.device)
+        self._stage_vals = torch.empty(self.max_count, dtype=torch.int32, device=self.device)
+        return "nccl"
+
+    def _split_shift(self, kptr: int, count: int, st: int) -> int:
+        import torch
+
+        glu, dist = _glu(), _dist()
+        if self.split_shift != "auto":
+            return int(self.split_shift)
+        # adaptive split digit: the highest 8 bits in which any two keys of the job differ
+        if self._minmax is None:
+            self._minmax = torch.zeros(2 * (self.world + 1), dtype=torch.int32, device=self.device)
+            self._mm_reduce = glu.Reduce(glu.DataType_Uint, glu.ReduceOperator_Min)
+        mm = self._minmax
+        mine = mm[2 * self.world:]
+        tmp, tmp_bytes = self._mm_reduce._scratch.ensure(int(glu.lib.glu_reduce_tmp_bytes(count, 3)), self.device)
+        glu.check(glu.lib.glu_reduce_into(kptr, count, 3, int(glu.ReduceOperator_Min), mine.data_ptr(), tmp, tmp_bytes, st),
+                  "DistributedRadixSort (min)")
+        glu.check(glu.lib.glu_reduce_into(kptr, count, 3, int(glu.ReduceOperator_Max), mine.data_ptr() + 4, tmp, tmp_bytes,
+                                          st), "DistributedRadixSort (max)")
+        dist.all_gather_into_tensor(mm[: 2 * self.world], mine, group=self.group)
+        host = mm[: 2 * self.world].cpu().numpy().view(np.uint32).reshape(self.world, 2)
+        return choose_split_shift(int(host[:, 0].min()), int(host[:, 1].max()))
+
+    def __call__(self, key_buffer, val_buffer, count: int):
+        import torch
+
+        glu, dist = _glu(), _dist()
+        kptr, kdev = glu._ptr_and_device(key_buffer)
+        vptr, _ = glu._ptr_and_device(val_buffer)
+        if not kptr or not vptr:
+            raise glu.GluError(1, "Invalid key / value buffer")
+        if count < 1 or count > self.max_count:
+            raise glu.GluError(1, f"count must be in [1, {self.max_count}]")
+        st = glu._current_stream(self.device)
+        shift = self._split_shift(kptr, count, st)
+
+        # 1-2. local digit histogram -> counts[src][bucket] on every rank (this all-gather also orders this call's
+        #      peer writes after every rank's previous use of its receive buffers)
+        glu.check(glu.lib.glu_radix_histogram_u32(kptr, count, shift, RADIX_BITS, self._hist.data_ptr(), st),
+                  "glu_radix_histogram_u32")
+        dist.all_gather_into_tensor(self._hist_all, self._hist, group=self.group)
+        hist_all = self._hist_all.cpu().numpy().view(np.uint32).reshape(self.world, RADIX)
+
+        # 3. bucket -> GPU assignment and the receive layout
+        plan = plan_exchange(hist_all)
+        self.last_plan = plan
+        m = int(plan.recv_totals[self.rank])
+        if int(plan.recv_totals.max()) > self.capacity:
+            raise glu.GluError(6, f"DistributedRadixSort: a rank would receive {int(plan.recv_totals.max())} pairs, "
+                                  f"capacity is {self.capacity} (raise capacity_factor or use split_shift='auto')")
+
+        # 4. partition (+ all-to-all)
+        tables = self._tables_host.numpy()
+        if self.exchange == "p2p":
+            tables[:RADIX] = self._peer_keys[plan.dest] + 4 * plan.dst_offset[self.rank]
+            tables[RADIX:] = self._peer_vals[plan.dest] + 4 * plan.dst_offset[self.rank]
+        else:
+            tables[:RADIX] = self._stage_keys.data_ptr() + 4 * plan.src_offset[self.rank]
+            tables[RADIX:] = self._stage_vals.data_ptr() + 4 * plan.src_offset[self.rank]
+        self._tables.copy_(self._tables_host, non_blocking=True)
+        glu.check(glu.lib.glu_radix_partition_u32kv(kptr, vptr, count, shift, RADIX_BITS, self._tables.data_ptr(),
+                                                    self._tables.data_ptr() + 8 * RADIX, self._part_tmp.data_ptr(),
+                                                    self._part_tmp.numel(), st), "glu_radix_partition_u32kv")
+        rk, rv = self._recv_keys.tensor, self._recv_vals.tensor
+        if self.exchange == "p2p":
+            # device-side barrier: when this tiny all-reduce completes, every rank's partition kernel has completed,
+            # i.e. every pair destined to this rank has landed in its receive buffers
+            dist.all_reduce(self._token, group=self.group)
+        else:
+            in_splits = [int(x) for x in plan.send_counts[self.rank]]
+            out_splits = [int(x) for x in plan.send_counts[:, self.rank]]
+            dist.all_to_all_single(rk[:m], self._stage_keys[:count], out_splits, in_splits, group=self.group)
+            dist.all_to_all_single(rv[:m], self._stage_vals[:count], out_splits, in_splits, group=self.group)
+
+        # 5. local sort of everything this rank received
+        if m > 1:
+            self._sorter(rk, rv, m)
+        return rk[:m], rv[:m], m

@@ -139,6 +139,40 @@ GLU_API size_t glu_radix_sort_u32kv_tmp_bytes(size_t count);
 GLU_API int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t count, size_t num_steps, void* d_tmp,
                                  size_t tmp_bytes, glu_stream_t stream);
 
+/* ------------------------------------------------------------------ building blocks of the multi-GPU path
+ * Not in the reference (it is single-GPU); these are what gl-radix-sort_b200/distributed.py composes with
+ * NCCL / NVLink peer memory (DESIGN.md "Multi-GPU").  Same conventions as above. */
+
+/* glu_reduce with the result written to d_result[0] (one element) instead of d_data[0]; d_data is not modified.
+ * count == 1 copies the element. */
+GLU_API int glu_reduce_into(const void* d_data, size_t count, int data_type, int op, void* d_result, void* d_tmp,
+                            size_t tmp_bytes, glu_stream_t stream);
+
+/* glu_scan_exclusive starting every partition from *d_init (one element in device memory, read when the kernel
+ * runs: the std::exclusive_scan `init`) instead of 0; d_init == NULL means 0.  A rank's base in a sharded scan. */
+GLU_API int glu_scan_exclusive_init(void* d_data, size_t count, size_t num_partitions, int data_type,
+                                    const void* d_init, void* d_tmp, size_t tmp_bytes, glu_stream_t stream);
+
+/* d_hist[0 .. 256) <- number of keys whose digit ((key >> shift) & ((1 << bits) - 1)) has each value
+ * (bins >= 1 << bits stay 0); 1 <= bits <= 8.  Reads the keys once. */
+GLU_API int glu_radix_histogram_u32(const uint32_t* d_keys, size_t count, unsigned shift, unsigned bits,
+                                    uint32_t* d_hist, glu_stream_t stream);
+
+/* Stable partition of the pairs by one digit — one onesweep pass whose output is a table of destinations:
+ * the i-th pair (in input order) whose digit is d goes to d_key_dst[d][i] / d_val_dst[d][i].  d_key_dst and
+ * d_val_dst are DEVICE arrays of 1 << bits pointers; the pointers may address peer GPUs' memory (NVLink P2P),
+ * which turns the pass into a fused partition + all-to-all.  Inputs are not modified. */
+GLU_API size_t glu_radix_partition_u32kv_tmp_bytes(size_t count);
+GLU_API int glu_radix_partition_u32kv(const uint32_t* d_keys, const uint32_t* d_vals, size_t count, unsigned shift,
+                                      unsigned bits, uint32_t* const* d_key_dst, uint32_t* const* d_val_dst,
+                                      void* d_tmp, size_t tmp_bytes, glu_stream_t stream);
+
+/* CUDA IPC plumbing for one-process-per-GPU peer access: export a glu_malloc'ed allocation, map a peer's. */
+#define GLU_IPC_HANDLE_BYTES 64
+GLU_API int glu_ipc_get_handle(void* d_ptr, unsigned char handle[GLU_IPC_HANDLE_BYTES]);
+GLU_API int glu_ipc_open_handle(const unsigned char handle[GLU_IPC_HANDLE_BYTES], void** d_ptr);
+GLU_API int glu_ipc_close_handle(void* d_ptr);
+
 /* ------------------------------------------------------------------------ host-buffer entry points (e2e)
  * Same semantics on HOST arrays: upload -> hot path -> download, synchronous.  These are what the
  * reference's test-suite does around every call with ShaderStorageBuffer(data) ... get_data<T>()

@@ -1,0 +1,168 @@
+"""CPU tests (no GPU) of the host-side logic of the multi-GPU path: bucket assignment, exchange layout, and a
+world_size-2 gloo run that performs the planned all-to-all on CPU tensors.  The data movement itself is emulated
+with numpy here (the product does it in glu_radix_partition_u32kv on the GPU); what is under test is that the PLAN
+— destinations, offsets, split sizes, stability across ranks — yields the oracle's stable sort."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def dmod(glu):
+    return glu.distributed
+
+
+def test_choose_split_shift(dmod):
+    assert dmod.choose_split_shift(0, 0xFFFFFFFF) == 24
+    assert dmod.choose_split_shift(48271, 2147483426) == 23      # the reference generator's 31-bit keys
+    assert dmod.choose_split_shift(0, 0xFFFF) == 8                # 16-bit-entropy keys
+    assert dmod.choose_split_shift(5, 5) == 0
+    assert dmod.choose_split_shift(0x12340000, 0x1234FFFF) == 8   # constant high bits do not matter
+
+
+def test_assign_buckets_balanced_and_monotone(dmod):
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 4, 8):
+        counts = rng.integers(0, 1000, size=256)
+        dest = dmod.assign_buckets(counts, world)
+        assert dest.min() >= 0 and dest.max() <= world - 1
+        assert np.all(np.diff(dest) >= 0)
+        loads = np.bincount(dest, weights=counts, minlength=world)
+        assert loads.max() <= counts.sum() / world + counts.max()
+    # everything in one bucket: it cannot be split, one rank takes all
+    one = np.zeros(256, dtype=np.int64)
+    one[17] = 12345
+    assert len(set(dmod.assign_buckets(one, 8).tolist())) >= 1
+    assert dmod.assign_buckets(np.zeros(256), 4).tolist() == [0] * 256
+
+
+def emulate(dmod, shards_k, shards_v, shift):
+    """numpy emulation of DistributedRadixSort's data movement driven by plan_exchange."""
+    world = len(shards_k)
+    hist_all = np.stack([np.bincount((k >> shift) & 0xFF, minlength=256) for k in shards_k])
+    plan = dmod.plan_exchange(hist_all)
+    recv_k = [np.zeros(int(t), dtype=np.uint32) for t in plan.recv_totals]
+    recv_v = [np.zeros(int(t), dtype=np.uint32) for t in plan.recv_totals]
+    written = [np.zeros(int(t), dtype=np.int32) for t in plan.recv_totals]
+    for s in range(world):
+        digit = (shards_k[s] >> shift) & 0xFF
+        for b in range(256):
+            sel = np.nonzero(digit == b)[0]  # stable partition: source order inside a bucket
+            g, off = int(plan.dest[b]), int(plan.dst_offset[s][b])
+            recv_k[g][off:off + sel.size] = shards_k[s][sel]
+            recv_v[g][off:off + sel.size] = shards_v[s][sel]
+            written[g][off:off + sel.size] += 1
+    for w in written:
+        assert np.all(w == 1)  # the layout tiles every receive buffer exactly once
+    out_k, out_v = [], []
+    for g in range(world):
+        order = np.argsort(recv_k[g], kind="stable")
+        out_k.append(recv_k[g][order])
+        out_v.append(recv_v[g][order])
+    return plan, np.concatenate(out_k), np.concatenate(out_v)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("kind", ["uniform", "ref31", "ent16", "dups"])
+def test_plan_exchange_gives_stable_global_sort(dmod, oracle, world, kind):
+    n = 20011
+    shards_k, shards_v = [], []
+    for r in range(world):
+        if kind == "uniform":
+            k = oracle.mt19937_u32(10 + r, n + 13 * r)
+        elif kind == "ref31":
+            k = oracle.random_u32(1 + r, n, 0, 0xFFFFFFFF)
+        elif kind == "ent16":
+            k = oracle.mt19937_u32(10 + r, n) & np.uint32(0xFFFF)
+        else:
+            k = oracle.random_u32(1 + r, n, 0, 10)
+        shards_k.append(k)
+    base = 0
+    for k in shards_k:
+        shards_v.append(np.arange(base, base + k.size, dtype=np.uint32))
+        base += k.size
+    allk, allv = np.concatenate(shards_k), np.concatenate(shards_v)
+    shift = dmod.choose_split_shift(int(allk.min()), int(allk.max()))
+    plan, gk, gv = emulate(dmod, shards_k, shards_v, shift)
+    ek, ev = oracle.stable_sort_pairs(allk, allv)
+    np.testing.assert_array_equal(gk, ek)
+    np.testing.assert_array_equal(gv, ev)
+    assert int(plan.send_counts.sum()) == allk.size
+    np.testing.assert_array_equal(plan.send_counts.sum(axis=0), plan.recv_totals)
+    if kind == "uniform" and world > 1:
+        assert plan.recv_totals.max() < 1.1 * allk.size / world
+
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["GLU_ROOT"])
+import __graft_entry__ as entry
+import oracle
+glu = entry.load_package()
+dmod = glu.distributed
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 30011 + 17 * rank
+keys = oracle.mt19937_u32(100 + rank, n)
+if os.environ.get("GLU_KIND") == "dups":
+    keys = keys % np.uint32(7)
+counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(counts, torch.tensor([n], dtype=torch.int64))
+base = int(sum(int(c) for c in counts[:rank]))
+vals = np.arange(base, base + n, dtype=np.uint32)
+# min / max -> split digit (all-gather, as DistributedRadixSort(split_shift="auto") does)
+mm = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(mm, torch.tensor([int(keys.min()), int(keys.max())], dtype=torch.int64))
+shift = dmod.choose_split_shift(min(int(x[0]) for x in mm), max(int(x[1]) for x in mm))
+# 1-2. histograms, all-gathered
+digit = (keys >> shift) & 0xFF
+hist = torch.from_numpy(np.bincount(digit, minlength=256).astype(np.int64))
+hists = [torch.zeros(256, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(hists, hist)
+plan = dmod.plan_exchange(torch.stack(hists).numpy())
+# 4. stable local partition (the GPU path does this in glu_radix_partition_u32kv), then the planned all-to-all
+order = np.argsort(digit, kind="stable")
+stage_k = torch.from_numpy(keys[order].view(np.int32).copy())
+stage_v = torch.from_numpy(vals[order].view(np.int32).copy())
+m = int(plan.recv_totals[rank])
+in_splits = [int(x) for x in plan.send_counts[rank]]
+out_splits = [int(x) for x in plan.send_counts[:, rank]]
+rk = torch.zeros(m, dtype=torch.int32)
+rv = torch.zeros(m, dtype=torch.int32)
+dist.all_to_all_single(rk, stage_k, out_splits, in_splits)
+dist.all_to_all_single(rv, stage_v, out_splits, in_splits)
+rk, rv = rk.numpy().view(np.uint32), rv.numpy().view(np.uint32)
+o = np.argsort(rk, kind="stable")
+rk, rv = rk[o], rv[o]
+# gather everything on rank 0 and compare with the oracle on the concatenated input
+gathered = [None] * world
+dist.gather_object((keys, vals, rk, rv), gathered if rank == 0 else None, dst=0)
+if rank == 0:
+    allk = np.concatenate([g[0] for g in gathered]); allv = np.concatenate([g[1] for g in gathered])
+    gk = np.concatenate([g[2] for g in gathered]); gv = np.concatenate([g[3] for g in gathered])
+    ek, ev = oracle.stable_sort_pairs(allk, allv)
+    assert np.array_equal(gk, ek) and np.array_equal(gv, ev), "distributed plan does not reproduce the stable sort"
+    print("OK", world, shift, [int(x) for x in plan.recv_totals])
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("kind", ["uniform", "dups"])
+def test_gloo_world2_exchange(tmp_path, kind, oracle):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, GLU_ROOT=ROOT, GLU_KIND=kind, OMP_NUM_THREADS="1")
+    port = 29500 + (os.getpid() % 500) + (1 if kind == "dups" else 0)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "OK 2" in r.stdout

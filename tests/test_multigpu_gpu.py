@@ -1,0 +1,225 @@
+"""GPU parity tests of the multi-GPU building blocks (glu_reduce_into, glu_scan_exclusive_init,
+glu_radix_histogram_u32, glu_radix_partition_u32kv) and of gl-radix-sort_b200/distributed.py, which is run in
+one process per GPU under torch.distributed.run over NCCL with as many ranks as the box has GPUs (at most 2;
+with one GPU the same code runs as a world of 1, which still goes through histogram -> plan -> peer-pointer
+partition -> local sort).  The oracle is the checker only."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import to_device, to_host
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _stream(dev):
+    import torch
+
+    return int(torch.cuda.current_stream(dev).cuda_stream)
+
+
+@pytest.mark.parametrize("n", [1, 5, 4097, 1_000_003])
+@pytest.mark.parametrize("shift,bits", [(0, 8), (8, 8), (24, 8), (27, 5), (3, 1)])
+def test_radix_histogram(glu, cuda_device, oracle, n, shift, bits):
+    import torch
+
+    keys = oracle.mt19937_u32(3, n + 1)
+    dk = to_device(keys, cuda_device)
+    hist = torch.full((256,), -1, dtype=torch.int32, device=cuda_device)
+    for off in (0, 1):  # 16-byte aligned and misaligned key pointers
+        glu.check(glu.lib.glu_radix_histogram_u32(dk.data_ptr() + 4 * off, n, shift, bits, hist.data_ptr(),
+                                                  _stream(cuda_device)), "hist")
+        want = np.bincount((keys[off:off + n] >> shift) & ((1 << bits) - 1), minlength=256)
+        np.testing.assert_array_equal(to_host(hist, np.uint32), want.astype(np.uint32))
+
+
+@pytest.mark.parametrize("n", [1, 33, 7679, 7680, 7681, 200_003, 3_000_017])
+@pytest.mark.parametrize("shift,bits,kind", [(24, 8, "uniform"), (8, 8, "uniform"), (0, 8, "dups"), (28, 4, "uniform")])
+def test_radix_partition_matches_stable_partition(glu, cuda_device, oracle, n, shift, bits, kind):
+    import torch
+
+    keys = oracle.mt19937_u32(5, n)
+    if kind == "dups":
+        keys = keys % np.uint32(3)
+    vals = np.arange(n, dtype=np.uint32)
+    digit = (keys >> shift) & ((1 << bits) - 1)
+    counts = np.bincount(digit, minlength=256).astype(np.int64)
+    offs = np.cumsum(counts) - counts
+    dk, dv = to_device(keys, cuda_device), to_device(vals, cuda_device)
+    ok = torch.zeros(n, dtype=torch.int32, device=cuda_device)
+    ov = torch.zeros(n, dtype=torch.int32, device=cuda_device)
+    tables = torch.from_numpy(np.concatenate([ok.data_ptr() + 4 * offs, ov.data_ptr() + 4 * offs])).to(cuda_device)
+    tmp = torch.empty(int(glu.lib.glu_radix_partition_u32kv_tmp_bytes(n)), dtype=torch.uint8, device=cuda_device)
+    glu.check(glu.lib.glu_radix_partition_u32kv(dk.data_ptr(), dv.data_ptr(), n, shift, bits, tables.data_ptr(),
+                                                tables.data_ptr() + 8 * 256, tmp.data_ptr(), tmp.numel(),
+                                                _stream(cuda_device)), "partition")
+    order = np.argsort(digit, kind="stable")
+    np.testing.assert_array_equal(to_host(ok, np.uint32), keys[order])
+    np.testing.assert_array_equal(to_host(ov, np.uint32), vals[order])
+    np.testing.assert_array_equal(to_host(dk, np.uint32), keys)  # inputs untouched
+
+
+def test_reduce_into_leaves_the_data_alone(glu, cuda_device, oracle):
+    import torch
+
+    data = oracle.mt19937_u32(11, 1_000_003)
+    dd = to_device(data, cuda_device)
+    out = torch.zeros(4, dtype=torch.int32, device=cuda_device)
+    tmp = torch.empty(int(glu.lib.glu_reduce_tmp_bytes(data.size, 3)), dtype=torch.uint8, device=cuda_device)
+    for op in (oracle.OP_SUM, oracle.OP_MUL, oracle.OP_MIN, oracle.OP_MAX):
+        glu.check(glu.lib.glu_reduce_into(dd.data_ptr(), data.size, 3, op, out.data_ptr() + 4, tmp.data_ptr(), tmp.numel(),
+                                          _stream(cuda_device)), "reduce_into")
+        assert int(to_host(out, np.uint32)[1]) == oracle.reduce(data, op)
+    np.testing.assert_array_equal(to_host(dd, np.uint32), data)
+    glu.check(glu.lib.glu_reduce_into(dd.data_ptr() + 40, 1, 3, 0, out.data_ptr(), tmp.data_ptr(), tmp.numel(),
+                                      _stream(cuda_device)), "reduce_into")
+    assert int(to_host(out, np.uint32)[0]) == int(data[10])
+
+
+@pytest.mark.parametrize("n", [1, 100, 8192, 70_001, (1 << 23) + 5])
+def test_scan_init_uint(glu, cuda_device, oracle, n):
+    import torch
+
+    data = oracle.mt19937_u32(12, n)
+    init = np.array([0xFFFFFF00], dtype=np.uint32)
+    dd, di = to_device(data, cuda_device), to_device(init, cuda_device)
+    tmp = torch.empty(int(glu.lib.glu_scan_exclusive_tmp_bytes(n, 1, 3)), dtype=torch.uint8, device=cuda_device)
+    glu.check(glu.lib.glu_scan_exclusive_init(dd.data_ptr(), n, 1, 3, di.data_ptr(), tmp.data_ptr(), tmp.numel(),
+                                              _stream(cuda_device)), "scan_init")
+    want = (oracle.exclusive_scan(data).astype(np.uint64) + int(init[0])).astype(np.uint32)
+    np.testing.assert_array_equal(to_host(dd, np.uint32), want)
+
+
+def test_scan_init_partitions_and_wide_types(glu, cuda_device, oracle):
+    import torch
+
+    # every partition starts from init
+    data = oracle.random_u32(123, 1000 * 37, 0, 100)
+    dd, di = to_device(data, cuda_device), to_device(np.array([7], dtype=np.uint32), cuda_device)
+    tmp = torch.empty(int(glu.lib.glu_scan_exclusive_tmp_bytes(1000, 37, 3)), dtype=torch.uint8, device=cuda_device)
+    glu.check(glu.lib.glu_scan_exclusive_init(dd.data_ptr(), 1000, 37, 3, di.data_ptr(), tmp.data_ptr(), tmp.numel(),
+                                              _stream(cuda_device)), "scan_init")
+    np.testing.assert_array_equal(to_host(dd, np.uint32), oracle.exclusive_scan(data, 1000, 37) + np.uint32(7))
+    # double (wide kernel): integers stored as doubles stay exact
+    n = 50_001
+    d64 = oracle.random_u32(5, n, 0, 1000).astype(np.float64)
+    dd = torch.from_numpy(d64.copy()).to(cuda_device)
+    di = torch.tensor([1e6], dtype=torch.float64, device=cuda_device)
+    tmp = torch.empty(int(glu.lib.glu_scan_exclusive_tmp_bytes(n, 1, 1)), dtype=torch.uint8, device=cuda_device)
+    glu.check(glu.lib.glu_scan_exclusive_init(dd.data_ptr(), n, 1, 1, di.data_ptr(), tmp.data_ptr(), tmp.numel(),
+                                              _stream(cuda_device)), "scan_init")
+    want = 1e6 + np.concatenate([[0.0], np.cumsum(d64)[:-1]])
+    np.testing.assert_array_equal(dd.cpu().numpy(), want)
+
+
+WORKER = r'''
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["GLU_ROOT"])
+import __graft_entry__ as entry
+import oracle
+glu = entry.load_package()
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+rank, world = dist.get_rank(), dist.get_world_size()
+launches0 = glu.kernel_launch_count()
+
+def up(a):
+    return torch.from_numpy(a.view(np.int32).copy()).to(dev)
+
+def gather(obj):
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
+
+# ---- sort: uniform 32-bit, the reference's 31-bit keys (adaptive split), heavy duplicates, 16-bit entropy
+for exchange in os.environ["GLU_EXCHANGES"].split(","):
+    sorter_fixed = glu.DistributedRadixSort(400_000, exchange=exchange, capacity_factor=2.5)
+    sorter_auto = glu.DistributedRadixSort(400_000, exchange=exchange, capacity_factor=2.5, split_shift="auto")
+    assert sorter_fixed.exchange == exchange, (sorter_fixed.exchange, exchange)
+    for kind, sorter in (("uniform", sorter_fixed), ("uniform", sorter_auto), ("ref31", sorter_auto), ("dups", sorter_auto),
+                         ("ent16", sorter_auto), ("uniform_again", sorter_fixed)):
+        n = 300_007 + 1013 * rank
+        if kind.startswith("uniform"):
+            keys = oracle.mt19937_u32(20 + rank, n)
+        elif kind == "ref31":
+            keys = oracle.random_u32(1 + rank, n, 0, 0xFFFFFFFF)
+        elif kind == "dups":
+            keys = oracle.random_u32(1 + rank, n, 0, 10)
+        else:
+            keys = oracle.mt19937_u32(20 + rank, n) & np.uint32(0xFFFF)
+        sizes = gather(n)
+        base = sum(sizes[:rank])
+        vals = np.arange(base, base + n, dtype=np.uint32)
+        dk, dv = up(keys), up(vals)
+        sk, sv, m = sorter(dk, dv, n)
+        torch.cuda.synchronize()
+        res = gather((keys, vals, sk.cpu().numpy().view(np.uint32), sv.cpu().numpy().view(np.uint32)))
+        assert np.array_equal(dk.cpu().numpy().view(np.uint32), keys), "inputs were modified"
+        if rank == 0:
+            allk = np.concatenate([r[0] for r in res]); allv = np.concatenate([r[1] for r in res])
+            gk = np.concatenate([r[2] for r in res]); gv = np.concatenate([r[3] for r in res])
+            ek, ev = oracle.stable_sort_pairs(allk, allv)
+            assert np.array_equal(gk, ek), f"{exchange}/{kind}: keys differ"
+            assert np.array_equal(gv, ev), f"{exchange}/{kind}: values differ (stability across ranks)"
+        dist.barrier()
+
+# ---- reduce / scan sharded by contiguous ranges
+n = 1_000_003 + 31 * rank
+data = oracle.mt19937_u32(40 + rank, n)
+alld = np.concatenate(gather(data))
+for op in (oracle.OP_SUM, oracle.OP_MUL, oracle.OP_MIN, oracle.OP_MAX):
+    dd = up(data)
+    glu.DistributedReduce(glu.DataType_Uint, op)(dd, n)
+    got = int(dd[0].item()) & 0xFFFFFFFF
+    assert got == oracle.reduce(alld, op), (op, got)
+f = (oracle.mt19937_u32(50 + rank, n).astype(np.float64) / 2**31 - 1.0).astype(np.float32)
+allf = np.concatenate(gather(f))
+for op in (oracle.OP_SUM, oracle.OP_MIN, oracle.OP_MAX):
+    df = torch.from_numpy(f.copy()).to(dev)
+    glu.DistributedReduce(glu.DataType_Float, op)(df, n)
+    got = float(df[0].item())
+    if op == oracle.OP_SUM:
+        want = float(allf.astype(np.float64).sum())
+        assert abs(got - want) <= 1e-5 * float(np.abs(allf.astype(np.float64)).sum()), (got, want)
+    else:
+        assert got == float(allf.min() if op == oracle.OP_MIN else allf.max())
+dd = up(data)
+glu.DistributedBlellochScan(glu.DataType_Uint)(dd, n)
+sizes = gather(n)
+base = sum(sizes[:rank])
+want = oracle.exclusive_scan(alld)[base:base + n]
+assert np.array_equal(dd.cpu().numpy().view(np.uint32), want), "sharded scan differs"
+torch.cuda.synchronize()
+if rank == 0:
+    print("OK world", world, "launches", glu.kernel_launch_count() - launches0, "lib", glu.LIB_PATH)
+dist.destroy_process_group()
+'''
+
+
+def _run_world(tmp_path, nproc, exchanges):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, GLU_ROOT=ROOT, GLU_EXCHANGES=exchanges)
+    port = 29600 + (os.getpid() % 300)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-6000:]
+    assert f"OK world {nproc}" in r.stdout
+
+
+def test_distributed_world(tmp_path, cuda_device):
+    import torch
+
+    nproc = min(2, torch.cuda.device_count())
+    _run_world(tmp_path, nproc, "p2p,nccl")
