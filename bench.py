@@ -234,10 +234,16 @@ def run_b200(args):
         v = torch.arange(n, dtype=torch.int32, device=dev)
         inputs.append((k, v))
 
+    last_out = [None]
     if world > 1:
-        dsort = entry.load_package().distributed.DistributedRadixSort(n)
-        step_fn = lambda k, v: dsort(k, v)  # noqa: E731
-        parallelism = f"msd-split x{world} (NVLink all-to-all) + local onesweep"
+        dsort = glu.DistributedRadixSort(n, exchange=os.environ.get("GLU_BENCH_EXCHANGE", "auto"))
+
+        def step_fn(k, v):
+            last_out[0] = dsort(k, v, n)
+
+        parallelism = (f"msd-split x{world}: top-8-bit histogram all-gather, balanced bucket->GPU prefix, "
+                       f"{'fused partition + NVLink peer-store all-to-all' if dsort.exchange == 'p2p' else 'partition + NCCL all_to_all'}"
+                       f", local onesweep sort")
     else:
         sorter = glu.RadixSort()
         sorter.prepare_internal_buffers(n)  # as the reference's benchmark does (test/radix_sort_tests.cpp:187)
@@ -277,7 +283,11 @@ def run_b200(args):
         ms_total = float(t.item())
 
     # sanity: the last timed step really sorted its input
-    k_sorted = inputs[warmup + steps - 1][0]
+    k_sorted = last_out[0][0] if world > 1 else inputs[warmup + steps - 1][0]
+    if world > 1:
+        totals = torch.tensor([last_out[0][2]], dtype=torch.int64, device=dev)
+        dist.all_reduce(totals)
+        assert int(totals.item()) == world * n, "distributed sort lost or duplicated pairs"
     k64 = k_sorted[: 1 << 24].to(torch.int64) & 0xFFFFFFFF
     assert bool((k64[1:] >= k64[:-1]).all()), "bench output is not sorted"
     del k64
@@ -345,6 +355,40 @@ def run_b200(args):
         line["side_metrics"] = side_metrics(glu, torch, dev, 1 << 28, peak)
         glu.profile_enable(False)
         line["cpu_baseline"] = cpu_baseline(args)
+    elif world > 1 and not args.no_side_metrics:
+        # ---- e2e at N GPUs: every rank uploads its shard from pinned host memory, the job sorts, every rank
+        # downloads its slice of the result; wall clock between barriers, max over ranks
+        del inputs[1:]
+        torch.cuda.empty_cache()
+        hk = torch.empty(n, dtype=torch.int32).pin_memory()
+        hv = torch.empty(n, dtype=torch.int32).pin_memory()
+        ok_ = torch.empty(dsort.capacity, dtype=torch.int32).pin_memory()
+        ov_ = torch.empty(dsort.capacity, dtype=torch.int32).pin_memory()
+        dk = torch.empty(n, dtype=torch.int32, device=dev)
+        dv = torch.empty(n, dtype=torch.int32, device=dev)
+        e2e_steps = min(steps, 5)
+        e2e_t = 0.0
+        for i in range(e2e_steps + 1):
+            hk.copy_(inputs[0][0].cpu() ^ (0x9E3779B9 * (i + 1) & 0x7FFFFFFF))
+            hv.copy_(inputs[0][1].cpu())
+            barrier()
+            t0 = time.perf_counter()
+            dk.copy_(hk, non_blocking=True)
+            dv.copy_(hv, non_blocking=True)
+            sk, sv, m = dsort(dk, dv, n)
+            ok_[:m].copy_(sk, non_blocking=True)
+            ov_[:m].copy_(sv, non_blocking=True)
+            barrier()
+            t1 = time.perf_counter()
+            if i > 0:
+                e2e_t += t1 - t0
+        t = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t.item())
+        line["e2e"] = {"value": world * n * e2e_steps / e2e_t / 1e9, "unit": "Gpairs/s",
+                       "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * n * world, "steps": e2e_steps,
+                       "ms_per_step": 1e3 * e2e_t / e2e_steps,
+                       "api": "DistributedRadixSort (per rank: pinned host shard -> H2D -> sort -> D2H of its slice)"}
     elif rank == 0:
         line["e2e"] = None
     if rank == 0:

@@ -206,3 +206,12 @@ TEST_CASE("Reduce-benchmark", "[.][benchmark]")
         std::printf("Reduce; Num elements: %zu, Elapsed: %s\n", k_num_elements, ns_to_human_string(ns).c_str());
     }
 }
+
+// The reference's error convention: a failed argument check prints and exits with status 1 (glu/errors.hpp:8-18).
+// Hidden: run by name from tests/test_cpp_runner_gpu.py, which expects the process to die here.
+TEST_CASE("Errors-null-buffer-exits", "[.]")
+{
+    Reduce reduce(DataType_Uint, ReduceOperator_Sum);
+    reduce(nullptr, 10); // "Invalid buffer"
+    CHECK(false);        // not reached
+}

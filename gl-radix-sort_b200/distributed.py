@@ -75,17 +75,16 @@ def plan_exchange(hist_all: np.ndarray) -> ExchangePlan:
     counts = np.asarray(hist_all, dtype=np.int64)
     world, radix = counts.shape
     dest = assign_buckets(counts.sum(axis=0), world)
-    send_counts = np.zeros((world, world), dtype=np.int64)
-    for g in range(world):
-        send_counts[:, g] = counts[:, dest == g].sum(axis=1)
+    onehot = (dest[:, None] == np.arange(world)[None, :]).astype(np.int64)  # [RADIX, world]
+    send_counts = counts @ onehot                                           # [src, dest]
     recv_totals = send_counts.sum(axis=0)
-    dst_offset = np.zeros((world, radix), dtype=np.int64)
-    fill = np.zeros(world, dtype=np.int64)
-    for b in range(radix):
-        g = int(dest[b])
-        within = np.cumsum(counts[:, b]) - counts[:, b]
-        dst_offset[:, b] = fill[g] + within
-        fill[g] += int(counts[:, b].sum())
+    # bucket b starts in dest[b]'s buffer after all earlier buckets of the same destination ...
+    bucket_totals = counts.sum(axis=0)
+    before = np.cumsum(bucket_totals) - bucket_totals                       # pairs in buckets < b (all destinations)
+    first_of_dest = np.concatenate([[0], np.cumsum(recv_totals)[:-1]])      # pairs in destinations < dest[b]
+    bucket_base = before - first_of_dest[dest]                              # dest ranges are contiguous in b
+    # ... and inside the bucket the sources follow each other in rank order
+    dst_offset = bucket_base[None, :] + (np.cumsum(counts, axis=0) - counts)
     src_offset = np.cumsum(counts, axis=1) - counts
     return ExchangePlan(dest, send_counts, recv_totals, dst_offset, src_offset)
 
