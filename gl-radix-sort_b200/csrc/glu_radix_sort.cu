@@ -261,37 +261,42 @@ namespace glu_b200
             uint32_t tile;
         };
 
-        // The CHAIN CTAs of a onesweep pass (see onesweep_kernel).  Chain CTA c turns the tiles' counts of
-        // digits [64c, 64c + 64) into running prefixes, as a stream of batches: a lane owns one digit and
-        // ROWS consecutive rows of the batch (all requested at once), sums them, the warps of a digit
-        // group are combined through shared memory, and the batch's prefix rows go out together.
+        // The CHAIN CTAs of a onesweep pass (see onesweep_kernel).  Chain CTA c turns the tiles' digit counts
+        // ("count rows") of digits [32 * GROUPS * c, ...) into running prefixes ("prefix rows").  A group of WPG
+        // warps owns 32 digits (one per lane) and walks the rows in batches of WPG * ROWS: warp w takes ROWS
+        // consecutive rows of the batch, requests them all at once (late rows are asked for again TOGETHER: one L2
+        // round trip per polling round however many are late), sums them, takes the running total of everything
+        // before its rows from its predecessor warp through shared memory (a ring: warp 0 continues from the last
+        // warp of the previous batch), hands its own running total on, and only then writes its prefix rows.
+        // prefix[t] therefore depends on count rows <= t only — never on a later tile — and the next batch's
+        // requests are already in flight while this one is combined.
         template<int WARPS, int ROWS, int GROUPS>
-        __device__ __noinline__ void chain_cta(uint32_t* smem_totals, uint32_t chain_id, const uint32_t* lookback,
+        __device__ __noinline__ void chain_cta(uint32_t* smem, uint32_t chain_id, const uint32_t* lookback,
                                                uint32_t* prefix, uint32_t num_tiles)
         {
             constexpr int WPG = WARPS / GROUPS; // warps per 32-digit group
             constexpr int BATCH = WPG * ROWS;   // rows per batch
-            uint32_t(*totals)[GROUPS][WPG][32] = reinterpret_cast<uint32_t(*)[GROUPS][WPG][32]>(smem_totals);
+            static_assert(WPG >= 2, "the carry ring needs two warps");
+            // smem was zeroed by the caller: carry values, then one "batches handed on" counter per warp
+            uint32_t(*carry)[GROUPS][WPG][32] = reinterpret_cast<uint32_t(*)[GROUPS][WPG][32]>(smem);
+            volatile uint32_t* seq = smem + 2 * GROUPS * WPG * 32;
             const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
             if (warp >= GROUPS * WPG)
                 return;
             const unsigned g = warp / WPG, w = warp % WPG;
             const uint32_t d = (chain_id * GROUPS + g) * 32 + lane;
             const uint32_t* col = lookback + d;
-            uint32_t base = 0;
-            unsigned parity = 0;
             uint32_t p[ROWS], q[ROWS];
 #pragma unroll
             for (int j = 0; j < ROWS; j++)
                 q[j] = w * ROWS + j < num_tiles ? ld_relaxed_u32(col + size_t(w * ROWS + j) * k_radix) : k_lb_local;
-            for (uint32_t t0 = 0; t0 < num_tiles; t0 += BATCH, parity ^= 1)
+            uint32_t batch = 0;
+            for (uint32_t t0 = 0; t0 < num_tiles; t0 += BATCH, batch++)
             {
                 const uint32_t r0 = t0 + w * ROWS;
 #pragma unroll
                 for (int j = 0; j < ROWS; j++)
                     p[j] = q[j];
-                // rows that are not published yet are asked for again TOGETHER: one L2 round trip per
-                // polling round, however many rows are late
                 while (true)
                 {
                     uint32_t all = k_lb_local;
@@ -305,7 +310,6 @@ namespace glu_b200
                         if ((p[j] & k_lb_local) == 0)
                             p[j] = ld_relaxed_u32(col + size_t(r0 + j) * k_radix);
                 }
-                // the next batch's rows are in flight while this one is combined and written
 #pragma unroll
                 for (int j = 0; j < ROWS; j++)
                     q[j] = r0 + BATCH + j < num_tiles ? ld_relaxed_u32(col + size_t(r0 + BATCH + j) * k_radix) : k_lb_local;
@@ -316,21 +320,27 @@ namespace glu_b200
                     run += p[j] & k_lb_value_mask;
                     p[j] = run;
                 }
-                totals[parity][g][w][lane] = run;
-                named_barrier_sync(1 + g, WPG * 32);
-                uint32_t off = 0, batch_total = 0;
-#pragma unroll
-                for (int ww = 0; ww < WPG; ww++)
+                // running total of all rows before mine
+                uint32_t in = 0;
+                if (w > 0 || batch > 0)
                 {
-                    const uint32_t tt = totals[parity][g][ww][lane];
-                    off += unsigned(ww) < w ? tt : 0u;
-                    batch_total += tt;
+                    const unsigned pw = w > 0 ? w - 1 : WPG - 1;
+                    const uint32_t pb = w > 0 ? batch : batch - 1;
+                    while (seq[g * WPG + pw] < pb + 1)
+                    {
+                    }
+                    __threadfence_block();
+                    in = *const_cast<volatile uint32_t*>(&carry[pb & 1][g][pw][lane]);
                 }
+                *const_cast<volatile uint32_t*>(&carry[batch & 1][g][w][lane]) = in + run;
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0)
+                    seq[g * WPG + w] = batch + 1;
 #pragma unroll
                 for (int j = 0; j < ROWS; j++)
                     if (r0 + j < num_tiles)
-                        st_relaxed_u32(prefix + size_t(r0 + j) * k_radix + d, k_lb_inclusive | (base + off + p[j]));
-                base += batch_total;
+                        st_relaxed_u32(prefix + size_t(r0 + j) * k_radix + d, k_lb_inclusive | (in + p[j]));
             }
         }
 
