@@ -192,6 +192,11 @@ namespace glu_b200
                      "r"(parity)
                      : "memory");
     }
+    // orders earlier generic-proxy accesses to shared memory before later async-proxy (TMA) accesses
+    __device__ __forceinline__ void fence_proxy_async_smem()
+    {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     __device__ __forceinline__ uint64_t l2_policy_evict_first()
     {
         uint64_t policy;

@@ -707,18 +707,21 @@ namespace glu_b200
             const int allow_tma =
                 ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
             constexpr size_t smem = sizeof(SweepSmem<THREADS, IPT, PEER>);
-            static const int chain_rows = env_int("GLU_SORT_CHAIN_ROWS", 4);
+            static const int chain_rows = env_int("GLU_SORT_CHAIN_ROWS", 8);
             static const int debug_no_lookback = env_int("GLU_SORT_DEBUG_NO_LOOKBACK", 0);
             static bool configured[64] = {};
             int dev = 0;
             GLU_CUDA_TRY(cudaGetDevice(&dev));
-            if (dev < 64 && !configured[dev])
+            if (dev >= 64)
+                return GLU_ERROR_INVALID_ARGUMENT;
+            if (!configured[dev])
             {
                 GLU_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
                 configured[dev] = true;
             }
+            const unsigned grid = tiles + (chain_rows >= 100 ? 4 : 8);
             ScopedKernelProfile prof(GLU_KERNEL_SORT_ONESWEEP, s);
-            kernel<<<tiles + (chain_rows >= 100 ? 4 : 8), THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
+            kernel<<<grid, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
                                                     tiles, allow_tma, chain_rows, debug_no_lookback, key_dst, val_dst);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;

@@ -4,9 +4,9 @@
 TAG=$1; shift
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-( timeout 600 python -m pytest tests/test_sort_gpu.py -m gpu -x -q 2>&1 | tail -5 ) > $OUT/pytest_sort.log
+( timeout 240 python -m pytest tests/test_sort_gpu.py tests/test_multigpu_gpu.py -m gpu -x -q 2>&1 | tail -5 ) > $OUT/pytest_sort.log
 cat $OUT/pytest_sort.log
 for cfg in "$@"; do
   echo "== $cfg" | tee -a $OUT/sweep.log
-  ( env $cfg timeout 300 python tools/quick_bench.py --log2n ${LOG2N:-28} --what sort --reps ${REPS:-10} 2>&1 | tail -2 ) | tee -a $OUT/sweep.log
+  ( env $cfg timeout 120 python tools/quick_bench.py --log2n ${LOG2N:-28} --what sort --reps ${REPS:-10} 2>&1 | tail -2 ) | tee -a $OUT/sweep.log
 done
