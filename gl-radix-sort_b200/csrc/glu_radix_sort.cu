@@ -58,81 +58,59 @@ namespace glu_b200
 
         // ------------------------------------------------------------------------------------ histogram
 
-        constexpr int k_hist_threads = 512;
+        constexpr int k_hist_threads = 1024;
         constexpr int k_hist_unroll = 4;
-        constexpr int k_hist_blocks_per_sm = 2;
-        constexpr int k_hist_copies = 8; // bank-interleaved private copies of every bin: lane l uses copy l & 7
+        constexpr int k_hist_blocks_per_sm = 1;
+        constexpr int k_hist_copies = 32; // one private copy of every bin per lane
 
-        // hist: [k_max_passes][256] zero-initialised; on exit hist holds EXCLUSIVE digit offsets.
+        // hist: [k_max_passes][256] zero-initialised; on exit hist holds EXCLUSIVE digit offsets
+        // (make_offsets) or the plain counts.  Digit place p of a key is ((key >> pre_shift) & key_mask) >> 8p.
         //
-        // Shared-memory atomics are the cost here (4 per key), so every bin has 8 copies laid out in
-        // consecutive banks: lanes of a warp only collide inside their own group of 4.  When at least
-        // half of a warp holds the same digit (constant or heavily skewed digit places) the warp
-        // switches to __match_any_sync aggregation: one atomic per distinct digit instead of a
-        // serialised same-address pile-up.
-        __global__ void __launch_bounds__(k_hist_threads)
+        // Shared-memory atomics are the cost here (one per key and digit place), and what makes them slow is
+        // lanes of a warp meeting in a bank.  So every bin has 32 copies, one per LANE, in 32 consecutive
+        // words: lane l only ever touches bank l — no bank conflicts and no same-address pile-up inside a warp
+        // whatever the key distribution (uniform, constant and skewed digit places cost the same), at 32 KB
+        // of shared memory per digit place (one 1024-thread CTA per SM).
+        __global__ void __launch_bounds__(k_hist_threads, 1)
             histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t head, uint32_t n_units,
                              int num_passes, uint32_t pre_shift, uint32_t key_mask, uint32_t* hist, uint32_t* ticket,
                              int make_offsets)
         {
-            __shared__ uint32_t s_hist[k_max_passes][k_radix][k_hist_copies];
+            extern __shared__ __align__(16) uint32_t s_hist[]; // [num_passes][k_radix][k_hist_copies]
             __shared__ uint32_t s_scan[k_hist_threads / 32];
             __shared__ bool s_is_last;
 
-            for (int i = threadIdx.x; i < k_max_passes * k_radix * k_hist_copies; i += k_hist_threads)
-                (&s_hist[0][0][0])[i] = 0;
+            for (int i = threadIdx.x; i < num_passes * k_radix * k_hist_copies / 4; i += k_hist_threads)
+                reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0, 0, 0, 0);
             __syncthreads();
 
             const unsigned lane = threadIdx.x & 31;
-            const unsigned copy = lane & (k_hist_copies - 1);
-            const uint32_t lt = lanemask_lt();
+            uint32_t* mine = s_hist + lane;
             const uint4* body = reinterpret_cast<const uint4*>(keys + head);
             const uint32_t stride = gridDim.x * k_hist_threads;
-            // warp-uniform loop bounds: the match/ballot collectives need every lane of the warp
-            for (uint32_t v0 = blockIdx.x * k_hist_threads + (threadIdx.x & ~31u); v0 < n_units;
-                 v0 += stride * k_hist_unroll)
+            for (uint32_t v0 = blockIdx.x * k_hist_threads + threadIdx.x; v0 < n_units; v0 += stride * k_hist_unroll)
             {
                 uint4 k[k_hist_unroll];
                 bool ok[k_hist_unroll];
 #pragma unroll
                 for (int u = 0; u < k_hist_unroll; u++)
                 {
-                    const uint64_t v = uint64_t(v0) + uint64_t(u) * stride + lane;
+                    const uint64_t v = uint64_t(v0) + uint64_t(u) * stride;
                     ok[u] = v < n_units;
                     k[u] = ok[u] ? ld_stream_v4(body + v) : make_uint4(0, 0, 0, 0);
                 }
 #pragma unroll
                 for (int u = 0; u < k_hist_unroll; u++)
                 {
-                    if (__ballot_sync(k_full_mask, ok[u]) == 0)
+                    if (!ok[u])
                         continue;
                     const uint32_t kk[4] = {(k[u].x >> pre_shift) & key_mask, (k[u].y >> pre_shift) & key_mask,
                                             (k[u].z >> pre_shift) & key_mask, (k[u].w >> pre_shift) & key_mask};
                     for (int p = 0; p < num_passes; p++)
                     {
-                        uint32_t d[4];
 #pragma unroll
                         for (int c = 0; c < 4; c++)
-                            d[c] = (kk[c] >> (8 * p)) & 0xffu;
-                        // skew probe on one of the four keys (cheap: 1 shuffle + 1 ballot per 4 atomics)
-                        const uint32_t d0 = __shfl_sync(k_full_mask, d[0], 0);
-                        const uint32_t same0 = __ballot_sync(k_full_mask, ok[u] && d[0] == d0);
-                        if (__popc(same0) >= 16)
-                        {
-#pragma unroll
-                            for (int c = 0; c < 4; c++)
-                            {
-                                const uint32_t peers = __match_any_sync(k_full_mask, ok[u] ? d[c] : 0xffffffffu);
-                                if (ok[u] && (peers & lt) == 0)
-                                    atomicAdd(&s_hist[p][d[c]][copy], uint32_t(__popc(peers)));
-                            }
-                        }
-                        else if (ok[u])
-                        {
-#pragma unroll
-                            for (int c = 0; c < 4; c++)
-                                atomicAdd(&s_hist[p][d[c]][copy], 1u);
-                        }
+                            atomicAdd(mine + ((p * k_radix + ((kk[c] >> (8 * p)) & 0xffu)) * k_hist_copies), 1u);
                     }
                 }
             }
@@ -145,7 +123,7 @@ namespace glu_b200
                 const uint32_t key = ok ? ((keys[idx] >> pre_shift) & key_mask) : 0;
                 if (ok)
                     for (int p = 0; p < num_passes; p++)
-                        atomicAdd(&s_hist[p][(key >> (8 * p)) & 0xffu][copy], 1u);
+                        atomicAdd(mine + ((p * k_radix + ((key >> (8 * p)) & 0xffu)) * k_hist_copies), 1u);
             }
             __syncthreads();
             for (int i = threadIdx.x; i < num_passes * k_radix; i += k_hist_threads)
@@ -153,13 +131,13 @@ namespace glu_b200
                 uint32_t c = 0;
 #pragma unroll
                 for (int j = 0; j < k_hist_copies; j++)
-                    c += (&s_hist[0][0][0])[i * k_hist_copies + j];
+                    c += s_hist[i * k_hist_copies + ((j + lane) & (k_hist_copies - 1))]; // rotated: bank-conflict free
                 if (c)
                     atomicAdd(&hist[i], c);
             }
-
             if (!make_offsets) // glu_radix_histogram_u32: raw counts
                 return;
+
             // last CTA: counts -> exclusive offsets, one digit place at a time
             __threadfence();
             __syncthreads();
@@ -769,9 +747,21 @@ namespace
         size_t grid = (size_t(n_units) + per_block - 1) / per_block;
         const size_t cap = size_t(sms) * k_hist_blocks_per_sm;
         grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
+        const size_t smem = size_t(num_passes) * k_radix * k_hist_copies * sizeof(uint32_t);
+        static bool configured[64] = {};
+        int dev = 0;
+        GLU_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev >= 64)
+            return GLU_ERROR_INVALID_ARGUMENT;
+        if (!configured[dev])
+        {
+            GLU_CUDA_TRY(cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              int(k_max_passes * k_radix * k_hist_copies * sizeof(uint32_t))));
+            configured[dev] = true;
+        }
         ScopedKernelProfile prof(GLU_KERNEL_SORT_HISTOGRAM, s);
-        histogram_kernel<<<unsigned(grid), k_hist_threads, 0, s>>>(d_keys, n, head, n_units, num_passes, pre_shift, key_mask,
-                                                                    hist, ticket, make_offsets);
+        histogram_kernel<<<unsigned(grid), k_hist_threads, smem, s>>>(d_keys, n, head, n_units, num_passes, pre_shift,
+                                                                       key_mask, hist, ticket, make_offsets);
         GLU_LAUNCH_CHECK();
         return GLU_SUCCESS;
     }

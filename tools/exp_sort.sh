@@ -8,5 +8,5 @@ mkdir -p $OUT
 cat $OUT/pytest_sort.log
 for cfg in "$@"; do
   echo "== $cfg" | tee -a $OUT/sweep.log
-  ( env $cfg timeout 120 python tools/quick_bench.py --log2n ${LOG2N:-28} --what sort --reps ${REPS:-10} 2>&1 | tail -2 ) | tee -a $OUT/sweep.log
+  ( env $cfg timeout 120 python tools/quick_bench.py --log2n ${LOG2N:-28} --what sort --reps ${REPS:-10} 2>&1 | tail -3 ) | tee -a $OUT/sweep.log
 done

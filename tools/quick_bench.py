@@ -56,6 +56,14 @@ if "sort" in args.what:
         vals.copy_(vals0)
 
     med, best = timeit(lambda: sorter(keys, vals, n), prep)
+    glu.profile_enable(True)
+    prep()
+    sorter(keys, vals, n)
+    torch.cuda.synchronize()
+    sweep_ms, sweep_n = glu.profile_collect(glu.KERNEL_SORT_ONESWEEP)
+    hist_ms, hist_n = glu.profile_collect(glu.KERNEL_SORT_HISTOGRAM)
+    glu.profile_enable(False)
+    print(f"       histogram {hist_ms / max(1, hist_n):.3f} ms, onesweep pass {sweep_ms / max(1, sweep_n):.3f} ms x {sweep_n}")
     print(f"sort   n=2^{args.log2n} {args.dist}: median {med:.3f} ms  best {best:.3f} ms  "
           f"{n / med / 1e6:.2f} Gpairs/s  {68 * n / med / 1e6:.0f} GB/s(68B/pair)  "
           f"cfg={os.environ.get('GLU_SORT_CONFIG', 'auto')} rank={os.environ.get('GLU_SORT_RANK', '0')} "
