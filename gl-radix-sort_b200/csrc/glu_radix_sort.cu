@@ -106,11 +106,18 @@ namespace glu_b200
                         continue;
                     const uint32_t kk[4] = {(k[u].x >> pre_shift) & key_mask, (k[u].y >> pre_shift) & key_mask,
                                             (k[u].z >> pre_shift) & key_mask, (k[u].w >> pre_shift) & key_mask};
-                    for (int p = 0; p < num_passes; p++)
+#pragma unroll
+                    for (int p = 0; p < k_max_passes; p++)
                     {
+                        if (p >= num_passes) // uniform
+                            break;
 #pragma unroll
                         for (int c = 0; c < 4; c++)
-                            atomicAdd(mine + ((p * k_radix + ((kk[c] >> (8 * p)) & 0xffu)) * k_hist_copies), 1u);
+                        {
+                            // byte p of the key (PRMT), scaled address (LEA), atomic: three instructions per count
+                            const uint32_t d = __byte_perm(kk[c], 0u, 0x4440u + p);
+                            atomicAdd(mine + p * k_radix * k_hist_copies + d * k_hist_copies, 1u);
+                        }
                     }
                 }
             }
@@ -366,10 +373,22 @@ namespace glu_b200
             const uint32_t chain_ctas = chain_rows >= 100 ? 4u : 8u; // 64 or 32 digits per chain CTA
             if (tid == 0)
             {
-                s.tile = atomicAdd(ticket, 1u);
                 mbarrier_init(&s.bar_keys, 1);
                 mbarrier_init(&s.bar_vals, 1);
                 mbarrier_init_fence();
+                const uint32_t t = atomicAdd(ticket, 1u);
+                s.tile = t;
+                // a full tile's bulk copies leave the moment the ticket is known (the rest of the CTA is still
+                // clearing its counters)
+                if (allow_tma && t >= chain_ctas && n - (t - chain_ctas) * uint32_t(TILE) >= uint32_t(TILE))
+                {
+                    const uint32_t tb = (t - chain_ctas) * uint32_t(TILE);
+                    const uint64_t policy = l2_policy_evict_first();
+                    mbarrier_arrive_expect_tx(&s.bar_keys, TILE * 4);
+                    tma_load_1d(s.keys, keys_in + tb, TILE * 4, &s.bar_keys, policy);
+                    mbarrier_arrive_expect_tx(&s.bar_vals, TILE * 4);
+                    tma_load_1d(s.vals, vals_in + tb, TILE * 4, &s.bar_vals, policy);
+                }
             }
             for (int i = tid; i < WARPS * k_radix / 4; i += THREADS)
                 reinterpret_cast<uint4*>(&s.warp_hist[0][0])[i] = make_uint4(0, 0, 0, 0);
@@ -399,18 +418,7 @@ namespace glu_b200
             const uint32_t my_off = warp * WARP_ELEMS + lane; // + i * 32   (warp-striped)
 
             // ---- stage the tile
-            if (use_tma)
-            {
-                if (tid == 0)
-                {
-                    const uint64_t policy = l2_policy_evict_first();
-                    mbarrier_arrive_expect_tx(&s.bar_keys, TILE * 4);
-                    tma_load_1d(s.keys, keys_in + tile_base, TILE * 4, &s.bar_keys, policy);
-                    mbarrier_arrive_expect_tx(&s.bar_vals, TILE * 4);
-                    tma_load_1d(s.vals, vals_in + tile_base, TILE * 4, &s.bar_vals, policy);
-                }
-            }
-            else
+            if (!use_tma)
             {
                 // Slots past the end of the input hold the largest key: they rank after every real key
                 // of the tile and are never written back.
