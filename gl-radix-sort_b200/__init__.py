@@ -56,6 +56,8 @@ ABI = {
     "glu_radix_histogram_u32": (_int, [_vp, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _vp]),
     "glu_radix_partition_u32kv_tmp_bytes": (_sz, [_sz]),
     "glu_radix_partition_u32kv": (_int, [_vp, _vp, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _vp, _sz, _vp]),
+    "glu_radix_partition_by_dest_u32kv": (_int, [_vp, _vp, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _vp, _vp, _sz,
+                                                 _vp]),
     "glu_ipc_get_handle": (_int, [_vp, ctypes.c_char_p]),
     "glu_ipc_open_handle": (_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "glu_ipc_close_handle": (_int, [_vp]),

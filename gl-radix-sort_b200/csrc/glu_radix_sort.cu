@@ -216,6 +216,19 @@ namespace glu_b200
                          : "r"(d));
             return peers;
         }
+
+        // same for digits < 16 (the destination ids of glu_radix_partition_by_dest_u32kv): four rounds
+        __device__ __forceinline__ uint32_t match_low4(uint32_t d)
+        {
+            uint32_t peers;
+            asm volatile("{\n"
+                         ".reg .pred p;\n"
+                         ".reg .b32 v, t, m;\n"
+                         "mov.b32 %0, 0xffffffff;\n" GLU_MATCH_BIT(1) GLU_MATCH_BIT(2) GLU_MATCH_BIT(4) GLU_MATCH_BIT(8) "}\n"
+                         : "=&r"(peers)
+                         : "r"(d));
+            return peers;
+        }
 #undef GLU_MATCH_BIT
 
         
@@ -228,6 +241,7 @@ namespace glu_b200
         {
             uint32_t* key[k_radix]; // address of tile-sorted slot 0, per digit
             uint32_t* val[k_radix];
+            uint8_t lut[k_radix];   // DEST: key digit -> destination id (the "digit" the pass partitions by)
         };
 
         template<int RANK_THREADS, int IPT, bool PEER = false> struct SweepSmem
@@ -349,15 +363,20 @@ namespace glu_b200
         //   5. values: staging buffer -> registers -> tile-sorted slot (in place); then slot p of both
         //      arrays goes to global[gbase[digit(key_p)] + p] — neighbouring threads, neighbouring
         //      addresses inside every digit run.
-        template<int RANK_THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false>
+        //
+        // PEER: digit run d goes to key_dst[d] / val_dst[d] instead of one output array.  DEST (with PEER): the pass
+        // partitions by dest_lut[digit] (< 16 destinations) instead of by the digit itself, so a tile leaves as a
+        // handful of long runs — what remote (NVLink) stores want.
+        template<int RANK_THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false>
         __global__ void __launch_bounds__(RANK_THREADS, MIN_BLOCKS)
             onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                             uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
                             uint32_t shift, uint32_t mask, const uint32_t* __restrict__ digit_offset,
                             uint32_t* lookback, uint32_t* prefix, uint32_t* ticket, uint32_t num_tiles, int allow_tma,
                             int chain_rows, int debug_no_lookback, uint32_t* const* key_dst = nullptr,
-                            uint32_t* const* val_dst = nullptr)
+                            uint32_t* const* val_dst = nullptr, const uint8_t* __restrict__ dest_lut = nullptr)
         {
+            static_assert(!DEST || PEER, "DEST is a flavour of PEER");
             static_assert(RANK_THREADS >= k_radix && RANK_THREADS % 32 == 0, "one ranking thread per digit");
             static_assert(IPT % 2 == 0, "ranks are packed two per register");
             using Smem = SweepSmem<RANK_THREADS, IPT, PEER>;
@@ -392,7 +411,19 @@ namespace glu_b200
             }
             for (int i = tid; i < WARPS * k_radix / 4; i += THREADS)
                 reinterpret_cast<uint4*>(&s.warp_hist[0][0])[i] = make_uint4(0, 0, 0, 0);
+            if constexpr (DEST)
+            {
+                if (tid < k_radix)
+                    s.dst.lut[tid] = dest_lut[tid];
+            }
             __syncthreads();
+            // what the pass partitions by
+            auto digit_of = [&](uint32_t k) -> uint32_t {
+                if constexpr (DEST)
+                    return s.dst.lut[(k >> shift) & mask];
+                else
+                    return (k >> shift) & mask;
+            };
             if (s.tile < chain_ctas)
             {
                 // ---- the first tickets = the CHAIN CTAs (the first CTAs to run, hence resident before any
@@ -439,29 +470,46 @@ namespace glu_b200
 #pragma unroll
                 for (int i = 0; i < IPT; i++)
                     key[i] = s.keys[my_off + i * 32];
-                // A digit shared by the whole warp would be a 32-way same-address atomic.  Probe the first
-                // key: a warp that looks skewed checks every key and counts warp-uniform digits once.
-                const uint32_t d_first = (key[0] >> shift) & mask;
-                if (__all_sync(k_full_mask, d_first == __shfl_sync(k_full_mask, d_first, 0)))
+                if constexpr (DEST)
                 {
+                    // a handful of destinations: plain atomics would pile up on the same few words, so the lanes
+                    // holding the same destination are matched and their leader adds the group's size
+                    const uint32_t lt_ = lanemask_lt();
 #pragma unroll
                     for (int i = 0; i < IPT; i++)
                     {
-                        const uint32_t d = (key[i] >> shift) & mask;
-                        if (__all_sync(k_full_mask, d == __shfl_sync(k_full_mask, d, 0)))
-                        {
-                            if (lane == 0)
-                                wh[d] += 32;
-                        }
-                        else
-                            atomicAdd(&wh[d], 1u);
+                        const uint32_t d = digit_of(key[i]);
+                        const uint32_t peers = match_low4(d);
+                        if ((peers & lt_) == 0)
+                            atomicAdd(&wh[d], uint32_t(__popc(peers)));
                     }
                 }
                 else
                 {
+                    // A digit shared by the whole warp would be a 32-way same-address atomic.  Probe the first
+                    // key: a warp that looks skewed checks every key and counts warp-uniform digits once.
+                    const uint32_t d_first = (key[0] >> shift) & mask;
+                    if (__all_sync(k_full_mask, d_first == __shfl_sync(k_full_mask, d_first, 0)))
+                    {
 #pragma unroll
-                    for (int i = 0; i < IPT; i++)
-                        atomicAdd(&wh[(key[i] >> shift) & mask], 1u);
+                        for (int i = 0; i < IPT; i++)
+                        {
+                            const uint32_t d = (key[i] >> shift) & mask;
+                            if (__all_sync(k_full_mask, d == __shfl_sync(k_full_mask, d, 0)))
+                            {
+                                if (lane == 0)
+                                    wh[d] += 32;
+                            }
+                            else
+                                atomicAdd(&wh[d], 1u);
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int i = 0; i < IPT; i++)
+                            atomicAdd(&wh[(key[i] >> shift) & mask], 1u);
+                    }
                 }
             }
             __syncthreads(); // every key is in registers; the counts are final
@@ -473,8 +521,8 @@ namespace glu_b200
 #pragma unroll
                 for (int w = 0; w < WARPS; w++)
                     total += s.warp_hist[w][tid];
-                // padding slots all carry digit `mask`
-                const uint32_t count_valid = total - (tid == mask ? uint32_t(TILE) - valid : 0u);
+                // padding slots all carry the digit of key 0xffffffff
+                const uint32_t count_valid = total - (tid == digit_of(0xffffffffu) ? uint32_t(TILE) - valid : 0u);
                 st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid], k_lb_local | count_valid);
                 inc = total;
 #pragma unroll
@@ -512,8 +560,8 @@ namespace glu_b200
 #pragma unroll
                 for (int i = 0; i < IPT; i++)
                 {
-                    const uint32_t d = (key[i] >> shift) & mask;
-                    const uint32_t peers = match_digit<MODE>(d);
+                    const uint32_t d = digit_of(key[i]);
+                    const uint32_t peers = DEST ? match_low4(d) : match_digit<MODE>(d);
                     const uint32_t before = wh[d];
                     __syncwarp();
                     wh[d] = before + __popc(peers); // every peer stores the same value
@@ -575,7 +623,7 @@ namespace glu_b200
                     const uint32_t vv = s.vals[p];
                     if constexpr (PEER)
                     {
-                        const uint32_t d = (kk >> shift) & mask;
+                        const uint32_t d = digit_of(kk);
                         s.dst.key[d][p] = kk;
                         s.dst.val[d][p] = vv;
                     }
@@ -594,7 +642,7 @@ namespace glu_b200
                     const uint32_t kk = s.keys[p];
                     if constexpr (PEER)
                     {
-                        const uint32_t d = (kk >> shift) & mask;
+                        const uint32_t d = digit_of(kk);
                         s.dst.key[d][p] = kk;
                         s.dst.val[d][p] = s.vals[p];
                     }
@@ -680,15 +728,15 @@ namespace glu_b200
             return l;
         }
 
-        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false>
+        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false>
         int launch_sweep(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint32_t n, uint32_t shift,
                          uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback, uint32_t* ticket,
                          unsigned tiles, cudaStream_t s, uint32_t* const* key_dst = nullptr,
-                         uint32_t* const* val_dst = nullptr)
+                         uint32_t* const* val_dst = nullptr, const uint8_t* dest_lut = nullptr)
         {
             // per pass: `tiles` count rows followed by `tiles` prefix rows; grid = tiles + the chain CTAs
             uint32_t* prefix = lookback + size_t(tiles) * k_radix;
-            auto kernel = onesweep_kernel<THREADS, IPT, MIN_BLOCKS, MODE, PEER>;
+            auto kernel = onesweep_kernel<THREADS, IPT, MIN_BLOCKS, MODE, PEER, DEST>;
             // TMA bulk copies need 16-byte aligned sources (tiles are multiples of 4 elements)
             const int allow_tma =
                 ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
@@ -708,7 +756,7 @@ namespace glu_b200
             const unsigned grid = tiles + (chain_rows >= 100 ? 4 : 8);
             ScopedKernelProfile prof(GLU_KERNEL_SORT_ONESWEEP, s);
             kernel<<<grid, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
-                                                    tiles, allow_tma, chain_rows, debug_no_lookback, key_dst, val_dst);
+                                                    tiles, allow_tma, chain_rows, debug_no_lookback, key_dst, val_dst, dest_lut);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
@@ -913,4 +961,37 @@ extern "C" int glu_radix_partition_u32kv(const uint32_t* d_keys, const uint32_t*
     return launch_sweep<k_part_threads, k_part_ipt, k_part_blocks, Rank_Ballot, true>(
         d_keys, d_vals, nullptr, nullptr, uint32_t(count), shift, (1u << bits) - 1u, nullptr, lookback, ticket, tiles, s,
         d_key_dst, d_val_dst);
+}
+
+extern "C" int glu_radix_partition_by_dest_u32kv(const uint32_t* d_keys, const uint32_t* d_vals, size_t count,
+                                                 unsigned shift, unsigned bits, const uint8_t* d_dest_of_digit,
+                                                 uint32_t* const* d_key_dst, uint32_t* const* d_val_dst, void* d_tmp,
+                                                 size_t tmp_bytes, glu_stream_t stream)
+{
+    if (!d_keys || !d_vals || !d_dest_of_digit || !d_key_dst || !d_val_dst || bits == 0 || bits > 8 || shift > 31)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    if (count == 0)
+        return GLU_SUCCESS;
+    if (count > k_max_count)
+        return GLU_ERROR_COUNT_TOO_LARGE;
+    if ((reinterpret_cast<uintptr_t>(d_keys) | reinterpret_cast<uintptr_t>(d_vals)) % sizeof(uint32_t) != 0 ||
+        (reinterpret_cast<uintptr_t>(d_key_dst) | reinterpret_cast<uintptr_t>(d_val_dst)) % sizeof(void*) != 0)
+        return GLU_ERROR_MISALIGNED;
+    const size_t need = glu_radix_partition_u32kv_tmp_bytes(count);
+    if (!d_tmp || tmp_bytes < need)
+        return GLU_ERROR_TMP_TOO_SMALL;
+    if (reinterpret_cast<uintptr_t>(d_tmp) % k_tmp_align != 0)
+        return GLU_ERROR_MISALIGNED;
+    if (current_sm_count() <= 0)
+        return GLU_ERROR_CUDA;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t tile = size_t(k_part_threads) * k_part_ipt;
+    const unsigned tiles = unsigned((count + tile - 1) / tile);
+    char* tmp = static_cast<char*>(d_tmp);
+    GLU_CUDA_TRY(cudaMemsetAsync(tmp, 0, need, s));
+    uint32_t* ticket = reinterpret_cast<uint32_t*>(tmp);
+    uint32_t* lookback = reinterpret_cast<uint32_t*>(tmp + k_tmp_align);
+    return launch_sweep<k_part_threads, k_part_ipt, k_part_blocks, Rank_Ballot, true, true>(
+        d_keys, d_vals, nullptr, nullptr, uint32_t(count), shift, (1u << bits) - 1u, nullptr, lookback, ticket, tiles, s,
+        d_key_dst, d_val_dst, d_dest_of_digit);
 }

@@ -10,12 +10,12 @@ The reference is single-GPU; this module is what BASELINE.json'
     1. every rank builds the 256-bin histogram of the split digit of its keys (``glu_radix_histogram_u32``);
     2. the histograms are all-gathered, so every rank knows ``counts[src][bucket]`` exactly;
     3. buckets are assigned to GPUs by balanced prefix (contiguous bucket ranges, ``assign_buckets``);
-    4. ONE partition pass per GPU (``glu_radix_partition_u32kv``, a onesweep pass) scatters every pair straight
-       into its destination GPU's receive buffer through NVLink peer pointers — the partition and the all-to-all
-       are the same kernel (``exchange="p2p"``, CUDA IPC mappings of the peers' buffers).  Inside the destination
-       a bucket's pairs are ordered by source rank, then by source position, which keeps the global sort stable.
-       ``exchange="nccl"`` is the two-step variant: partition into a local staging buffer, then
-       ``all_to_all_single``;
+    4. ONE partition pass per GPU (``glu_radix_partition_by_dest_u32kv``, a onesweep pass whose "digit" is the
+       destination rank of the key's bucket) scatters every pair straight into its destination GPU's receive buffer
+       through NVLink peer pointers — the partition and the all-to-all are the same kernel (``exchange="p2p"``,
+       CUDA IPC mappings of the peers' buffers).  A destination receives the sources' contributions one after the
+       other in rank order, each in source order, which keeps the global sort stable.  ``exchange="nccl"`` is
+       the two-step variant: partition into a local staging buffer, then ``all_to_all_single``;
     5. every rank sorts what it received with the local onesweep sort.  The concatenation of the ranks' outputs
        in rank order is the stable sort of the concatenation of the inputs.
 
@@ -63,21 +63,29 @@ class ExchangePlan:
     dest: np.ndarray          # [RADIX]        destination rank of each bucket
     send_counts: np.ndarray   # [world, world] pairs rank s sends to rank g
     recv_totals: np.ndarray   # [world]        pairs each rank ends up with
-    dst_offset: np.ndarray    # [world, RADIX] where rank s's run of bucket b starts in dest[b]'s receive buffer
+    recv_offset: np.ndarray   # [world, world] where rank s's pairs start in rank g's receive buffer (source-major)
+    send_offset: np.ndarray   # [world, world] where the pairs for rank g start in rank s's destination-major staging
+    dst_offset: np.ndarray    # [world, RADIX] bucket-major layout: where rank s's run of bucket b starts in dest[b]'s buffer
     src_offset: np.ndarray    # [world, RADIX] where bucket b starts in rank s's own bucket-major order
 
 
 def plan_exchange(hist_all: np.ndarray) -> ExchangePlan:
     """From counts[src][bucket] (the all-gathered histograms) to the complete layout of the all-to-all.
 
-    Receive layout of rank g: its buckets in increasing order; inside a bucket the sources in rank order; inside a
-    source the pairs in source order.  Equal keys therefore stay in global input order (rank, then position)."""
+    Two receive layouts are planned, both stable (equal keys share a bucket, hence a destination, and stay in global
+    input order: source rank, then source position):
+      * source-major (recv_offset): rank g's buffer is [pairs from rank 0][pairs from rank 1]..., each in source order —
+        what the partition-by-destination pass and the NCCL all-to-all produce;
+      * bucket-major (dst_offset): g's buckets in increasing order, inside a bucket the sources in rank order — what
+        the 256-way pointer-table partition produces (worlds of more than 16 ranks)."""
     counts = np.asarray(hist_all, dtype=np.int64)
     world, radix = counts.shape
     dest = assign_buckets(counts.sum(axis=0), world)
     onehot = (dest[:, None] == np.arange(world)[None, :]).astype(np.int64)  # [RADIX, world]
     send_counts = counts @ onehot                                           # [src, dest]
     recv_totals = send_counts.sum(axis=0)
+    recv_offset = np.cumsum(send_counts, axis=0) - send_counts
+    send_offset = np.cumsum(send_counts, axis=1) - send_counts
     # bucket b starts in dest[b]'s buffer after all earlier buckets of the same destination ...
     bucket_totals = counts.sum(axis=0)
     before = np.cumsum(bucket_totals) - bucket_totals                       # pairs in buckets < b (all destinations)
@@ -86,7 +94,7 @@ def plan_exchange(hist_all: np.ndarray) -> ExchangePlan:
     # ... and inside the bucket the sources follow each other in rank order
     dst_offset = bucket_base[None, :] + (np.cumsum(counts, axis=0) - counts)
     src_offset = np.cumsum(counts, axis=1) - counts
-    return ExchangePlan(dest, send_counts, recv_totals, dst_offset, src_offset)
+    return ExchangePlan(dest, send_counts, recv_totals, recv_offset, send_offset, dst_offset, src_offset)
 
 
 # ------------------------------------------------------------------------------------------------------ GPU side
@@ -231,14 +239,17 @@ class DistributedRadixSort:
                                      device=self.device)
         self._hist = torch.zeros(RADIX, dtype=torch.int32, device=self.device)
         self._hist_all = torch.zeros(self.world * RADIX, dtype=torch.int32, device=self.device)
-        self._tables = torch.zeros(2 * RADIX, dtype=torch.int64, device=self.device)
-        self._tables_host = torch.zeros(2 * RADIX, dtype=torch.int64).pin_memory()
+        # [256 key pointers][256 value pointers][256-byte digit -> destination table, as 32 int64]
+        self._tables = torch.zeros(2 * RADIX + RADIX // 8, dtype=torch.int64, device=self.device)
+        self._tables_host = torch.zeros(2 * RADIX + RADIX // 8, dtype=torch.int64).pin_memory()
+        self.by_dest = self.world <= 16
         self._minmax = None
         self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._peer_keys = self._peer_vals = None
         self._stage_keys = self._stage_vals = None
         self.exchange = self._setup_exchange(exchange)
         self.last_plan = None
+        self.timing = None  # set to a dict to get per-phase wall times in ms (synchronises after every phase)
 
     # -- peer mappings (CUDA IPC): rank g's receive buffers mapped into this process
     def _setup_exchange(self, exchange: str) -> str:
@@ -317,6 +328,20 @@ class DistributedRadixSort:
         if count < 1 or count > self.max_count:
             raise glu.GluError(1, f"count must be in [1, {self.max_count}]")
         st = glu._current_stream(self.device)
+        timing = self.timing
+        if timing is not None:
+            import time
+
+            def mark(name):
+                torch.cuda.synchronize()
+                now = time.perf_counter()
+                timing[name] = timing.get(name, 0.0) + 1e3 * (now - mark.t)
+                mark.t = now
+            torch.cuda.synchronize()
+            mark.t = time.perf_counter()
+        else:
+            def mark(name):
+                pass
         shift = self._split_shift(kptr, count, st)
 
         # 1-2. local digit histogram -> counts[src][bucket] on every rank (this all-gather also orders this call's
@@ -325,6 +350,7 @@ class DistributedRadixSort:
                   "glu_radix_histogram_u32")
         dist.all_gather_into_tensor(self._hist_all, self._hist, group=self.group)
         hist_all = self._hist_all.cpu().numpy().view(np.uint32).reshape(self.world, RADIX)
+        mark("histogram+allgather+d2h")
 
         # 3. bucket -> GPU assignment and the receive layout
         plan = plan_exchange(hist_all)
@@ -334,18 +360,38 @@ class DistributedRadixSort:
             raise glu.GluError(6, f"DistributedRadixSort: a rank would receive {int(plan.recv_totals.max())} pairs, "
                                   f"capacity is {self.capacity} (raise capacity_factor or use split_shift='auto')")
 
-        # 4. partition (+ all-to-all)
+        # 4. partition (+ all-to-all).  Up to 16 ranks the pass partitions by destination (a tile leaves as `world`
+        #    long runs — remote stores near link speed); beyond that by bucket through a 256-entry pointer table.
         tables = self._tables_host.numpy()
-        if self.exchange == "p2p":
-            tables[:RADIX] = self._peer_keys[plan.dest] + 4 * plan.dst_offset[self.rank]
-            tables[RADIX:] = self._peer_vals[plan.dest] + 4 * plan.dst_offset[self.rank]
+        r = self.rank
+        if self.by_dest:
+            tables[:RADIX] = 0
+            tables[RADIX:2 * RADIX] = 0
+            if self.exchange == "p2p":
+                tables[:self.world] = self._peer_keys + 4 * plan.recv_offset[r]
+                tables[RADIX:RADIX + self.world] = self._peer_vals + 4 * plan.recv_offset[r]
+            else:
+                tables[:self.world] = self._stage_keys.data_ptr() + 4 * plan.send_offset[r]
+                tables[RADIX:RADIX + self.world] = self._stage_vals.data_ptr() + 4 * plan.send_offset[r]
+            tables[2 * RADIX:].view(np.uint8)[:] = plan.dest.astype(np.uint8)
+        elif self.exchange == "p2p":
+            tables[:RADIX] = self._peer_keys[plan.dest] + 4 * plan.dst_offset[r]
+            tables[RADIX:2 * RADIX] = self._peer_vals[plan.dest] + 4 * plan.dst_offset[r]
         else:
-            tables[:RADIX] = self._stage_keys.data_ptr() + 4 * plan.src_offset[self.rank]
-            tables[RADIX:] = self._stage_vals.data_ptr() + 4 * plan.src_offset[self.rank]
+            tables[:RADIX] = self._stage_keys.data_ptr() + 4 * plan.src_offset[r]
+            tables[RADIX:2 * RADIX] = self._stage_vals.data_ptr() + 4 * plan.src_offset[r]
         self._tables.copy_(self._tables_host, non_blocking=True)
-        glu.check(glu.lib.glu_radix_partition_u32kv(kptr, vptr, count, shift, RADIX_BITS, self._tables.data_ptr(),
-                                                    self._tables.data_ptr() + 8 * RADIX, self._part_tmp.data_ptr(),
-                                                    self._part_tmp.numel(), st), "glu_radix_partition_u32kv")
+        mark("plan+tables")
+        tptr = self._tables.data_ptr()
+        if self.by_dest:
+            glu.check(glu.lib.glu_radix_partition_by_dest_u32kv(kptr, vptr, count, shift, RADIX_BITS, tptr + 16 * RADIX,
+                                                                tptr, tptr + 8 * RADIX, self._part_tmp.data_ptr(),
+                                                                self._part_tmp.numel(), st),
+                      "glu_radix_partition_by_dest_u32kv")
+        else:
+            glu.check(glu.lib.glu_radix_partition_u32kv(kptr, vptr, count, shift, RADIX_BITS, tptr, tptr + 8 * RADIX,
+                                                        self._part_tmp.data_ptr(), self._part_tmp.numel(), st),
+                      "glu_radix_partition_u32kv")
         rk, rv = self._recv_keys.tensor, self._recv_vals.tensor
         if self.exchange == "p2p":
             # device-side barrier: when this tiny all-reduce completes, every rank's partition kernel has completed,
@@ -357,7 +403,9 @@ class DistributedRadixSort:
             dist.all_to_all_single(rk[:m], self._stage_keys[:count], out_splits, in_splits, group=self.group)
             dist.all_to_all_single(rv[:m], self._stage_vals[:count], out_splits, in_splits, group=self.group)
 
+        mark("partition+exchange")
         # 5. local sort of everything this rank received
         if m > 1:
             self._sorter(rk, rv, m)
+        mark("local sort")
         return rk[:m], rv[:m], m

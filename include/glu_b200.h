@@ -167,6 +167,16 @@ GLU_API int glu_radix_partition_u32kv(const uint32_t* d_keys, const uint32_t* d_
                                       unsigned bits, uint32_t* const* d_key_dst, uint32_t* const* d_val_dst,
                                       void* d_tmp, size_t tmp_bytes, glu_stream_t stream);
 
+/* The same pass partitioning by DESTINATION instead of by digit: the i-th pair whose digit maps to destination
+ * g = d_dest_of_digit[digit] (a device array of 256 bytes, every g < 16) goes to d_key_dst[g][i] / d_val_dst[g][i].
+ * d_key_dst / d_val_dst are device arrays of 256 pointers of which only the first max(g)+1 are read.  A tile then
+ * leaves the SM as a few long runs (tile / #destinations pairs each) instead of 256 short ones, which is what
+ * remote stores over NVLink need to run near link speed: the fused partition + all-to-all of the multi-GPU sort. */
+GLU_API int glu_radix_partition_by_dest_u32kv(const uint32_t* d_keys, const uint32_t* d_vals, size_t count,
+                                              unsigned shift, unsigned bits, const uint8_t* d_dest_of_digit,
+                                              uint32_t* const* d_key_dst, uint32_t* const* d_val_dst, void* d_tmp,
+                                              size_t tmp_bytes, glu_stream_t stream);
+
 /* CUDA IPC plumbing for one-process-per-GPU peer access: export a glu_malloc'ed allocation, map a peer's. */
 #define GLU_IPC_HANDLE_BYTES 64
 GLU_API int glu_ipc_get_handle(void* d_ptr, unsigned char handle[GLU_IPC_HANDLE_BYTES]);

@@ -41,7 +41,7 @@ def test_assign_buckets_balanced_and_monotone(dmod):
     assert dmod.assign_buckets(np.zeros(256), 4).tolist() == [0] * 256
 
 
-def emulate(dmod, shards_k, shards_v, shift):
+def emulate(dmod, shards_k, shards_v, shift, layout="bucket"):
     """numpy emulation of DistributedRadixSort's data movement driven by plan_exchange."""
     world = len(shards_k)
     hist_all = np.stack([np.bincount((k >> shift) & 0xFF, minlength=256) for k in shards_k])
@@ -51,12 +51,22 @@ def emulate(dmod, shards_k, shards_v, shift):
     written = [np.zeros(int(t), dtype=np.int32) for t in plan.recv_totals]
     for s in range(world):
         digit = (shards_k[s] >> shift) & 0xFF
-        for b in range(256):
-            sel = np.nonzero(digit == b)[0]  # stable partition: source order inside a bucket
-            g, off = int(plan.dest[b]), int(plan.dst_offset[s][b])
-            recv_k[g][off:off + sel.size] = shards_k[s][sel]
-            recv_v[g][off:off + sel.size] = shards_v[s][sel]
-            written[g][off:off + sel.size] += 1
+        if layout == "bucket":  # 256-way pointer-table partition
+            for b in range(256):
+                sel = np.nonzero(digit == b)[0]  # stable partition: source order inside a bucket
+                g, off = int(plan.dest[b]), int(plan.dst_offset[s][b])
+                recv_k[g][off:off + sel.size] = shards_k[s][sel]
+                recv_v[g][off:off + sel.size] = shards_v[s][sel]
+                written[g][off:off + sel.size] += 1
+        else:  # partition by destination: source order inside a destination
+            to = plan.dest[digit]
+            for g in range(world):
+                sel = np.nonzero(to == g)[0]
+                off = int(plan.recv_offset[s][g])
+                assert sel.size == int(plan.send_counts[s][g])
+                recv_k[g][off:off + sel.size] = shards_k[s][sel]
+                recv_v[g][off:off + sel.size] = shards_v[s][sel]
+                written[g][off:off + sel.size] += 1
     for w in written:
         assert np.all(w == 1)  # the layout tiles every receive buffer exactly once
     out_k, out_v = [], []
@@ -67,9 +77,10 @@ def emulate(dmod, shards_k, shards_v, shift):
     return plan, np.concatenate(out_k), np.concatenate(out_v)
 
 
+@pytest.mark.parametrize("layout", ["bucket", "dest"])
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 @pytest.mark.parametrize("kind", ["uniform", "ref31", "ent16", "dups"])
-def test_plan_exchange_gives_stable_global_sort(dmod, oracle, world, kind):
+def test_plan_exchange_gives_stable_global_sort(dmod, oracle, world, kind, layout):
     n = 20011
     shards_k, shards_v = [], []
     for r in range(world):
@@ -88,7 +99,7 @@ def test_plan_exchange_gives_stable_global_sort(dmod, oracle, world, kind):
         base += k.size
     allk, allv = np.concatenate(shards_k), np.concatenate(shards_v)
     shift = dmod.choose_split_shift(int(allk.min()), int(allk.max()))
-    plan, gk, gv = emulate(dmod, shards_k, shards_v, shift)
+    plan, gk, gv = emulate(dmod, shards_k, shards_v, shift, layout)
     ek, ev = oracle.stable_sort_pairs(allk, allv)
     np.testing.assert_array_equal(gk, ek)
     np.testing.assert_array_equal(gv, ev)

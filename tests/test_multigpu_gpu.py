@@ -64,6 +64,36 @@ def test_radix_partition_matches_stable_partition(glu, cuda_device, oracle, n, s
     np.testing.assert_array_equal(to_host(dk, np.uint32), keys)  # inputs untouched
 
 
+@pytest.mark.parametrize("n", [1, 33, 7679, 7680, 7681, 200_003, 3_000_017])
+@pytest.mark.parametrize("ndest,kind", [(1, "uniform"), (2, "uniform"), (3, "dups"), (8, "uniform"), (16, "uniform")])
+def test_radix_partition_by_dest_matches_stable_partition(glu, cuda_device, oracle, n, ndest, kind):
+    import torch
+
+    keys = oracle.mt19937_u32(6, n)
+    if kind == "dups":
+        keys = (keys % np.uint32(5)) << np.uint32(24)
+    vals = np.arange(n, dtype=np.uint32)
+    lut = (np.arange(256) * ndest // 256).astype(np.uint8)  # contiguous bucket ranges, like assign_buckets
+    to = lut[(keys >> 24) & 0xFF]
+    counts = np.bincount(to, minlength=ndest).astype(np.int64)
+    offs = np.cumsum(counts) - counts
+    dk, dv = to_device(keys, cuda_device), to_device(vals, cuda_device)
+    ok = torch.zeros(n, dtype=torch.int32, device=cuda_device)
+    ov = torch.zeros(n, dtype=torch.int32, device=cuda_device)
+    tab = np.zeros(2 * 256 + 32, dtype=np.int64)
+    tab[:ndest] = ok.data_ptr() + 4 * offs
+    tab[256:256 + ndest] = ov.data_ptr() + 4 * offs
+    tab[512:].view(np.uint8)[:] = lut
+    tables = torch.from_numpy(tab).to(cuda_device)
+    tmp = torch.empty(int(glu.lib.glu_radix_partition_u32kv_tmp_bytes(n)), dtype=torch.uint8, device=cuda_device)
+    glu.check(glu.lib.glu_radix_partition_by_dest_u32kv(dk.data_ptr(), dv.data_ptr(), n, 24, 8, tables.data_ptr() + 4096,
+                                                        tables.data_ptr(), tables.data_ptr() + 2048, tmp.data_ptr(),
+                                                        tmp.numel(), _stream(cuda_device)), "partition_by_dest")
+    order = np.argsort(to, kind="stable")
+    np.testing.assert_array_equal(to_host(ok, np.uint32), keys[order])
+    np.testing.assert_array_equal(to_host(ov, np.uint32), vals[order])
+
+
 def test_reduce_into_leaves_the_data_alone(glu, cuda_device, oracle):
     import torch
 
