@@ -76,7 +76,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def mark(self):
+        """Number of samples seen so far (call at the start and at the end of the timed region)."""
+        return len(self.lines)
+
+    def stop(self, first=0, last=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -87,7 +91,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        # samples taken inside the timed region (one before and one after included); the sampler itself starts
+        # before the warm-up because nvidia-smi takes a while to deliver its first line
+        window = self.lines[max(0, first - 1):(last + 1 if last is not None else None)] or self.lines[-3:]
+        for line in window:
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 9:
                 continue
@@ -255,27 +262,30 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(warmup):
         step_fn(*inputs[i])
     barrier()
     glu.profile_enable(True)
     glu.profile_collect(glu.KERNEL_SORT_ONESWEEP)
     glu.profile_collect(glu.KERNEL_SORT_HISTOGRAM)
+    glu.profile_collect(glu.KERNEL_SORT_PARTITION)
     launches0 = glu.kernel_launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    mark0 = sampler.mark()
     ev0.record()
     for i in range(steps):
         step_fn(*inputs[warmup + i])
     ev1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(mark0, sampler.mark())
     ms_total = ev0.elapsed_time(ev1)
     gpu_launches = glu.kernel_launch_count() - launches0
     sweep_ms, sweep_launches = glu.profile_collect(glu.KERNEL_SORT_ONESWEEP)
     hist_ms, hist_launches = glu.profile_collect(glu.KERNEL_SORT_HISTOGRAM)
+    part_ms, part_launches = glu.profile_collect(glu.KERNEL_SORT_PARTITION)
     glu.profile_enable(False)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -303,6 +313,7 @@ def run_b200(args):
                 "algorithmic_bytes_per_launch": PASS_BYTES_PER_PAIR * pairs_per_launch,
                 "kernel_share_of_step": sweep_ms / ms_total,
                 "histogram_ms_per_launch": hist_ms / max(1, hist_launches),
+                "partition_exchange_ms_per_launch": (part_ms / part_launches) if part_launches else None,
                 "whole_sort": {"bytes_per_pair": SORT_BYTES_PER_PAIR,
                                "achieved_GB/s": SORT_BYTES_PER_PAIR * world * n * steps / (ms_total * 1e-3) / 1e9 / world,
                                "frac": SORT_BYTES_PER_PAIR * n * steps / (ms_total * 1e-3) / 1e9 / peak}}

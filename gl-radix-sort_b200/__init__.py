@@ -145,7 +145,7 @@ def kernel_launch_count() -> int:
     return int(_lib.glu_kernel_launch_count())
 
 
-KERNEL_REDUCE, KERNEL_SCAN, KERNEL_SORT_HISTOGRAM, KERNEL_SORT_ONESWEEP = 0, 1, 2, 3
+KERNEL_REDUCE, KERNEL_SCAN, KERNEL_SORT_HISTOGRAM, KERNEL_SORT_ONESWEEP, KERNEL_SORT_PARTITION = 0, 1, 2, 3, 4
 
 
 def profile_enable(on: bool) -> None:

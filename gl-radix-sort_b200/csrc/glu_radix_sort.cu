@@ -754,7 +754,7 @@ namespace glu_b200
                 configured[dev] = true;
             }
             const unsigned grid = tiles + (chain_rows >= 100 ? 4 : 8);
-            ScopedKernelProfile prof(GLU_KERNEL_SORT_ONESWEEP, s);
+            ScopedKernelProfile prof(PEER ? GLU_KERNEL_SORT_PARTITION : GLU_KERNEL_SORT_ONESWEEP, s);
             kernel<<<grid, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
                                                     tiles, allow_tma, chain_rows, debug_no_lookback, key_dst, val_dst, dest_lut);
             GLU_LAUNCH_CHECK();

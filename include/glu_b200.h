@@ -103,7 +103,8 @@ typedef enum glu_kernel_id
     GLU_KERNEL_SCAN = 1,
     GLU_KERNEL_SORT_HISTOGRAM = 2,
     GLU_KERNEL_SORT_ONESWEEP = 3,
-    GLU_KERNEL_COUNT_ = 4
+    GLU_KERNEL_SORT_PARTITION = 4, /* the multi-GPU partition / exchange pass */
+    GLU_KERNEL_COUNT_ = 5
 } glu_kernel_id;
 GLU_API int glu_profile_enable(int on);
 GLU_API int glu_profile_collect(int kernel_id, double* total_ms, uint64_t* launches);
