@@ -31,7 +31,8 @@ namespace glu_b200
         constexpr uint32_t k_lb_local = 1u << 30;     // counts row: tile-local digit count published (bits 0..29)
         constexpr uint32_t k_lb_inclusive = 1u << 31; // prefix row: inclusive count over tiles 0..t (bits 0..30)
         constexpr uint32_t k_lb_value_mask = (1u << 30) - 1u;
-        constexpr size_t k_max_count = size_t(1) << 30;
+        // 31-bit running digit counts in the prefix rows (bit 31 is the flag), 32-bit element indices
+        constexpr size_t k_max_count = (size_t(1) << 31) - 1;
 
         struct PassPlan
         {

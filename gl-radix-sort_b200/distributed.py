@@ -229,8 +229,8 @@ class DistributedRadixSort:
         self.max_count = int(max_count)
         self.capacity = int(max_count * capacity_factor) + 1024
         self.split_shift = split_shift
-        if self.capacity > (1 << 30):
-            raise glu.GluError(6, "DistributedRadixSort: per-rank capacity exceeds 2^30 pairs")
+        if self.capacity >= (1 << 31):
+            raise glu.GluError(6, "DistributedRadixSort: per-rank capacity must stay below 2^31 pairs")
         self._recv_keys = _DeviceArray(self.capacity, self.device)
         self._recv_vals = _DeviceArray(self.capacity, self.device)
         self._sorter = glu.RadixSort()

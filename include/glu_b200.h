@@ -135,7 +135,7 @@ GLU_API int glu_scan_exclusive(void* d_data, size_t count, size_t num_partitions
  * num_steps keeps the reference's meaning (number of 4-bit steps: only the low 4*num_steps key bits
  * take part; 0 or >= 8 = all 32 bits).  Deviation: the result always lands in d_keys / d_vals (the
  * reference leaves an odd-num_steps result in its internal scratch).  count <= 1 is a no-op
- * (glu/RadixSort.hpp:278).  count must be <= 2^30. */
+ * (glu/RadixSort.hpp:278).  count must be < 2^31 (the reference's own limit: 32-bit uniforms). */
 GLU_API size_t glu_radix_sort_u32kv_tmp_bytes(size_t count);
 GLU_API int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t count, size_t num_steps, void* d_tmp,
                                  size_t tmp_bytes, glu_stream_t stream);

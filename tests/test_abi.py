@@ -72,7 +72,7 @@ def test_argument_errors_are_status_codes_not_exits(glu):
     assert L.glu_radix_sort_u32kv(fake, fake, 1, 0, None, 0, None) == 0  # count <= 1 is a silent no-op
     assert L.glu_radix_sort_u32kv(fake, fake, 0, 0, None, 0, None) == 0
     assert L.glu_radix_sort_u32kv(fake, fake, 8, 0, None, 0, None) == 4
-    assert L.glu_radix_sort_u32kv(fake, fake, (1 << 30) + 1, 0, fake, 1 << 40, None) == 6
+    assert L.glu_radix_sort_u32kv(fake, fake, 1 << 31, 0, fake, 1 << 40, None) == 6
 
 
 def test_tmp_size_queries(glu):
@@ -84,7 +84,7 @@ def test_tmp_size_queries(glu):
     n = 1 << 20
     need = L.glu_radix_sort_u32kv_tmp_bytes(n)
     assert 2 * 4 * n <= need <= 2 * 4 * n + (8 << 20)  # two scratch arrays + O(tiles) control words
-    assert L.glu_radix_sort_u32kv_tmp_bytes((1 << 30) + 1) == 0
+    assert L.glu_radix_sort_u32kv_tmp_bytes(1 << 31) == 0
 
 
 def test_python_mirror_validates_like_the_reference(glu):

@@ -211,3 +211,37 @@ def test_sort_host_entry_point(glu, cuda_device, oracle):
     ek, ev = oracle.stable_sort_pairs(keys, vals)
     np.testing.assert_array_equal(hk, ek)
     np.testing.assert_array_equal(hv, ev)
+
+
+def test_sort_beyond_2_30_pairs(glu, cuda_device):
+    """2^30 + 2^27 pairs (BASELINE configs[3] puts 2^30 pairs on a GPU, and the multi-GPU receive buffers need head
+    room above that): no CPU oracle at this size, so the size-independent properties — keys non-decreasing, equal keys
+    keep their input order (values = index), and an order-independent checksum of the (key, value) pairs."""
+    import torch
+
+    if torch.cuda.get_device_properties(0).total_memory < 60 * (1 << 30):
+        pytest.skip("needs ~30 GiB of device memory")
+    n = (1 << 30) + (1 << 27)
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    keys = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int32, device=cuda_device, generator=g)
+    keys[: 1 << 20] = 7  # a long run of equal keys: stability must hold across many tiles
+    vals = torch.arange(n, dtype=torch.int32, device=cuda_device)
+
+    def checksum(k, v):
+        total = 0
+        for i in range(0, n, 1 << 28):  # chunked: the int64 temporaries are 2 GiB each
+            kk = k[i:i + (1 << 28)].to(torch.int64) & 0xFFFFFFFF
+            vv = v[i:i + (1 << 28)].to(torch.int64)
+            total = (total + int(((kk * 0x9E3779B1 + vv * 0x85EBCA77) & 0xFFFFFFFFFFFF).sum().item())) & ((1 << 62) - 1)
+        return total
+
+    before = checksum(keys, vals)
+    glu.RadixSort()(keys, vals, n)
+    torch.cuda.synchronize()
+    assert checksum(keys, vals) == before
+    for i in range(0, n - 1, 1 << 28):
+        j = min(n, i + (1 << 28) + 1)
+        k = keys[i:j].to(torch.int64) & 0xFFFFFFFF
+        v = vals[i:j]
+        ok = (k[1:] > k[:-1]) | ((k[1:] == k[:-1]) & (v[1:] > v[:-1]))
+        assert bool(ok.all()), f"order / stability violated in chunk starting at {i}"
