@@ -1,10 +1,13 @@
-// util/Random.hpp — the input generator of the reference's test-suite (test/util/Random.hpp:12-38).
-// It defines the golden inputs, so its observable behaviour is reproduced exactly:
-//   engine  = std::minstd_rand seeded with `seed` (default-seeded when seed == 0);
-//   sample  = engine() % (max - min) + min           -> half-open [min, max), modulo bias included;
-// "full range" keys sample_int_vector<uint32_t>(n, 0, UINT32_MAX) are therefore 31-bit.
+// util/Random.hpp — input generator of the reference's test-suite, restated (test/util/Random.hpp:12-38).
+//
+// The seeded test inputs ARE the golden inputs, so the observable sequence must match the reference exactly:
+//   * engine: std::minstd_rand (fully specified by the C++ standard), default-constructed for seed 0;
+//   * a sample in [lo, hi) is  lo + engine() % (hi - lo)   — modulo bias and all.
+// Since minstd_rand yields at most 2^31 - 2, "full range" uint32 keys never have bit 31 set;
+// tests/golden/reference_golden.json pins the first outputs.
 #pragma once
 
+#include <cstddef>
 #include <cstdint>
 #include <random>
 #include <vector>
@@ -15,25 +18,31 @@ namespace glu
 {
     class Random
     {
+    public:
+        explicit Random(uint64_t seed = 0)
+        {
+            if (seed != 0)
+                m_engine.seed(static_cast<std::minstd_rand::result_type>(seed));
+        }
+
+        /// One draw from the half-open range [lo, hi).
+        template<typename IntegerT> IntegerT sample_int(IntegerT lo, IntegerT hi)
+        {
+            GLU_CHECK_ARGUMENT(lo < hi, "Min must be strictly lower than Max");
+            const auto span = hi - lo;
+            return static_cast<IntegerT>(lo + m_engine() % span);
+        }
+
+        /// `count` consecutive draws.
+        template<typename IntegerT> std::vector<IntegerT> sample_int_vector(size_t count, IntegerT lo, IntegerT hi)
+        {
+            std::vector<IntegerT> draws(count);
+            for (IntegerT& d : draws)
+                d = sample_int(lo, hi);
+            return draws;
+        }
+
     private:
         std::minstd_rand m_engine;
-
-    public:
-        explicit Random(uint64_t seed = 0) : m_engine(seed != 0 ? std::minstd_rand(seed) : std::minstd_rand()) {}
-
-        template<typename IntegerT> IntegerT sample_int(IntegerT min, IntegerT max)
-        {
-            GLU_CHECK_ARGUMENT(min < max, "Min must be strictly lower than Max");
-            return IntegerT(m_engine() % (max - min) + min);
-        }
-
-        template<typename IntegerT> std::vector<IntegerT> sample_int_vector(size_t num_elements, IntegerT min, IntegerT max)
-        {
-            std::vector<IntegerT> out;
-            out.reserve(num_elements);
-            while (out.size() < num_elements)
-                out.push_back(sample_int(min, max));
-            return out;
-        }
     };
 } // namespace glu

@@ -396,7 +396,8 @@ namespace glu_b200
                 mbarrier_init(&s.bar_keys, 1);
                 mbarrier_init(&s.bar_vals, 1);
                 mbarrier_init_fence();
-                const uint32_t t = atomicAdd(ticket, 1u);
+                // debug_no_lookback bit 1: tile id = blockIdx.x (relies on in-order CTA dispatch, like CUB's scan)
+                const uint32_t t = (debug_no_lookback & 2) ? blockIdx.x : atomicAdd(ticket, 1u);
                 s.tile = t;
                 // a full tile's bulk copies leave the moment the ticket is known (the rest of the CTA is still
                 // clearing its counters)
@@ -586,7 +587,7 @@ namespace glu_b200
                 if (tid < k_radix)
                 {
                     uint32_t exclusive = 0;
-                    if (tile > 0 && !debug_no_lookback) // debug_no_lookback: timing experiments only (wrong results)
+                    if (tile > 0 && !(debug_no_lookback & 1)) // bit 0: timing experiments only (wrong results)
                     {
                         const uint32_t* p = prefix + size_t(tile - 1) * k_radix + tid;
                         uint32_t x = ld_relaxed_u32(p);
