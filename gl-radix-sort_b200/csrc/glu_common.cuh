@@ -213,5 +213,11 @@ namespace glu_b200
                      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                      : "memory");
     }
+    // Asks L2 to fetch `bytes` (a multiple of 16, 16-byte aligned address) ahead of a later bulk copy; no completion
+    // is signalled and nothing lands in shared memory (SASS: UBLKPF).
+    __device__ __forceinline__ void tma_prefetch_l2_1d(const void* gmem_src, uint32_t bytes)
+    {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+    }
 #endif // __CUDACC__
 } // namespace glu_b200

@@ -31,6 +31,7 @@ namespace glu_b200
         constexpr uint32_t k_lb_local = 1u << 30;     // counts row: tile-local digit count published (bits 0..29)
         constexpr uint32_t k_lb_inclusive = 1u << 31; // prefix row: inclusive count over tiles 0..t (bits 0..30)
         constexpr uint32_t k_lb_value_mask = (1u << 30) - 1u;
+        constexpr int k_opt_no_lookback = 1, k_opt_ticket = 2; // GLU_SORT_OPTIONS bits
         // 31-bit running digit counts in the prefix rows (bit 31 is the flag), 32-bit element indices
         constexpr size_t k_max_count = (size_t(1) << 31) - 1;
 
@@ -374,7 +375,7 @@ namespace glu_b200
                             uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
                             uint32_t shift, uint32_t mask, const uint32_t* __restrict__ digit_offset,
                             uint32_t* lookback, uint32_t* prefix, uint32_t* ticket, uint32_t num_tiles, int allow_tma,
-                            int chain_rows, int debug_no_lookback, uint32_t* const* key_dst = nullptr,
+                            int chain_rows, int options, uint32_t* const* key_dst = nullptr,
                             uint32_t* const* val_dst = nullptr, const uint8_t* __restrict__ dest_lut = nullptr)
         {
             static_assert(!DEST || PEER, "DEST is a flavour of PEER");
@@ -396,8 +397,10 @@ namespace glu_b200
                 mbarrier_init(&s.bar_keys, 1);
                 mbarrier_init(&s.bar_vals, 1);
                 mbarrier_init_fence();
-                // debug_no_lookback bit 1: tile id = blockIdx.x (relies on in-order CTA dispatch, like CUB's scan)
-                const uint32_t t = (debug_no_lookback & 2) ? blockIdx.x : atomicAdd(ticket, 1u);
+                // Tile ids: blockIdx.x (default; CTAs are dispatched in blockIdx order, so every CTA a tile waits
+                // for is resident or done — the assumption CUB's DeviceScan makes too; saves the L2 round trip
+                // in front of the bulk copies) or an atomic ticket (k_opt_ticket: order by construction).
+                const uint32_t t = (options & k_opt_ticket) ? atomicAdd(ticket, 1u) : blockIdx.x;
                 s.tile = t;
                 // a full tile's bulk copies leave the moment the ticket is known (the rest of the CTA is still
                 // clearing its counters)
@@ -587,7 +590,7 @@ namespace glu_b200
                 if (tid < k_radix)
                 {
                     uint32_t exclusive = 0;
-                    if (tile > 0 && !(debug_no_lookback & 1)) // bit 0: timing experiments only (wrong results)
+                    if (tile > 0 && !(options & k_opt_no_lookback)) // k_opt_no_lookback: timing experiments only
                     {
                         const uint32_t* p = prefix + size_t(tile - 1) * k_radix + tid;
                         uint32_t x = ld_relaxed_u32(p);
@@ -675,6 +678,7 @@ namespace glu_b200
             {5, 256, 8},  // 2048 (small inputs: more CTAs)
             {6, 384, 16}, // 6144, 3 CTAs/SM
             {7, 320, 18}, // 5760, 4 CTAs/SM
+            {8, 320, 24}, // 7680, 3 CTAs/SM with 64 registers per thread
         };
         constexpr int k_num_configs = int(sizeof(k_configs) / sizeof(k_configs[0]));
 
@@ -693,7 +697,7 @@ namespace glu_b200
                 return k_configs[5];
             if (count <= (size_t(1) << 21))
                 return k_configs[2];
-            return k_configs[3];
+            return k_configs[8];
         }
 
         bool use_tma_env()
@@ -744,7 +748,8 @@ namespace glu_b200
                 ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
             constexpr size_t smem = sizeof(SweepSmem<THREADS, IPT, PEER>);
             static const int chain_rows = env_int("GLU_SORT_CHAIN_ROWS", 8);
-            static const int debug_no_lookback = env_int("GLU_SORT_DEBUG_NO_LOOKBACK", 0);
+            // bit 0: skip the look-back (timing experiments, wrong results); bit 1: tile ids from an atomic ticket
+            static const int options = env_int("GLU_SORT_OPTIONS", 0);
             static bool configured[64] = {};
             int dev = 0;
             GLU_CUDA_TRY(cudaGetDevice(&dev));
@@ -758,7 +763,7 @@ namespace glu_b200
             const unsigned grid = tiles + (chain_rows >= 100 ? 4 : 8);
             ScopedKernelProfile prof(PEER ? GLU_KERNEL_SORT_PARTITION : GLU_KERNEL_SORT_ONESWEEP, s);
             kernel<<<grid, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
-                                                    tiles, allow_tma, chain_rows, debug_no_lookback, key_dst, val_dst, dest_lut);
+                                                    tiles, allow_tma, chain_rows, options, key_dst, val_dst, dest_lut);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
@@ -779,6 +784,7 @@ namespace glu_b200
                 GLU_SWEEP_CASE(4, 512, 22, 2)
                 GLU_SWEEP_CASE(6, 384, 16, 3)
                 GLU_SWEEP_CASE(7, 320, 18, 4)
+                GLU_SWEEP_CASE(8, 320, 24, 3)
             default: return launch_sweep<256, 8, 4, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
 #undef GLU_SWEEP_CASE
             }
@@ -791,7 +797,7 @@ using namespace glu_b200;
 namespace
 {
     // the partition pass always uses the large-input tile shape
-    constexpr int k_part_threads = 384, k_part_ipt = 20, k_part_blocks = 3;
+    constexpr int k_part_threads = 320, k_part_ipt = 24, k_part_blocks = 3;
 
     int launch_histogram(const uint32_t* d_keys, uint32_t n, int num_passes, uint32_t pre_shift, uint32_t key_mask,
                          uint32_t* hist, uint32_t* ticket, int make_offsets, int sms, cudaStream_t s)

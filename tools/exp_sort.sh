@@ -4,7 +4,7 @@
 TAG=$1; shift
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-( timeout 240 python -m pytest tests/test_sort_gpu.py tests/test_multigpu_gpu.py -m gpu -x -q 2>&1 | tail -5 ) > $OUT/pytest_sort.log
+( timeout ${PYTEST_TIMEOUT:-240} python -m pytest tests/test_sort_gpu.py tests/test_multigpu_gpu.py -m gpu -x -q -k "${PYTEST_K:-not beyond_2_30}" --durations=5 2>&1 | tail -12 ) > $OUT/pytest_sort.log
 cat $OUT/pytest_sort.log
 for cfg in "$@"; do
   echo "== $cfg" | tee -a $OUT/sweep.log
