@@ -2,7 +2,7 @@
 """bench.py — headline benchmark of the glu hot path on B200 (contract: see the task prompt / DESIGN.md §measurement).
 
 Metric (BASELINE.json): Gpairs/s of RadixSort on 32-bit key + 32-bit value pairs.
-  N = 1 : one step = one stable sort of 2^28 uniform-random uint32 (key, value) pairs (BASELINE config 3),
+  N = 1 : one step = one stable sort of 2^28 uniform-random uint32 (key, value) pairs (BASELINE configs[2]),
           inputs resident in HBM, K independent unsorted inputs (one per step; 2 GiB each, far larger than L2).
   N > 1 : weak scaling, 2^28 pairs per GPU per step, MSD split + NVLink all-to-all + local sort
           (gl-radix-sort_b200/distributed.py); value = pairs of all ranks / max-over-ranks device time.
@@ -340,28 +340,58 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_side_metrics:
         del inputs[1:]
         torch.cuda.empty_cache()
-        # ---- e2e: the same sort through the host-buffer C-ABI call, pinned host memory, copies inside
-        hk, hk_ptr = pinned_u32(glu, n)
-        hv, hv_ptr = pinned_u32(glu, n)
-        src_k = inputs[0][0]
-        e2e_steps = min(steps, 5)
-        e2e_t = 0.0
-        for i in range(e2e_steps + 1):
+        # ---- e2e: the same sort through the host-buffer C-ABI, pinned host memory, copies inside the timed region.
+        # One independent pinned (keys, values) input per step; the steps go through glu_host_sort_queue (depth 2):
+        # the upload of step k+1 overlaps the sort and the download of step k, every step still pays its own
+        # H2D + sort + D2H.  The synchronous single call (glu_radix_sort_u32kv_host) is timed beside it.
+        e2e_steps = min(steps, 8)
+        host = []
+        for i in range(e2e_steps):
+            hk, hk_ptr = pinned_u32(glu, n)
+            hv, hv_ptr = pinned_u32(glu, n)
             hk[:] = np.random.default_rng(100 + i).integers(0, 1 << 32, size=n, dtype=np.uint32)
             hv[:] = np.arange(n, dtype=np.uint32)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            glu.radix_sort_u32kv_host(hk, hv, n)
-            t1 = time.perf_counter()
-            if i > 0:  # first call warms the allocation path
-                e2e_t += t1 - t0
-        assert bool(np.all(hk[:-1][: 1 << 22] <= hk[1:][: 1 << 22]))
+            host.append((hk, hv, hk_ptr, hv_ptr))
+        queue = glu.HostSortQueue(n, depth=2)
+        wk, wk_ptr = pinned_u32(glu, 1 << 20)
+        wv, wv_ptr = pinned_u32(glu, 1 << 20)
+        wk[:] = np.arange(1 << 20, dtype=np.uint32)[::-1]
+        wv[:] = 0
+        queue.submit(wk, wv)  # warms the queue's streams
+        queue.submit(wk, wv)
+        queue.wait()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for hk, hv, _, _ in host:
+            queue.submit(hk, hv, n)
+        queue.wait()
+        e2e_t = time.perf_counter() - t0
+        queue.close()
+        for hk, hv, _, _ in host:
+            assert bool(np.all(hk[:-1][: 1 << 22] <= hk[1:][: 1 << 22])), "e2e output is not sorted"
+        # synchronous call on a fresh input (first call warms its allocation path)
+        glu.radix_sort_u32kv_host(wk, wv)
+        hk, hv = host[0][0], host[0][1]
+        hk[:] = np.random.default_rng(99).integers(0, 1 << 32, size=n, dtype=np.uint32)
+        hv[:] = np.arange(n, dtype=np.uint32)
+        glu.radix_sort_u32kv_host(hk, hv, n)
+        hk[:] = np.random.default_rng(98).integers(0, 1 << 32, size=n, dtype=np.uint32)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        glu.radix_sort_u32kv_host(hk, hv, n)
+        sync_t = time.perf_counter() - t0
         line["e2e"] = {"value": n * e2e_steps / e2e_t / 1e9, "unit": "Gpairs/s", "h2d_bytes_per_step": 8 * n,
                        "d2h_bytes_per_step": 8 * n, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_t / e2e_steps,
-                       "api": "glu_radix_sort_u32kv_host (pinned host buffers; H2D + sort + D2H inside the call)"}
-        glu.lib.glu_free_host(hk_ptr)
-        glu.lib.glu_free_host(hv_ptr)
-        del src_k
+                       "api": "glu_host_sort_queue (depth 2; per step: pinned host arrays -> H2D -> sort -> D2H, "
+                              "consecutive steps overlapped)",
+                       "synchronous_call": {"value": n / sync_t / 1e9, "ms": 1e3 * sync_t,
+                                            "api": "glu_radix_sort_u32kv_host"}}
+        for _, _, p0, p1 in host:
+            glu.lib.glu_free_host(p0)
+            glu.lib.glu_free_host(p1)
+        glu.lib.glu_free_host(wk_ptr)
+        glu.lib.glu_free_host(wv_ptr)
+        del host, hk, hv, wk, wv
         glu.profile_enable(True)
         line["side_metrics"] = side_metrics(glu, torch, dev, 1 << 28, peak)
         glu.profile_enable(False)

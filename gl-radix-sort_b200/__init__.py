@@ -64,6 +64,10 @@ ABI = {
     "glu_reduce_host": (_int, [_vp, _sz, _int, _int]),
     "glu_scan_exclusive_host": (_int, [_vp, _sz, _sz, _int]),
     "glu_radix_sort_u32kv_host": (_int, [_vp, _vp, _sz, _sz]),
+    "glu_host_sort_queue_create": (_int, [ctypes.POINTER(_vp), _sz, _int]),
+    "glu_host_sort_queue_submit": (_int, [_vp, _vp, _vp, _sz, _sz]),
+    "glu_host_sort_queue_wait": (_int, [_vp]),
+    "glu_host_sort_queue_destroy": (_int, [_vp]),
     "glu_device_count": (_int, [ctypes.POINTER(_int)]),
     "glu_set_device": (_int, [_int]),
     "glu_device_info": (_int, [_int, ctypes.c_char_p, _sz, ctypes.POINTER(_int), ctypes.POINTER(_int),
@@ -310,6 +314,40 @@ def radix_sort_u32kv_host(keys, vals, count: int | None = None, num_steps: int =
     if count is None:
         count = keys.size
     check(_lib.glu_radix_sort_u32kv_host(_np_ptr(keys), _np_ptr(vals), count, num_steps), "radix_sort_u32kv_host")
+
+
+class HostSortQueue:
+    """glu_host_sort_queue_*: up to `depth` host-buffer sorts in flight, so that the upload of one job overlaps the sort
+    and the download of the previous one.  The numpy arrays passed to submit() must stay alive (and should be pinned)
+    until wait() returns; the results land in them in place."""
+
+    def __init__(self, max_count: int, depth: int = 2):
+        self._q = _vp()
+        check(_lib.glu_host_sort_queue_create(ctypes.byref(self._q), max_count, depth), "host_sort_queue_create")
+        self._keepalive = []
+
+    def submit(self, keys, vals, count: int | None = None, num_steps: int = 0) -> None:
+        if count is None:
+            count = keys.size
+        self._keepalive.append((keys, vals))
+        check(_lib.glu_host_sort_queue_submit(self._q, _np_ptr(keys), _np_ptr(vals), count, num_steps),
+              "host_sort_queue_submit")
+
+    def wait(self) -> None:
+        check(_lib.glu_host_sort_queue_wait(self._q), "host_sort_queue_wait")
+        self._keepalive.clear()
+
+    def close(self) -> None:
+        if self._q:
+            check(_lib.glu_host_sort_queue_destroy(self._q), "host_sort_queue_destroy")
+            self._q = _vp()
+            self._keepalive.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 from . import distributed  # noqa: E402  (multi-GPU composition; imports torch lazily)

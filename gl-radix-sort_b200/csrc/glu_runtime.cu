@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <vector>
 
 #include "glu_common.cuh"
@@ -448,6 +449,120 @@ extern "C"
         GLU_CUDA_TRY(cudaStreamSynchronize(0));
         return GLU_SUCCESS;
     }
+}
+
+// ---- queue of host-buffer sorts (upload / sort / download of consecutive jobs overlap) ---------------------------
+struct glu_host_sort_queue
+{
+    struct Slot
+    {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        uint32_t* keys = nullptr;
+        uint32_t* vals = nullptr;
+        void* tmp = nullptr;
+        bool busy = false;
+    };
+    int device = 0;
+    size_t max_count = 0, tmp_bytes = 0;
+    std::vector<Slot> slots;
+    size_t next = 0;
+};
+
+extern "C" int glu_host_sort_queue_destroy(glu_host_sort_queue_t* q)
+{
+    if (!q)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    int rc = GLU_SUCCESS;
+    for (auto& s : q->slots)
+    {
+        if (s.stream && cudaStreamSynchronize(s.stream) != cudaSuccess)
+            rc = GLU_ERROR_CUDA;
+        if (s.keys)
+            cudaFree(s.keys);
+        if (s.vals)
+            cudaFree(s.vals);
+        if (s.tmp)
+            cudaFree(s.tmp);
+        if (s.done)
+            cudaEventDestroy(s.done);
+        if (s.stream)
+            cudaStreamDestroy(s.stream);
+    }
+    delete q;
+    return rc;
+}
+
+extern "C" int glu_host_sort_queue_create(glu_host_sort_queue_t** out, size_t max_count, int depth)
+{
+    if (!out || depth < 1 || depth > 8 || max_count == 0)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    const size_t tmp_bytes = glu_radix_sort_u32kv_tmp_bytes(max_count);
+    if (tmp_bytes == 0)
+        return GLU_ERROR_COUNT_TOO_LARGE;
+    glu_host_sort_queue* q = new (std::nothrow) glu_host_sort_queue;
+    if (!q)
+        return GLU_ERROR_CUDA;
+    q->max_count = max_count;
+    q->tmp_bytes = tmp_bytes;
+    q->slots.resize(size_t(depth));
+    bool ok = cudaGetDevice(&q->device) == cudaSuccess;
+    for (auto& s : q->slots)
+    {
+        ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.keys), max_count * sizeof(uint32_t)) == cudaSuccess;
+        ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.vals), max_count * sizeof(uint32_t)) == cudaSuccess;
+        ok = ok && cudaMalloc(&s.tmp, tmp_bytes) == cudaSuccess;
+    }
+    if (!ok)
+    {
+        cudaGetLastError();
+        glu_host_sort_queue_destroy(q);
+        return GLU_ERROR_CUDA;
+    }
+    *out = q;
+    return GLU_SUCCESS;
+}
+
+extern "C" int glu_host_sort_queue_submit(glu_host_sort_queue_t* q, uint32_t* h_keys, uint32_t* h_vals, size_t count,
+                                          size_t num_steps)
+{
+    if (!q || !h_keys || !h_vals)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    if (count > q->max_count)
+        return GLU_ERROR_COUNT_TOO_LARGE;
+    if (count <= 1) // glu/RadixSort.hpp:278-279
+        return GLU_SUCCESS;
+    glu_host_sort_queue::Slot& s = q->slots[q->next];
+    q->next = (q->next + 1) % q->slots.size();
+    if (s.busy)
+        GLU_CUDA_TRY(cudaEventSynchronize(s.done));
+    s.busy = false;
+    const size_t bytes = count * sizeof(uint32_t);
+    GLU_CUDA_TRY(cudaMemcpyAsync(s.keys, h_keys, bytes, cudaMemcpyHostToDevice, s.stream));
+    GLU_CUDA_TRY(cudaMemcpyAsync(s.vals, h_vals, bytes, cudaMemcpyHostToDevice, s.stream));
+    const int rc = glu_radix_sort_u32kv(s.keys, s.vals, count, num_steps, s.tmp, q->tmp_bytes, s.stream);
+    if (rc != GLU_SUCCESS)
+        return rc;
+    GLU_CUDA_TRY(cudaMemcpyAsync(h_keys, s.keys, bytes, cudaMemcpyDeviceToHost, s.stream));
+    GLU_CUDA_TRY(cudaMemcpyAsync(h_vals, s.vals, bytes, cudaMemcpyDeviceToHost, s.stream));
+    GLU_CUDA_TRY(cudaEventRecord(s.done, s.stream));
+    s.busy = true;
+    return GLU_SUCCESS;
+}
+
+extern "C" int glu_host_sort_queue_wait(glu_host_sort_queue_t* q)
+{
+    if (!q)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    for (auto& s : q->slots)
+    {
+        if (s.busy)
+            GLU_CUDA_TRY(cudaEventSynchronize(s.done));
+        s.busy = false;
+    }
+    return GLU_SUCCESS;
 }
 
 // ---- CUDA IPC (one process per GPU: map a peer rank's receive buffer into this process) ----------------------------

@@ -192,6 +192,20 @@ GLU_API int glu_reduce_host(void* h_data, size_t count, int data_type, int op);
 GLU_API int glu_scan_exclusive_host(void* h_data, size_t count, size_t num_partitions, int data_type);
 GLU_API int glu_radix_sort_u32kv_host(uint32_t* h_keys, uint32_t* h_vals, size_t count, size_t num_steps);
 
+/* A queue of host-buffer sorts for callers that sort one batch after another (the loop of
+ * test/radix_sort_tests.cpp:160-193 with real data): up to `depth` jobs are in flight, each on its own stream with
+ * its own device arrays and scratch, so the upload of job k+1 overlaps the sort and the download of job k (PCIe is
+ * full duplex; a single synchronous call leaves each direction idle half of the time).  submit() enqueues
+ * upload -> glu_radix_sort_u32kv -> download and returns; it blocks only while the slot it needs (the job submitted
+ * `depth` submits ago) is still running.  The host arrays must stay valid until wait() and should be pinned
+ * (glu_malloc_host).  Results land in place in the host arrays, exactly as with glu_radix_sort_u32kv_host. */
+typedef struct glu_host_sort_queue glu_host_sort_queue_t;
+GLU_API int glu_host_sort_queue_create(glu_host_sort_queue_t** queue, size_t max_count, int depth);
+GLU_API int glu_host_sort_queue_submit(glu_host_sort_queue_t* queue, uint32_t* h_keys, uint32_t* h_vals, size_t count,
+                                       size_t num_steps);
+GLU_API int glu_host_sort_queue_wait(glu_host_sort_queue_t* queue); /* every submitted job is complete */
+GLU_API int glu_host_sort_queue_destroy(glu_host_sort_queue_t* queue);
+
 /* ------------------------------------------------------- device plumbing for the C++ classes and test runner
  * (the ShaderStorageBuffer / measure_gl_elapsed_time roles, glu/gl_utils.hpp:146-265) */
 GLU_API int glu_device_count(int* count);

@@ -213,6 +213,30 @@ def test_sort_host_entry_point(glu, cuda_device, oracle):
     np.testing.assert_array_equal(hv, ev)
 
 
+def test_sort_host_queue_overlapped_jobs(glu, cuda_device, oracle):
+    """glu_host_sort_queue_*: several host-buffer sorts in flight (depth 2, more jobs than slots, ragged sizes,
+    one job limited by num_steps); every job must equal std::stable_sort of its own pairs."""
+    sizes = [300_000, 1, 70_001, 1_000_003, 2, 555_555]
+    q = glu.HostSortQueue(max(sizes), depth=2)
+    jobs = []
+    for j, n in enumerate(sizes):
+        keys = oracle.mt19937_u32(40 + j, n)
+        if j == 2:
+            keys &= np.uint32(0xFFFF)
+        vals = np.arange(n, dtype=np.uint32)
+        hk, hv = keys.copy(), vals.copy()
+        q.submit(hk, hv, n, 4 if j == 2 else 0)
+        jobs.append((keys, vals, hk, hv))
+    q.wait()
+    for keys, vals, hk, hv in jobs:
+        ek, ev = oracle.stable_sort_pairs(keys, vals)
+        np.testing.assert_array_equal(hk, ek)
+        np.testing.assert_array_equal(hv, ev)
+    with pytest.raises(glu.GluError):
+        q.submit(np.zeros(max(sizes) + 1, np.uint32), np.zeros(max(sizes) + 1, np.uint32))
+    q.close()
+
+
 def test_sort_beyond_2_30_pairs(glu, cuda_device):
     """2^30 + 2^27 pairs (BASELINE configs[3] puts 2^30 pairs on a GPU, and the multi-GPU receive buffers need head
     room above that): no CPU oracle at this size, so the size-independent properties — keys non-decreasing, equal keys
