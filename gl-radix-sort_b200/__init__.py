@@ -58,6 +58,10 @@ ABI = {
     "glu_radix_partition_u32kv": (_int, [_vp, _vp, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _vp, _sz, _vp]),
     "glu_radix_partition_by_dest_u32kv": (_int, [_vp, _vp, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _vp, _vp, _sz,
                                                  _vp]),
+    "glu_radix_sort_u32kv_dyn": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _sz, _vp]),
+    "glu_radix_partition_by_dest_u32kv_dyn": (_int, [_vp, _vp, _vp, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _vp, _vp,
+                                                     _sz, _vp]),
+    "glu_radix_exchange_plan": (_int, [_vp, _int, _int, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "glu_ipc_get_handle": (_int, [_vp, ctypes.c_char_p]),
     "glu_ipc_open_handle": (_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "glu_ipc_close_handle": (_int, [_vp]),
@@ -290,6 +294,24 @@ class RadixSort:
         tmp, tmp_bytes = self._scratch.ensure(0, dev)
         st = _current_stream(dev) if stream is None else stream
         check(_lib.glu_radix_sort_u32kv(kptr, vptr, count, num_steps, tmp, tmp_bytes, st), "RadixSort")
+
+    def sort_device_count(self, key_buffer, val_buffer, count_buffer, max_count: int, num_steps: int = 0,
+                          stream: int | None = None) -> None:
+        """The same sort with the number of pairs read from device memory (`count_buffer`: one uint32, <= max_count)
+        when the kernels run — glu_radix_sort_u32kv_dyn, a building block of the multi-GPU sort."""
+        kptr, kdev = _ptr_and_device(key_buffer)
+        vptr, vdev = _ptr_and_device(val_buffer)
+        cptr, _ = _ptr_and_device(count_buffer)
+        if not kptr or not vptr or not cptr:
+            raise GluError(1, "Invalid key / value / count buffer")
+        if max_count <= 1:
+            return
+        dev = _device_of(kdev if kdev is not None else vdev)
+        self.prepare_internal_buffers(max_count, dev)
+        tmp, tmp_bytes = self._scratch.ensure(0, dev)
+        st = _current_stream(dev) if stream is None else stream
+        check(_lib.glu_radix_sort_u32kv_dyn(kptr, vptr, cptr, max_count, num_steps, tmp, tmp_bytes, st),
+              "RadixSort.sort_device_count")
 
 
 # ---- host-buffer entry points (numpy arrays; upload + hot path + download inside the call) ------------------------

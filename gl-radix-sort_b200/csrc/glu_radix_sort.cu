@@ -74,10 +74,15 @@ namespace glu_b200
         // whatever the key distribution (uniform, constant and skewed digit places cost the same), at 32 KB
         // of shared memory per digit place (one 1024-thread CTA per SM).
         __global__ void __launch_bounds__(k_hist_threads, 1)
-            histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t head, uint32_t n_units,
-                             int num_passes, uint32_t pre_shift, uint32_t key_mask, uint32_t* hist, uint32_t* ticket,
-                             int make_offsets)
+            histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ d_n,
+                             uint32_t head, int num_passes, uint32_t pre_shift, uint32_t key_mask, uint32_t* hist,
+                             uint32_t* ticket, int make_offsets)
         {
+            // d_n: the count lives in device memory (written by an earlier kernel of the stream, *_dyn entry points)
+            if (d_n)
+                n = __ldg(d_n);
+            head = head < n ? head : n;                // keys before the first 16-byte boundary
+            const uint32_t n_units = (n - head) / 4;   // 128-bit units of the aligned body
             extern __shared__ __align__(16) uint32_t s_hist[]; // [num_passes][k_radix][k_hist_copies]
             __shared__ uint32_t s_scan[k_hist_threads / 32];
             __shared__ bool s_is_last;
@@ -375,8 +380,9 @@ namespace glu_b200
                             uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
                             uint32_t shift, uint32_t mask, const uint32_t* __restrict__ digit_offset,
                             uint32_t* lookback, uint32_t* prefix, uint32_t* ticket, uint32_t num_tiles, int allow_tma,
-                            int chain_rows, int options, uint32_t* const* key_dst = nullptr,
-                            uint32_t* const* val_dst = nullptr, const uint8_t* __restrict__ dest_lut = nullptr)
+                            int chain_rows, int options, const uint32_t* __restrict__ d_n = nullptr,
+                            uint32_t* const* key_dst = nullptr, uint32_t* const* val_dst = nullptr,
+                            const uint8_t* __restrict__ dest_lut = nullptr)
         {
             static_assert(!DEST || PEER, "DEST is a flavour of PEER");
             static_assert(RANK_THREADS >= k_radix && RANK_THREADS % 32 == 0, "one ranking thread per digit");
@@ -392,6 +398,13 @@ namespace glu_b200
 
             const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
             const uint32_t chain_ctas = chain_rows >= 100 ? 4u : 8u; // 64 or 32 digits per chain CTA
+            if (d_n)
+            {
+                // *_dyn entry points: the count is device-resident (<= the n the grid and the scratch were sized
+                // for); CTAs past the last tile leave at once
+                n = __ldg(d_n);
+                num_tiles = (n + uint32_t(TILE) - 1) / uint32_t(TILE);
+            }
             if (tid == 0)
             {
                 mbarrier_init(&s.bar_keys, 1);
@@ -404,7 +417,7 @@ namespace glu_b200
                 s.tile = t;
                 // a full tile's bulk copies leave the moment the ticket is known (the rest of the CTA is still
                 // clearing its counters)
-                if (allow_tma && t >= chain_ctas && n - (t - chain_ctas) * uint32_t(TILE) >= uint32_t(TILE))
+                if (allow_tma && t >= chain_ctas && uint64_t(t - chain_ctas + 1) * uint32_t(TILE) <= uint64_t(n))
                 {
                     const uint32_t tb = (t - chain_ctas) * uint32_t(TILE);
                     const uint64_t policy = l2_policy_evict_first();
@@ -412,6 +425,14 @@ namespace glu_b200
                     tma_load_1d(s.keys, keys_in + tb, TILE * 4, &s.bar_keys, policy);
                     mbarrier_arrive_expect_tx(&s.bar_vals, TILE * 4);
                     tma_load_1d(s.vals, vals_in + tb, TILE * 4, &s.bar_vals, policy);
+                    // L2 prefetch of the tile that will occupy this CTA slot `options >> 8` tiles from now: its bulk
+                    // copies then start from L2 instead of paying the loaded-DRAM latency at CTA start
+                    const uint64_t ahead = uint64_t(t - chain_ctas) + uint32_t(options >> 8);
+                    if ((options >> 8) != 0 && (ahead + 1) * uint64_t(TILE) <= uint64_t(n))
+                    {
+                        tma_prefetch_l2_1d(keys_in + ahead * TILE, TILE * 4);
+                        tma_prefetch_l2_1d(vals_in + ahead * TILE, TILE * 4);
+                    }
                 }
             }
             for (int i = tid; i < WARPS * k_radix / 4; i += THREADS)
@@ -447,6 +468,8 @@ namespace glu_b200
                 return;
             }
             const uint32_t tile = s.tile - chain_ctas;
+            if (tile >= num_tiles)
+                return;
             const uint32_t tile_base = tile * uint32_t(TILE);
             const uint32_t valid = n - tile_base < uint32_t(TILE) ? n - tile_base : uint32_t(TILE);
             const bool full = valid == uint32_t(TILE);
@@ -737,8 +760,9 @@ namespace glu_b200
         template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false>
         int launch_sweep(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint32_t n, uint32_t shift,
                          uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback, uint32_t* ticket,
-                         unsigned tiles, cudaStream_t s, uint32_t* const* key_dst = nullptr,
-                         uint32_t* const* val_dst = nullptr, const uint8_t* dest_lut = nullptr)
+                         unsigned tiles, cudaStream_t s, const uint32_t* d_n = nullptr,
+                         uint32_t* const* key_dst = nullptr, uint32_t* const* val_dst = nullptr,
+                         const uint8_t* dest_lut = nullptr)
         {
             // per pass: `tiles` count rows followed by `tiles` prefix rows; grid = tiles + the chain CTAs
             uint32_t* prefix = lookback + size_t(tiles) * k_radix;
@@ -749,7 +773,13 @@ namespace glu_b200
             constexpr size_t smem = sizeof(SweepSmem<THREADS, IPT, PEER>);
             static const int chain_rows = env_int("GLU_SORT_CHAIN_ROWS", 8);
             // bit 0: skip the look-back (timing experiments, wrong results); bit 1: tile ids from an atomic ticket
-            static const int options = env_int("GLU_SORT_OPTIONS", 0);
+            // bits 8..: L2 prefetch distance in tiles (GLU_SORT_PREFETCH; 0 = off).  Default: one tile per SM ahead —
+            // a third of the resident wave at 3 CTAs per SM; 74..444 measured within 1 % of each other at 2^28,
+            // 888 (two waves: the lines are evicted again before they are used) 6 % slower than no prefetch.
+            static const int prefetch_env = env_int("GLU_SORT_PREFETCH", -1);
+            const int prefetch_tiles = prefetch_env >= 0 ? (prefetch_env > 0xffff ? 0xffff : prefetch_env) : current_sm_count();
+            static const int options_env = env_int("GLU_SORT_OPTIONS", 0) & 0xff;
+            const int options = options_env | (prefetch_tiles << 8);
             static bool configured[64] = {};
             int dev = 0;
             GLU_CUDA_TRY(cudaGetDevice(&dev));
@@ -763,7 +793,7 @@ namespace glu_b200
             const unsigned grid = tiles + (chain_rows >= 100 ? 4 : 8);
             ScopedKernelProfile prof(PEER ? GLU_KERNEL_SORT_PARTITION : GLU_KERNEL_SORT_ONESWEEP, s);
             kernel<<<grid, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
-                                                    tiles, allow_tma, chain_rows, options, key_dst, val_dst, dest_lut);
+                                                    tiles, allow_tma, chain_rows, options, d_n, key_dst, val_dst, dest_lut);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
@@ -771,12 +801,12 @@ namespace glu_b200
         template<int MODE>
         int dispatch_sweep(const SweepConfig& c, const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo,
                            uint32_t n, uint32_t shift, uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback,
-                           uint32_t* ticket, unsigned tiles, cudaStream_t s)
+                           uint32_t* ticket, unsigned tiles, cudaStream_t s, const uint32_t* d_n)
         {
             switch (c.id)
             {
 #define GLU_SWEEP_CASE(ID, T, I, B)                                                                                    \
-    case ID: return launch_sweep<T, I, B, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+    case ID: return launch_sweep<T, I, B, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s, d_n);
                 GLU_SWEEP_CASE(0, 512, 16, 2)
                 GLU_SWEEP_CASE(1, 384, 18, 3)
                 GLU_SWEEP_CASE(2, 256, 16, 4)
@@ -785,7 +815,7 @@ namespace glu_b200
                 GLU_SWEEP_CASE(6, 384, 16, 3)
                 GLU_SWEEP_CASE(7, 320, 18, 4)
                 GLU_SWEEP_CASE(8, 320, 24, 3)
-            default: return launch_sweep<256, 8, 4, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+            default: return launch_sweep<256, 8, 4, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s, d_n);
 #undef GLU_SWEEP_CASE
             }
         }
@@ -799,14 +829,14 @@ namespace
     // the partition pass always uses the large-input tile shape
     constexpr int k_part_threads = 320, k_part_ipt = 24, k_part_blocks = 3;
 
+    // n: the count, or its upper bound when d_n (device-resident count) is given
     int launch_histogram(const uint32_t* d_keys, uint32_t n, int num_passes, uint32_t pre_shift, uint32_t key_mask,
-                         uint32_t* hist, uint32_t* ticket, int make_offsets, int sms, cudaStream_t s)
+                         uint32_t* hist, uint32_t* ticket, int make_offsets, int sms, cudaStream_t s,
+                         const uint32_t* d_n = nullptr)
     {
         const uintptr_t addr = reinterpret_cast<uintptr_t>(d_keys);
-        uint32_t head = uint32_t(((16 - (addr & 15)) & 15) / sizeof(uint32_t));
-        if (head > n)
-            head = n;
-        const uint32_t n_units = (n - head) / 4;
+        const uint32_t head = uint32_t(((16 - (addr & 15)) & 15) / sizeof(uint32_t));
+        const uint32_t n_units = (n - (head < n ? head : n)) / 4;
         const size_t per_block = size_t(k_hist_threads) * k_hist_unroll;
         size_t grid = (size_t(n_units) + per_block - 1) / per_block;
         const size_t cap = size_t(sms) * k_hist_blocks_per_sm;
@@ -824,7 +854,7 @@ namespace
             configured[dev] = true;
         }
         ScopedKernelProfile prof(GLU_KERNEL_SORT_HISTOGRAM, s);
-        histogram_kernel<<<unsigned(grid), k_hist_threads, smem, s>>>(d_keys, n, head, n_units, num_passes, pre_shift,
+        histogram_kernel<<<unsigned(grid), k_hist_threads, smem, s>>>(d_keys, n, d_n, head, num_passes, pre_shift,
                                                                        key_mask, hist, ticket, make_offsets);
         GLU_LAUNCH_CHECK();
         return GLU_SUCCESS;
@@ -840,6 +870,14 @@ extern "C" size_t glu_radix_sort_u32kv_tmp_bytes(size_t count)
     return make_layout(count).total;
 }
 
+namespace
+{
+    // count: the number of pairs, or (d_n != nullptr) the bound the grids and the scratch are sized for while the
+    // actual number is read from *d_n by the kernels
+    int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* d_n, size_t num_steps, void* d_tmp,
+                  size_t tmp_bytes, glu_stream_t stream);
+}
+
 extern "C" int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t count, size_t num_steps, void* d_tmp,
                                     size_t tmp_bytes, glu_stream_t stream)
 {
@@ -847,6 +885,26 @@ extern "C" int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t c
         return GLU_ERROR_INVALID_ARGUMENT;
     if (count <= 1) // glu/RadixSort.hpp:278-279
         return GLU_SUCCESS;
+    return sort_impl(d_keys, d_vals, count, nullptr, num_steps, d_tmp, tmp_bytes, stream);
+}
+
+extern "C" int glu_radix_sort_u32kv_dyn(uint32_t* d_keys, uint32_t* d_vals, const uint32_t* d_count, size_t max_count,
+                                        size_t num_steps, void* d_tmp, size_t tmp_bytes, glu_stream_t stream)
+{
+    if (!d_keys || !d_vals || !d_count)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(d_count) % sizeof(uint32_t) != 0)
+        return GLU_ERROR_MISALIGNED;
+    if (max_count <= 1)
+        return GLU_SUCCESS;
+    return sort_impl(d_keys, d_vals, max_count, d_count, num_steps, d_tmp, tmp_bytes, stream);
+}
+
+namespace
+{
+int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* d_n, size_t num_steps, void* d_tmp,
+              size_t tmp_bytes, glu_stream_t stream)
+{
     if (count > k_max_count)
         return GLU_ERROR_COUNT_TOO_LARGE;
     if ((reinterpret_cast<uintptr_t>(d_keys) | reinterpret_cast<uintptr_t>(d_vals)) % sizeof(uint32_t) != 0)
@@ -874,7 +932,7 @@ extern "C" int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t c
     GLU_CUDA_TRY(cudaMemsetAsync(tmp, 0, used_control, s));
 
     {
-        const int rc = launch_histogram(d_keys, n, plan.num_passes, 0u, plan.key_mask, hist, tickets + 4, 1, sms, s);
+        const int rc = launch_histogram(d_keys, n, plan.num_passes, 0u, plan.key_mask, hist, tickets + 4, 1, sms, s, d_n);
         if (rc != GLU_SUCCESS)
             return rc;
     }
@@ -892,9 +950,9 @@ extern "C" int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t c
         uint32_t* lb = lookback + 2 * size_t(p) * l.tiles * k_radix;
         int rc = mode == Rank_Ballot
                      ? dispatch_sweep<Rank_Ballot>(cfg, ki, vi, ko, vo, n, plan.shift[p], plan.mask[p],
-                                                   hist + p * k_radix, lb, tickets + p, unsigned(l.tiles), s)
+                                                   hist + p * k_radix, lb, tickets + p, unsigned(l.tiles), s, d_n)
                      : dispatch_sweep<Rank_Match>(cfg, ki, vi, ko, vo, n, plan.shift[p], plan.mask[p],
-                                                  hist + p * k_radix, lb, tickets + p, unsigned(l.tiles), s);
+                                                  hist + p * k_radix, lb, tickets + p, unsigned(l.tiles), s, d_n);
         if (rc != GLU_SUCCESS)
             return rc;
     }
@@ -907,6 +965,7 @@ extern "C" int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t c
     }
     return GLU_SUCCESS;
 }
+} // namespace
 
 // ------------------------------------------------------------------------------ multi-GPU building blocks
 
@@ -968,13 +1027,44 @@ extern "C" int glu_radix_partition_u32kv(const uint32_t* d_keys, const uint32_t*
     uint32_t* lookback = reinterpret_cast<uint32_t*>(tmp + k_tmp_align);
     return launch_sweep<k_part_threads, k_part_ipt, k_part_blocks, Rank_Ballot, true>(
         d_keys, d_vals, nullptr, nullptr, uint32_t(count), shift, (1u << bits) - 1u, nullptr, lookback, ticket, tiles, s,
-        d_key_dst, d_val_dst);
+        nullptr, d_key_dst, d_val_dst);
+}
+
+namespace
+{
+    int partition_by_dest_impl(const uint32_t* d_keys, const uint32_t* d_vals, size_t count, const uint32_t* d_n,
+                               unsigned shift, unsigned bits, const uint8_t* d_dest_of_digit, uint32_t* const* d_key_dst,
+                               uint32_t* const* d_val_dst, void* d_tmp, size_t tmp_bytes, glu_stream_t stream);
 }
 
 extern "C" int glu_radix_partition_by_dest_u32kv(const uint32_t* d_keys, const uint32_t* d_vals, size_t count,
                                                  unsigned shift, unsigned bits, const uint8_t* d_dest_of_digit,
                                                  uint32_t* const* d_key_dst, uint32_t* const* d_val_dst, void* d_tmp,
                                                  size_t tmp_bytes, glu_stream_t stream)
+{
+    return partition_by_dest_impl(d_keys, d_vals, count, nullptr, shift, bits, d_dest_of_digit, d_key_dst, d_val_dst,
+                                  d_tmp, tmp_bytes, stream);
+}
+
+extern "C" int glu_radix_partition_by_dest_u32kv_dyn(const uint32_t* d_keys, const uint32_t* d_vals,
+                                                     const uint32_t* d_count, size_t max_count, unsigned shift,
+                                                     unsigned bits, const uint8_t* d_dest_of_digit,
+                                                     uint32_t* const* d_key_dst, uint32_t* const* d_val_dst, void* d_tmp,
+                                                     size_t tmp_bytes, glu_stream_t stream)
+{
+    if (!d_count)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(d_count) % sizeof(uint32_t) != 0)
+        return GLU_ERROR_MISALIGNED;
+    return partition_by_dest_impl(d_keys, d_vals, max_count, d_count, shift, bits, d_dest_of_digit, d_key_dst, d_val_dst,
+                                  d_tmp, tmp_bytes, stream);
+}
+
+namespace
+{
+int partition_by_dest_impl(const uint32_t* d_keys, const uint32_t* d_vals, size_t count, const uint32_t* d_n,
+                           unsigned shift, unsigned bits, const uint8_t* d_dest_of_digit, uint32_t* const* d_key_dst,
+                           uint32_t* const* d_val_dst, void* d_tmp, size_t tmp_bytes, glu_stream_t stream)
 {
     if (!d_keys || !d_vals || !d_dest_of_digit || !d_key_dst || !d_val_dst || bits == 0 || bits > 8 || shift > 31)
         return GLU_ERROR_INVALID_ARGUMENT;
@@ -1001,5 +1091,126 @@ extern "C" int glu_radix_partition_by_dest_u32kv(const uint32_t* d_keys, const u
     uint32_t* lookback = reinterpret_cast<uint32_t*>(tmp + k_tmp_align);
     return launch_sweep<k_part_threads, k_part_ipt, k_part_blocks, Rank_Ballot, true, true>(
         d_keys, d_vals, nullptr, nullptr, uint32_t(count), shift, (1u << bits) - 1u, nullptr, lookback, ticket, tiles, s,
-        d_key_dst, d_val_dst, d_dest_of_digit);
+        d_n, d_key_dst, d_val_dst, d_dest_of_digit);
+}
+} // namespace
+
+// ------------------------------------------------------------------------------ exchange plan on the device
+
+namespace glu_b200
+{
+namespace
+{
+    constexpr int k_max_plan_world = 16; // the by-destination partition handles < 16 destinations... 16 pointers
+
+    // One CTA of 256 threads, thread b = bucket b.  The device-side twin of distributed.plan_exchange /
+    // assign_buckets (gl-radix-sort_b200/distributed.py): same integer arithmetic, same results.
+    __global__ void __launch_bounds__(k_radix, 1)
+        exchange_plan_kernel(const uint32_t* __restrict__ hist_all, int world, int rank, uint32_t send_count,
+                             uint64_t capacity, const uint64_t* __restrict__ peer_keys,
+                             const uint64_t* __restrict__ peer_vals, uint64_t* key_dst, uint64_t* val_dst,
+                             uint8_t* dest_of_digit, uint32_t* counts, uint64_t* info)
+    {
+        __shared__ unsigned long long s_warp[k_radix / 32];
+        __shared__ uint32_t s_send[k_max_plan_world][k_max_plan_world]; // pairs source s sends to destination g
+        __shared__ unsigned long long s_recv[k_max_plan_world];
+        __shared__ int s_overflow;
+        const unsigned b = threadIdx.x, lane = b & 31, warp = b >> 5;
+        if (b < k_max_plan_world * k_max_plan_world)
+            (&s_send[0][0])[b] = 0;
+        if (b == 0)
+            s_overflow = 0;
+        uint32_t cnt[k_max_plan_world];
+        unsigned long long bucket = 0;
+#pragma unroll
+        for (int src = 0; src < k_max_plan_world; src++)
+        {
+            cnt[src] = src < world ? hist_all[src * k_radix + b] : 0u;
+            bucket += cnt[src];
+        }
+        // exclusive prefix of the bucket totals over b, and the job's total
+        unsigned long long inc = bucket;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned long long t = __shfl_up_sync(k_full_mask, inc, o);
+            if (lane >= unsigned(o))
+                inc += t;
+        }
+        if (lane == 31)
+            s_warp[warp] = inc;
+        __syncthreads();
+        unsigned long long before = inc - bucket, total = 0;
+        for (unsigned w = 0; w < k_radix / 32; w++)
+        {
+            if (w < warp)
+                before += s_warp[w];
+            total += s_warp[w];
+        }
+        // a bucket goes to the rank in whose share of the global order its midpoint falls (assign_buckets)
+        unsigned dest = 0;
+        if (total)
+        {
+            const unsigned long long d = (2 * before + bucket) * (unsigned long long)world / (2 * total);
+            dest = d < (unsigned long long)(world - 1) ? unsigned(d) : unsigned(world - 1);
+        }
+        dest_of_digit[b] = uint8_t(dest);
+#pragma unroll
+        for (int src = 0; src < k_max_plan_world; src++)
+            if (src < world && cnt[src])
+                atomicAdd(&s_send[src][dest], cnt[src]);
+        __syncthreads();
+        // destination g's receive buffer: the sources one after the other in rank order (source-major, stable)
+        unsigned long long recv = 0, offset = 0;
+        if (b < unsigned(world))
+        {
+            for (int src = 0; src < world; src++)
+            {
+                if (src < rank)
+                    offset += s_send[src][b];
+                recv += s_send[src][b];
+            }
+            s_recv[b] = recv;
+            if (recv > capacity)
+                atomicOr(&s_overflow, 1);
+        }
+        __syncthreads();
+        const bool overflow = s_overflow != 0;
+        key_dst[b] = (b < unsigned(world) && !overflow) ? peer_keys[b] + 4ull * offset : 0ull;
+        val_dst[b] = (b < unsigned(world) && !overflow) ? peer_vals[b] + 4ull * offset : 0ull;
+        if (b < unsigned(world))
+            info[b] = recv;
+        if (b == 0)
+        {
+            // on overflow nothing is sent and nothing is sorted; the host raises once it has read info[]
+            counts[0] = overflow ? 0u : send_count;
+            counts[1] = overflow ? 0u : uint32_t(s_recv[rank]);
+            info[world] = s_recv[rank];
+            info[world + 1] = overflow ? 1ull : 0ull;
+        }
+    }
+} // namespace
+} // namespace glu_b200
+
+extern "C" int glu_radix_exchange_plan(const uint32_t* d_hist_all, int world, int rank, size_t send_count,
+                                       size_t capacity, const uint64_t* d_peer_keys, const uint64_t* d_peer_vals,
+                                       uint32_t** d_key_dst, uint32_t** d_val_dst, uint8_t* d_dest_of_digit,
+                                       uint32_t* d_counts, uint64_t* d_info, glu_stream_t stream)
+{
+    if (!d_hist_all || !d_peer_keys || !d_peer_vals || !d_key_dst || !d_val_dst || !d_dest_of_digit || !d_counts ||
+        !d_info || world < 1 || world > k_max_plan_world || rank < 0 || rank >= world)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    if (send_count > k_max_count || capacity > k_max_count)
+        return GLU_ERROR_COUNT_TOO_LARGE;
+    if ((reinterpret_cast<uintptr_t>(d_hist_all) | reinterpret_cast<uintptr_t>(d_counts)) % sizeof(uint32_t) != 0 ||
+        (reinterpret_cast<uintptr_t>(d_peer_keys) | reinterpret_cast<uintptr_t>(d_peer_vals) |
+         reinterpret_cast<uintptr_t>(d_key_dst) | reinterpret_cast<uintptr_t>(d_val_dst) |
+         reinterpret_cast<uintptr_t>(d_info)) % sizeof(uint64_t) != 0)
+        return GLU_ERROR_MISALIGNED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    exchange_plan_kernel<<<1, k_radix, 0, s>>>(d_hist_all, world, rank, uint32_t(send_count), uint64_t(capacity),
+                                               d_peer_keys, d_peer_vals, reinterpret_cast<uint64_t*>(d_key_dst),
+                                               reinterpret_cast<uint64_t*>(d_val_dst), d_dest_of_digit, d_counts, d_info);
+    GLU_LAUNCH_CHECK();
+    return GLU_SUCCESS;
 }

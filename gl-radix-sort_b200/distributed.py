@@ -219,7 +219,7 @@ class DistributedRadixSort:
     slice of the global result, valid until the next call.  Rank r's keys are <= rank r+1's."""
 
     def __init__(self, max_count: int, group=None, capacity_factor: float = 1.25, exchange: str = "auto",
-                 split_shift: int | str = 32 - RADIX_BITS):
+                 split_shift: int | str = 32 - RADIX_BITS, plan: str = "auto"):
         import torch
 
         glu, dist = _glu(), _dist()
@@ -248,7 +248,27 @@ class DistributedRadixSort:
         self._peer_keys = self._peer_vals = None
         self._stage_keys = self._stage_vals = None
         self.exchange = self._setup_exchange(exchange)
+        # plan="device": the exchange plan is computed by glu_radix_exchange_plan and the partition / local sort read
+        # their counts from device memory — the step has no host round trip between the histogram and the sort (the
+        # host only waits, after everything is enqueued, for the few bytes that tell it how much it received).
+        # plan="host": histogram -> host (numpy plan_exchange) -> tables uploaded; needed by the NCCL exchange (its
+        # split sizes are host arguments) and by worlds of more than 16 ranks.
+        if plan not in ("auto", "device", "host"):
+            raise ValueError(plan)
+        can_device = self.exchange == "p2p" and self.by_dest
+        if plan == "device" and not can_device:
+            raise glu.GluError(1, "DistributedRadixSort: plan='device' needs the p2p exchange and at most 16 ranks")
+        self.plan_mode = "device" if (plan in ("auto", "device") and can_device) else "host"
+        if self.plan_mode == "device":
+            peers = torch.from_numpy(np.concatenate([self._peer_keys, self._peer_vals]).astype(np.int64))
+            self._peers_dev = peers.to(self.device)                      # [world] key bases, [world] value bases
+            self._counts_dev = torch.zeros(2, dtype=torch.int32, device=self.device)   # pairs sent, pairs received
+            self._info_dev = torch.zeros(self.world + 2, dtype=torch.int64, device=self.device)
+            self._info_host = torch.zeros(self.world + 2, dtype=torch.int64).pin_memory()
+            self._hist_host = torch.zeros(self.world * RADIX, dtype=torch.int32).pin_memory()
+            self._plan_event = torch.cuda.Event()
         self.last_plan = None
+        self._last_hist = None
         self.timing = None  # set to a dict to get per-phase wall times in ms (synchronises after every phase)
 
     # -- peer mappings (CUDA IPC): rank g's receive buffers mapped into this process
@@ -343,6 +363,8 @@ class DistributedRadixSort:
             def mark(name):
                 pass
         shift = self._split_shift(kptr, count, st)
+        if self.plan_mode == "device":
+            return self._call_device_plan(kptr, vptr, count, shift, st, mark)
 
         # 1-2. local digit histogram -> counts[src][bucket] on every rank (this all-gather also orders this call's
         #      peer writes after every rank's previous use of its receive buffers)
@@ -409,3 +431,50 @@ class DistributedRadixSort:
             self._sorter(rk, rv, m)
         mark("local sort")
         return rk[:m], rv[:m], m
+
+    def _call_device_plan(self, kptr: int, vptr: int, count: int, shift: int, st: int, mark):
+        """The step without a host round trip: histogram -> all-gather -> plan kernel -> partition (+ NVLink all-to-all)
+        -> device barrier -> local sort, all enqueued back to back; counts travel through device memory."""
+        glu, dist = _glu(), _dist()
+        world, rank = self.world, self.rank
+        glu.check(glu.lib.glu_radix_histogram_u32(kptr, count, shift, RADIX_BITS, self._hist.data_ptr(), st),
+                  "glu_radix_histogram_u32")
+        # (this all-gather also orders this call's peer writes after every rank's previous use of its receive buffers)
+        dist.all_gather_into_tensor(self._hist_all, self._hist, group=self.group)
+        tptr = self._tables.data_ptr()
+        pptr = self._peers_dev.data_ptr()
+        glu.check(glu.lib.glu_radix_exchange_plan(self._hist_all.data_ptr(), world, rank, count, self.capacity, pptr,
+                                                  pptr + 8 * world, tptr, tptr + 8 * RADIX, tptr + 16 * RADIX,
+                                                  self._counts_dev.data_ptr(), self._info_dev.data_ptr(), st),
+                  "glu_radix_exchange_plan")
+        self._info_host.copy_(self._info_dev, non_blocking=True)
+        self._hist_host.copy_(self._hist_all, non_blocking=True)
+        self._plan_event.record()
+        mark("histogram+allgather+plan")
+        cptr = self._counts_dev.data_ptr()
+        glu.check(glu.lib.glu_radix_partition_by_dest_u32kv_dyn(kptr, vptr, cptr, count, shift, RADIX_BITS,
+                                                                tptr + 16 * RADIX, tptr, tptr + 8 * RADIX,
+                                                                self._part_tmp.data_ptr(), self._part_tmp.numel(), st),
+                  "glu_radix_partition_by_dest_u32kv_dyn")
+        # device-side barrier: when this tiny all-reduce completes, every rank's partition kernel has completed
+        dist.all_reduce(self._token, group=self.group)
+        mark("partition+exchange")
+        rk, rv = self._recv_keys.tensor, self._recv_vals.tensor
+        self._sorter.sort_device_count(rk, rv, cptr + 4, self.capacity)
+        mark("local sort")
+        # only now does the host look at the plan: the GPU is busy with the partition and the sort meanwhile
+        self._plan_event.synchronize()
+        info = self._info_host.numpy()
+        self.last_plan = None
+        self._last_hist = self._hist_host.numpy().view(np.uint32).reshape(world, RADIX)
+        if int(info[world + 1]) != 0:
+            raise glu.GluError(6, f"DistributedRadixSort: a rank would receive {int(info[:world].max())} pairs, "
+                                  f"capacity is {self.capacity} (raise capacity_factor or use split_shift='auto')")
+        m = int(info[world])
+        return rk[:m], rv[:m], m
+
+    def plan_of_last_call(self) -> ExchangePlan:
+        """The exchange plan of the last call (host restatement of what the device computed, for inspection/tests)."""
+        if self.last_plan is None and self._last_hist is not None:
+            self.last_plan = plan_exchange(self._last_hist.copy())
+        return self.last_plan

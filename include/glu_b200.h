@@ -178,6 +178,34 @@ GLU_API int glu_radix_partition_by_dest_u32kv(const uint32_t* d_keys, const uint
                                               uint32_t* const* d_key_dst, uint32_t* const* d_val_dst, void* d_tmp,
                                               size_t tmp_bytes, glu_stream_t stream);
 
+/* Device-resident counts: the same kernels reading the number of pairs from *d_count (a uint32 in device memory written
+ * by an earlier operation of the stream; *d_count <= max_count) — what lets the multi-GPU sort run without a host
+ * round trip between its exchange plan and the passes that depend on it.  Grids and d_tmp are sized for max_count
+ * (glu_radix_sort_u32kv_tmp_bytes(max_count) / glu_radix_partition_u32kv_tmp_bytes(max_count)); after the sort
+ * elements [*d_count, max_count) of d_keys / d_vals are undefined. */
+GLU_API int glu_radix_sort_u32kv_dyn(uint32_t* d_keys, uint32_t* d_vals, const uint32_t* d_count, size_t max_count,
+                                     size_t num_steps, void* d_tmp, size_t tmp_bytes, glu_stream_t stream);
+GLU_API int glu_radix_partition_by_dest_u32kv_dyn(const uint32_t* d_keys, const uint32_t* d_vals,
+                                                  const uint32_t* d_count, size_t max_count, unsigned shift,
+                                                  unsigned bits, const uint8_t* d_dest_of_digit,
+                                                  uint32_t* const* d_key_dst, uint32_t* const* d_val_dst, void* d_tmp,
+                                                  size_t tmp_bytes, glu_stream_t stream);
+
+/* The exchange plan of the multi-GPU sort, computed on the device from the all-gathered split-digit histograms
+ * d_hist_all[world][256] (world <= 16): bucket -> destination rank by balanced prefix (contiguous bucket ranges),
+ * and this rank's destination table for glu_radix_partition_by_dest_u32kv_dyn —
+ *   d_dest_of_digit[256]            destination rank of every bucket,
+ *   d_key_dst / d_val_dst[256]      entry g < world: d_peer_keys[g] / d_peer_vals[g] (base address of rank g's receive
+ *                                   arrays as mapped in THIS process) advanced past what ranks < `rank` send to g,
+ *   d_counts[0]                     pairs this rank sends (= send_count), d_counts[1] pairs this rank receives,
+ *   d_info[world + 2]               pairs every rank receives, then d_counts[1], then an overflow flag.
+ * If any rank would receive more than `capacity` pairs the flag is set, both counts are 0 and every destination is
+ * NULL, so the dependent passes do nothing; the host reads d_info and reports.  One tiny kernel, no host sync. */
+GLU_API int glu_radix_exchange_plan(const uint32_t* d_hist_all, int world, int rank, size_t send_count, size_t capacity,
+                                    const uint64_t* d_peer_keys, const uint64_t* d_peer_vals, uint32_t** d_key_dst,
+                                    uint32_t** d_val_dst, uint8_t* d_dest_of_digit, uint32_t* d_counts,
+                                    uint64_t* d_info, glu_stream_t stream);
+
 /* CUDA IPC plumbing for one-process-per-GPU peer access: export a glu_malloc'ed allocation, map a peer's. */
 #define GLU_IPC_HANDLE_BYTES 64
 GLU_API int glu_ipc_get_handle(void* d_ptr, unsigned char handle[GLU_IPC_HANDLE_BYTES]);

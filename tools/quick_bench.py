@@ -46,6 +46,18 @@ if "sort" in args.what:
         keys0 = torch.zeros(n, dtype=torch.int32, device=dev)
     elif args.dist == "ent16":
         keys0 = torch.randint(0, 1 << 16, (n,), dtype=torch.int32, device=dev, generator=g)
+    elif args.dist == "ent16hi":
+        keys0 = torch.randint(0, 1 << 16, (n,), dtype=torch.int32, device=dev, generator=g) << 16
+    elif args.dist == "zipf":
+        # Zipf(s = 1.1) over 2^20 distinct keys by inverse-CDF sampling (BASELINE.json configs[4])
+        ranks = torch.arange(1, (1 << 20) + 1, dtype=torch.float64, device=dev)
+        cdf = torch.cumsum(ranks.pow(-1.1), 0)
+        cdf /= cdf[-1].clone()
+        u = torch.rand(n, dtype=torch.float64, device=dev, generator=g)
+        keys0 = torch.searchsorted(cdf, u).to(torch.int32)
+        del ranks, cdf, u
+    else:
+        raise SystemExit(f"unknown --dist {args.dist}")
     vals0 = torch.arange(n, dtype=torch.int32, device=dev)
     keys, vals = keys0.clone(), vals0.clone()
     sorter = glu.RadixSort()
