@@ -374,18 +374,7 @@ namespace glu_b200
         // PEER: digit run d goes to key_dst[d] / val_dst[d] instead of one output array.  DEST (with PEER): the pass
         // partitions by dest_lut[digit] (< 16 destinations) instead of by the digit itself, so a tile leaves as a
         // handful of long runs — what remote (NVLink) stores want.
-        //
-        // LOAD: how the tile reaches the SM.  0: keys and values by TMA bulk copies into shared memory (staging = the
-        // tile-sorted arrays, reused in place).  1: keys straight into registers with warp-striped streaming loads (a
-        // CTA has nothing to do before its keys arrive anyway; saves the staging write + read-back of shared memory,
-        // the busiest pipe of this kernel), values by TMA.  2: values straight into registers too, after ranking.
-        //
-        // MFIRST ("match first"): the digit matching moves into the counting step.  The lowest lane of every group of
-        // equal digits adds the group's size to the warp's counter with ONE returning shared-memory atomic and
-        // broadcasts the old value, which makes (old + lower peers) the key's stable rank inside its warp; ranking is
-        // then offset[warp][digit] + that rank, with no read-modify-write chain and no warp barriers between items.
-        template<int RANK_THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false, int LOAD = 0,
-                 bool MFIRST = false>
+        template<int RANK_THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false>
         __global__ void __launch_bounds__(RANK_THREADS, MIN_BLOCKS)
             onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                             uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
@@ -432,16 +421,10 @@ namespace glu_b200
                 {
                     const uint32_t tb = (t - chain_ctas) * uint32_t(TILE);
                     const uint64_t policy = l2_policy_evict_first();
-                    if constexpr (LOAD == 0)
-                    {
-                        mbarrier_arrive_expect_tx(&s.bar_keys, TILE * 4);
-                        tma_load_1d(s.keys, keys_in + tb, TILE * 4, &s.bar_keys, policy);
-                    }
-                    if constexpr (LOAD <= 1)
-                    {
-                        mbarrier_arrive_expect_tx(&s.bar_vals, TILE * 4);
-                        tma_load_1d(s.vals, vals_in + tb, TILE * 4, &s.bar_vals, policy);
-                    }
+                    mbarrier_arrive_expect_tx(&s.bar_keys, TILE * 4);
+                    tma_load_1d(s.keys, keys_in + tb, TILE * 4, &s.bar_keys, policy);
+                    mbarrier_arrive_expect_tx(&s.bar_vals, TILE * 4);
+                    tma_load_1d(s.vals, vals_in + tb, TILE * 4, &s.bar_vals, policy);
                     // L2 prefetch of the tile that will occupy this CTA slot `options >> 8` tiles from now: its bulk
                     // copies then start from L2 instead of paying the loaded-DRAM latency at CTA start
                     const uint64_t ahead = uint64_t(t - chain_ctas) + uint32_t(options >> 8);
@@ -494,49 +477,27 @@ namespace glu_b200
             const uint32_t my_off = warp * WARP_ELEMS + lane; // + i * 32   (warp-striped)
 
             // ---- stage the tile
-            if (!use_tma && LOAD <= 1)
+            if (!use_tma)
             {
                 // Slots past the end of the input hold the largest key: they rank after every real key
                 // of the tile and are never written back.
                 for (uint32_t idx = tid; idx < uint32_t(TILE); idx += THREADS)
                 {
-                    if constexpr (LOAD == 0)
-                        s.keys[idx] = idx < valid ? keys_in[tile_base + idx] : 0xffffffffu;
+                    s.keys[idx] = idx < valid ? keys_in[tile_base + idx] : 0xffffffffu;
                     s.vals[idx] = idx < valid ? vals_in[tile_base + idx] : 0u;
                 }
                 __syncthreads();
             }
 
             // ---- early counts: the warp's digit histogram
-            static_assert(!MFIRST || !DEST, "MFIRST is a flavour of the plain digit pass");
             uint32_t key[IPT];
-            uint32_t rank2[IPT / 2]; // two 16-bit ranks per register: warp-local (MFIRST), then tile-sorted slots
             uint32_t* wh = s.warp_hist[warp];
             {
-                if constexpr (LOAD >= 1)
-                {
-                    const uint32_t* src = keys_in + tile_base + my_off;
-                    if (full)
-                    {
+                if (use_tma)
+                    mbarrier_wait(&s.bar_keys, 0);
 #pragma unroll
-                        for (int i = 0; i < IPT; i++)
-                            key[i] = ld_stream_u32(src + i * 32);
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int i = 0; i < IPT; i++)
-                            key[i] = my_off + i * 32 < valid ? ld_stream_u32(src + i * 32) : 0xffffffffu;
-                    }
-                }
-                else
-                {
-                    if (use_tma)
-                        mbarrier_wait(&s.bar_keys, 0);
-#pragma unroll
-                    for (int i = 0; i < IPT; i++)
-                        key[i] = s.keys[my_off + i * 32];
-                }
+                for (int i = 0; i < IPT; i++)
+                    key[i] = s.keys[my_off + i * 32];
                 if constexpr (DEST)
                 {
                     // a handful of destinations: plain atomics would pile up on the same few words, so the lanes
@@ -549,26 +510,6 @@ namespace glu_b200
                         const uint32_t peers = match_low4(d);
                         if ((peers & lt_) == 0)
                             atomicAdd(&wh[d], uint32_t(__popc(peers)));
-                    }
-                }
-                else if constexpr (MFIRST)
-                {
-                    const uint32_t lt_ = lanemask_lt();
-#pragma unroll
-                    for (int i = 0; i < IPT; i++)
-                    {
-                        const uint32_t d = (key[i] >> shift) & mask;
-                        const uint32_t peers = match_digit<MODE>(d);
-                        const int leader = __ffs(int(peers)) - 1;
-                        uint32_t base = 0;
-                        if (int(lane) == leader)
-                            base = atomicAdd(&wh[d], uint32_t(__popc(peers)));
-                        base = __shfl_sync(k_full_mask, base, leader);
-                        const uint32_t r = base + __popc(peers & lt_);
-                        if (i & 1)
-                            rank2[i / 2] |= r << 16;
-                        else
-                            rank2[i / 2] = r;
                     }
                 }
                 else
@@ -640,24 +581,10 @@ namespace glu_b200
             }
             __syncthreads();
 
+            uint32_t rank2[IPT / 2]; // two 16-bit tile-sorted slots per register
             {
                 // ---- rank + scatter keys (in place)
                 const uint32_t lt = lanemask_lt();
-                if constexpr (MFIRST)
-                {
-#pragma unroll
-                    for (int i = 0; i < IPT; i++)
-                    {
-                        const uint32_t local = (i & 1) ? rank2[i / 2] >> 16 : rank2[i / 2] & 0xffffu;
-                        const uint32_t r = wh[(key[i] >> shift) & mask] + local;
-                        s.keys[r] = key[i];
-                        if (i & 1)
-                            rank2[i / 2] = (rank2[i / 2] & 0xffffu) | (r << 16);
-                        else
-                            rank2[i / 2] = (rank2[i / 2] & 0xffff0000u) | r;
-                    }
-                }
-                else
 #pragma unroll
                 for (int i = 0; i < IPT; i++)
                 {
@@ -675,31 +602,12 @@ namespace glu_b200
                         rank2[i / 2] = r;
                 }
                 // ---- values: staging buffer -> registers (the key registers are dead now)
+                if (use_tma)
+                    mbarrier_wait(&s.bar_vals, 0);
                 uint32_t val[IPT];
-                if constexpr (LOAD == 2)
-                {
-                    const uint32_t* src = vals_in + tile_base + my_off;
-                    if (full)
-                    {
 #pragma unroll
-                        for (int i = 0; i < IPT; i++)
-                            val[i] = ld_stream_u32(src + i * 32);
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int i = 0; i < IPT; i++)
-                            val[i] = my_off + i * 32 < valid ? ld_stream_u32(src + i * 32) : 0u;
-                    }
-                }
-                else
-                {
-                    if (use_tma)
-                        mbarrier_wait(&s.bar_vals, 0);
-#pragma unroll
-                    for (int i = 0; i < IPT; i++)
-                        val[i] = s.vals[my_off + i * 32];
-                }
+                for (int i = 0; i < IPT; i++)
+                    val[i] = s.vals[my_off + i * 32];
 
                 // ---- this digit's count in all earlier tiles: one row, written by the chain CTA
                 if (tid < k_radix)
@@ -722,8 +630,7 @@ namespace glu_b200
                     else
                         s.gbase[tid] = digit_offset[tid] + exclusive - s.tile_start[tid];
                 }
-                if constexpr (LOAD <= 1)
-                    __syncthreads(); // all values are in registers (the staging array is reused in place)
+                __syncthreads(); // all values are in registers
 #pragma unroll
                 for (int i = 0; i < IPT; i += 2)
                 {
@@ -797,8 +704,6 @@ namespace glu_b200
             {8, 320, 24}, // 7680, 3 CTAs/SM with 64 registers per thread
         };
         constexpr int k_num_configs = int(sizeof(k_configs) / sizeof(k_configs[0]));
-        constexpr int k_default_load = 0;   // see onesweep_kernel's LOAD
-        constexpr int k_default_mfirst = 0; // see onesweep_kernel's MFIRST
 
         int env_int(const char* name, int fallback)
         {
@@ -852,8 +757,7 @@ namespace glu_b200
             return l;
         }
 
-        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false, int LOAD = 0,
-                 bool MFIRST = false>
+        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false>
         int launch_sweep(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint32_t n, uint32_t shift,
                          uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback, uint32_t* ticket,
                          unsigned tiles, cudaStream_t s, const uint32_t* d_n = nullptr,
@@ -862,7 +766,7 @@ namespace glu_b200
         {
             // per pass: `tiles` count rows followed by `tiles` prefix rows; grid = tiles + the chain CTAs
             uint32_t* prefix = lookback + size_t(tiles) * k_radix;
-            auto kernel = onesweep_kernel<THREADS, IPT, MIN_BLOCKS, MODE, PEER, DEST, LOAD, MFIRST>;
+            auto kernel = onesweep_kernel<THREADS, IPT, MIN_BLOCKS, MODE, PEER, DEST>;
             // TMA bulk copies need 16-byte aligned sources (tiles are multiples of 4 elements)
             const int allow_tma =
                 ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
@@ -910,27 +814,7 @@ namespace glu_b200
                 GLU_SWEEP_CASE(4, 512, 22, 2)
                 GLU_SWEEP_CASE(6, 384, 16, 3)
                 GLU_SWEEP_CASE(7, 320, 18, 4)
-            case 8:
-            {
-                // GLU_SORT_LOAD: 0 = TMA staging of keys and values, 1 = keys straight into registers, 2 = both
-                static const int load = env_int("GLU_SORT_LOAD", k_default_load);
-                static const int mfirst = env_int("GLU_SORT_MFIRST", k_default_mfirst);
-#define GLU_SWEEP_MF(L)                                                                                                \
-    if (MODE == Rank_Ballot && mfirst && load == L)                                                                   \
-        return launch_sweep<320, 24, 3, Rank_Ballot, false, false, L, true>(ki, vi, ko, vo, n, shift, mask, digit_offset,     \
-                                                                             lookback, ticket, tiles, s, d_n);
-                GLU_SWEEP_MF(0)
-                GLU_SWEEP_MF(1)
-                GLU_SWEEP_MF(2)
-#undef GLU_SWEEP_MF
-                if (MODE == Rank_Ballot && load == 1)
-                    return launch_sweep<320, 24, 3, Rank_Ballot, false, false, 1>(ki, vi, ko, vo, n, shift, mask, digit_offset,
-                                                                                  lookback, ticket, tiles, s, d_n);
-                if (MODE == Rank_Ballot && load == 2)
-                    return launch_sweep<320, 24, 3, Rank_Ballot, false, false, 2>(ki, vi, ko, vo, n, shift, mask, digit_offset,
-                                                                                  lookback, ticket, tiles, s, d_n);
-                return launch_sweep<320, 24, 3, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s, d_n);
-            }
+                GLU_SWEEP_CASE(8, 320, 24, 3)
             default: return launch_sweep<256, 8, 4, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s, d_n);
 #undef GLU_SWEEP_CASE
             }
