@@ -123,6 +123,51 @@ TEST_CASE("RadixSort-num-steps", "")
         sort_and_check(keys, num_steps);
 }
 
+// Beyond the reference: key-only, bit-range and descending sorts through RadixSort::sort_ex.
+TEST_CASE("RadixSort-ex-keys-only-bit-range-descending", "")
+{
+    std::mt19937 engine(9);
+    for (size_t n : {3000, 100003, 2500001})
+    {
+        std::vector<uint32_t> keys(n), vals(n);
+        for (uint32_t& k : keys)
+            k = engine();
+        std::iota(vals.begin(), vals.end(), 0u);
+        RadixSort radix_sort;
+        { // keys only, ascending and descending
+            DeviceBuffer key_buffer(keys);
+            radix_sort.sort_ex(key_buffer.handle(), nullptr, n);
+            std::vector<uint32_t> expected = keys;
+            std::sort(expected.begin(), expected.end());
+            CHECK(key_buffer.get_data<uint32_t>() == expected);
+            key_buffer.write_data(keys.data(), n * sizeof(uint32_t));
+            radix_sort.sort_ex(key_buffer.handle(), nullptr, n, 0, 32, true);
+            std::reverse(expected.begin(), expected.end());
+            CHECK(key_buffer.get_data<uint32_t>() == expected);
+        }
+        for (bool descending : {false, true})
+        { // pairs, key bits [6, 19) only
+            const unsigned begin_bit = 6, end_bit = 19;
+            DeviceBuffer key_buffer(keys), val_buffer(vals);
+            radix_sort.sort_ex(key_buffer.handle(), val_buffer.handle(), n, begin_bit, end_bit, descending);
+            const uint32_t mask = (1u << (end_bit - begin_bit)) - 1u;
+            std::vector<std::pair<uint32_t, uint32_t>> pairs(n);
+            for (size_t i = 0; i < n; i++)
+                pairs[i] = {keys[i], vals[i]};
+            std::stable_sort(pairs.begin(), pairs.end(), [=](const auto& a, const auto& b) {
+                const uint32_t fa = (a.first >> begin_bit) & mask, fb = (b.first >> begin_bit) & mask;
+                return descending ? fa > fb : fa < fb;
+            });
+            const std::vector<uint32_t> sorted_keys = key_buffer.get_data<uint32_t>();
+            const std::vector<uint32_t> sorted_vals = val_buffer.get_data<uint32_t>();
+            bool equal = true;
+            for (size_t i = 0; i < n && equal; i++)
+                equal = pairs[i].first == sorted_keys[i] && pairs[i].second == sorted_vals[i];
+            CHECK(equal);
+        }
+    }
+}
+
 TEST_CASE("RadixSort-benchmark", "[.][benchmark]")
 {
     for (size_t k_num_elements : {1024, 16384, 65536, 131072, 524288, 1048576, 2097152, 4194304, 8388608, 16777216,

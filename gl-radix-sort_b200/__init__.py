@@ -51,6 +51,8 @@ ABI = {
     "glu_scan_exclusive": (_int, [_vp, _sz, _sz, _int, _vp, _sz, _vp]),
     "glu_radix_sort_u32kv_tmp_bytes": (_sz, [_sz]),
     "glu_radix_sort_u32kv": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _vp]),
+    "glu_radix_sort_u32_ex_tmp_bytes": (_sz, [_sz, _int]),
+    "glu_radix_sort_u32_ex": (_int, [_vp, _vp, _sz, ctypes.c_uint, ctypes.c_uint, _int, _vp, _sz, _vp]),
     "glu_reduce_into": (_int, [_vp, _sz, _int, _int, _vp, _vp, _sz, _vp]),
     "glu_scan_exclusive_init": (_int, [_vp, _sz, _sz, _int, _vp, _vp, _sz, _vp]),
     "glu_radix_histogram_u32": (_int, [_vp, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _vp]),
@@ -294,6 +296,30 @@ class RadixSort:
         tmp, tmp_bytes = self._scratch.ensure(0, dev)
         st = _current_stream(dev) if stream is None else stream
         check(_lib.glu_radix_sort_u32kv(kptr, vptr, count, num_steps, tmp, tmp_bytes, st), "RadixSort")
+
+    def sort_ex(self, key_buffer, val_buffer, count: int, begin_bit: int = 0, end_bit: int = 32,
+                descending: bool = False, stream: int | None = None) -> None:
+        """glu_radix_sort_u32_ex: `val_buffer=None` sorts keys only; only key bits [begin_bit, end_bit) take part;
+        `descending` puts the largest key first.  Always stable (equal keys keep their input order)."""
+        kptr, kdev = _ptr_and_device(key_buffer)
+        vptr, vdev = _ptr_and_device(val_buffer) if val_buffer is not None else (None, None)
+        if not kptr:
+            raise GluError(1, "Invalid key buffer")
+        if val_buffer is not None and not vptr:
+            raise GluError(1, "Invalid value buffer")
+        if not (0 <= begin_bit <= end_bit <= 32):
+            raise GluError(1, "RadixSort.sort_ex: need 0 <= begin_bit <= end_bit <= 32")
+        if count <= 1 or begin_bit == end_bit:
+            return
+        dev = _device_of(kdev if kdev is not None else vdev)
+        need = int(_lib.glu_radix_sort_u32_ex_tmp_bytes(count, 1 if vptr else 0))
+        if need == 0:
+            raise GluError(6, "RadixSort.sort_ex")
+        tmp, tmp_bytes = self._scratch.ensure(need, dev)
+        self._device = dev
+        st = _current_stream(dev) if stream is None else stream
+        check(_lib.glu_radix_sort_u32_ex(kptr, vptr, count, begin_bit, end_bit, 1 if descending else 0, tmp, tmp_bytes,
+                                         st), "RadixSort.sort_ex")
 
     def sort_device_count(self, key_buffer, val_buffer, count_buffer, max_count: int, num_steps: int = 0,
                           stream: int | None = None) -> None:

@@ -32,30 +32,39 @@ namespace glu_b200
         constexpr uint32_t k_lb_inclusive = 1u << 31; // prefix row: inclusive count over tiles 0..t (bits 0..30)
         constexpr uint32_t k_lb_value_mask = (1u << 30) - 1u;
         constexpr int k_opt_no_lookback = 1, k_opt_ticket = 2; // GLU_SORT_OPTIONS bits
+        // onesweep_kernel FLAVOR bits (glu_radix_sort_u32_ex): no value array; digits complemented (descending order)
+        constexpr int k_flavor_keys_only = 1, k_flavor_descending = 2;
         // 31-bit running digit counts in the prefix rows (bit 31 is the flag), 32-bit element indices
         constexpr size_t k_max_count = (size_t(1) << 31) - 1;
 
         struct PassPlan
         {
             int num_passes;
-            uint32_t key_mask; // bits that take part in the sort (glu/RadixSort.hpp:331 num_steps)
+            uint32_t begin_bit; // first key bit that takes part (0 for glu::RadixSort; glu_radix_sort_u32_ex)
+            uint32_t key_mask;  // (key >> begin_bit) & key_mask = the bits that take part (glu/RadixSort.hpp:331 num_steps)
             uint32_t shift[k_max_passes];
             uint32_t mask[k_max_passes];
         };
 
-        PassPlan make_pass_plan(size_t num_steps)
+        // key bits [begin_bit, begin_bit + bits) take part, least significant digit first
+        PassPlan make_bit_plan(unsigned begin_bit, int bits)
         {
             PassPlan p{};
-            int bits = (num_steps == 0 || num_steps >= 8) ? 32 : int(4 * num_steps);
+            p.begin_bit = begin_bit;
             p.key_mask = bits == 32 ? 0xffffffffu : ((1u << bits) - 1u);
             p.num_passes = (bits + 7) / 8;
             for (int i = 0; i < p.num_passes; i++)
             {
                 int b = bits - 8 * i < 8 ? bits - 8 * i : 8;
-                p.shift[i] = 8u * i;
+                p.shift[i] = begin_bit + 8u * i;
                 p.mask[i] = (1u << b) - 1u;
             }
             return p;
+        }
+
+        PassPlan make_pass_plan(size_t num_steps)
+        {
+            return make_bit_plan(0u, (num_steps == 0 || num_steps >= 8) ? 32 : int(4 * num_steps));
         }
 
         // ------------------------------------------------------------------------------------ histogram
@@ -76,7 +85,7 @@ namespace glu_b200
         __global__ void __launch_bounds__(k_hist_threads, 1)
             histogram_kernel(const uint32_t* __restrict__ keys, uint32_t n, const uint32_t* __restrict__ d_n,
                              uint32_t head, int num_passes, uint32_t pre_shift, uint32_t key_mask, uint32_t* hist,
-                             uint32_t* ticket, int make_offsets)
+                             uint32_t* ticket, int make_offsets, int descending)
         {
             // d_n: the count lives in device memory (written by an earlier kernel of the stream, *_dyn entry points)
             if (d_n)
@@ -152,7 +161,8 @@ namespace glu_b200
             if (!make_offsets) // glu_radix_histogram_u32: raw counts
                 return;
 
-            // last CTA: counts -> exclusive offsets, one digit place at a time
+            // last CTA: counts -> exclusive offsets, one digit place at a time.  descending: the passes partition by
+            // the COMPLEMENTED digit (mask ^ digit), so entry t is the number of keys whose complemented digit is < t
             __threadfence();
             __syncthreads();
             if (threadIdx.x == 0)
@@ -167,7 +177,8 @@ namespace glu_b200
                 uint32_t c = 0, inc = 0;
                 if (threadIdx.x < k_radix)
                 {
-                    c = __ldcg(&hist[p * k_radix + threadIdx.x]);
+                    const uint32_t flip = descending ? ((key_mask >> (8 * p)) & 0xffu) : 0u;
+                    c = __ldcg(&hist[p * k_radix + (threadIdx.x ^ flip)]); // all reads precede the barrier, all writes follow it
                     inc = c;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1)
@@ -251,12 +262,12 @@ namespace glu_b200
             uint8_t lut[k_radix];   // DEST: key digit -> destination id (the "digit" the pass partitions by)
         };
 
-        template<int RANK_THREADS, int IPT, bool PEER = false> struct SweepSmem
+        template<int RANK_THREADS, int IPT, bool PEER = false, bool HAS_VALS = true> struct SweepSmem
         {
             static constexpr int WARPS = RANK_THREADS / 32; // ranking warps
             static constexpr int TILE = RANK_THREADS * IPT;
             alignas(128) uint32_t keys[TILE];   // TMA destination (input order), then tile-sorted keys
-            alignas(128) uint32_t vals[TILE];   // TMA destination (input order), then tile-sorted values
+            alignas(128) uint32_t vals[HAS_VALS ? TILE : 32]; // TMA destination (input order), then tile-sorted values
             alignas(16) uint32_t warp_hist[WARPS][k_radix]; // per-warp digit counts, then running slot offsets
             uint32_t gbase[k_radix];            // global index of tile-sorted slot 0, per digit
             uint32_t tile_start[k_radix];       // first tile-sorted slot of each digit
@@ -374,7 +385,11 @@ namespace glu_b200
         // PEER: digit run d goes to key_dst[d] / val_dst[d] instead of one output array.  DEST (with PEER): the pass
         // partitions by dest_lut[digit] (< 16 destinations) instead of by the digit itself, so a tile leaves as a
         // handful of long runs — what remote (NVLink) stores want.
-        template<int RANK_THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false>
+        //
+        // FLAVOR (glu_radix_sort_u32_ex): k_flavor_keys_only — there is no value array (vals_in / vals_out are not
+        // touched); k_flavor_descending — the pass partitions by the complemented digit, which sorts descending and
+        // keeps equal keys in input order.  FLAVOR 0 compiles to exactly the code it was before the flavours existed.
+        template<int RANK_THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false, int FLAVOR = 0>
         __global__ void __launch_bounds__(RANK_THREADS, MIN_BLOCKS)
             onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                             uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
@@ -387,7 +402,11 @@ namespace glu_b200
             static_assert(!DEST || PEER, "DEST is a flavour of PEER");
             static_assert(RANK_THREADS >= k_radix && RANK_THREADS % 32 == 0, "one ranking thread per digit");
             static_assert(IPT % 2 == 0, "ranks are packed two per register");
-            using Smem = SweepSmem<RANK_THREADS, IPT, PEER>;
+            static_assert(FLAVOR == 0 || !PEER, "the flavours belong to the single-GPU sort");
+            constexpr bool KEYS_ONLY = (FLAVOR & k_flavor_keys_only) != 0;
+            constexpr uint32_t FLIP = (FLAVOR & k_flavor_descending) ? 0xffffffffu : 0u;
+            constexpr uint32_t PAD_KEY = ~FLIP; // ranks after every real key of its tile
+            using Smem = SweepSmem<RANK_THREADS, IPT, PEER, !KEYS_ONLY>;
             constexpr int THREADS = RANK_THREADS;
             constexpr int WARPS = Smem::WARPS;
             constexpr int TILE = Smem::TILE;
@@ -423,15 +442,19 @@ namespace glu_b200
                     const uint64_t policy = l2_policy_evict_first();
                     mbarrier_arrive_expect_tx(&s.bar_keys, TILE * 4);
                     tma_load_1d(s.keys, keys_in + tb, TILE * 4, &s.bar_keys, policy);
-                    mbarrier_arrive_expect_tx(&s.bar_vals, TILE * 4);
-                    tma_load_1d(s.vals, vals_in + tb, TILE * 4, &s.bar_vals, policy);
+                    if constexpr (!KEYS_ONLY)
+                    {
+                        mbarrier_arrive_expect_tx(&s.bar_vals, TILE * 4);
+                        tma_load_1d(s.vals, vals_in + tb, TILE * 4, &s.bar_vals, policy);
+                    }
                     // L2 prefetch of the tile that will occupy this CTA slot `options >> 8` tiles from now: its bulk
                     // copies then start from L2 instead of paying the loaded-DRAM latency at CTA start
                     const uint64_t ahead = uint64_t(t - chain_ctas) + uint32_t(options >> 8);
                     if ((options >> 8) != 0 && (ahead + 1) * uint64_t(TILE) <= uint64_t(n))
                     {
                         tma_prefetch_l2_1d(keys_in + ahead * TILE, TILE * 4);
-                        tma_prefetch_l2_1d(vals_in + ahead * TILE, TILE * 4);
+                        if constexpr (!KEYS_ONLY)
+                            tma_prefetch_l2_1d(vals_in + ahead * TILE, TILE * 4);
                     }
                 }
             }
@@ -448,7 +471,7 @@ namespace glu_b200
                 if constexpr (DEST)
                     return s.dst.lut[(k >> shift) & mask];
                 else
-                    return (k >> shift) & mask;
+                    return ((k ^ FLIP) >> shift) & mask;
             };
             if (s.tile < chain_ctas)
             {
@@ -483,8 +506,9 @@ namespace glu_b200
                 // of the tile and are never written back.
                 for (uint32_t idx = tid; idx < uint32_t(TILE); idx += THREADS)
                 {
-                    s.keys[idx] = idx < valid ? keys_in[tile_base + idx] : 0xffffffffu;
-                    s.vals[idx] = idx < valid ? vals_in[tile_base + idx] : 0u;
+                    s.keys[idx] = idx < valid ? keys_in[tile_base + idx] : PAD_KEY;
+                    if constexpr (!KEYS_ONLY)
+                        s.vals[idx] = idx < valid ? vals_in[tile_base + idx] : 0u;
                 }
                 __syncthreads();
             }
@@ -516,13 +540,13 @@ namespace glu_b200
                 {
                     // A digit shared by the whole warp would be a 32-way same-address atomic.  Probe the first
                     // key: a warp that looks skewed checks every key and counts warp-uniform digits once.
-                    const uint32_t d_first = (key[0] >> shift) & mask;
+                    const uint32_t d_first = digit_of(key[0]);
                     if (__all_sync(k_full_mask, d_first == __shfl_sync(k_full_mask, d_first, 0)))
                     {
 #pragma unroll
                         for (int i = 0; i < IPT; i++)
                         {
-                            const uint32_t d = (key[i] >> shift) & mask;
+                            const uint32_t d = digit_of(key[i]);
                             if (__all_sync(k_full_mask, d == __shfl_sync(k_full_mask, d, 0)))
                             {
                                 if (lane == 0)
@@ -536,7 +560,7 @@ namespace glu_b200
                     {
 #pragma unroll
                         for (int i = 0; i < IPT; i++)
-                            atomicAdd(&wh[(key[i] >> shift) & mask], 1u);
+                            atomicAdd(&wh[digit_of(key[i])], 1u);
                     }
                 }
             }
@@ -549,8 +573,8 @@ namespace glu_b200
 #pragma unroll
                 for (int w = 0; w < WARPS; w++)
                     total += s.warp_hist[w][tid];
-                // padding slots all carry the digit of key 0xffffffff
-                const uint32_t count_valid = total - (tid == digit_of(0xffffffffu) ? uint32_t(TILE) - valid : 0u);
+                // padding slots all carry the digit of the padding key
+                const uint32_t count_valid = total - (tid == digit_of(PAD_KEY) ? uint32_t(TILE) - valid : 0u);
                 st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid], k_lb_local | count_valid);
                 inc = total;
 #pragma unroll
@@ -602,12 +626,15 @@ namespace glu_b200
                         rank2[i / 2] = r;
                 }
                 // ---- values: staging buffer -> registers (the key registers are dead now)
-                if (use_tma)
-                    mbarrier_wait(&s.bar_vals, 0);
-                uint32_t val[IPT];
+                uint32_t val[KEYS_ONLY ? 2 : IPT];
+                if constexpr (!KEYS_ONLY)
+                {
+                    if (use_tma)
+                        mbarrier_wait(&s.bar_vals, 0);
 #pragma unroll
-                for (int i = 0; i < IPT; i++)
-                    val[i] = s.vals[my_off + i * 32];
+                    for (int i = 0; i < IPT; i++)
+                        val[i] = s.vals[my_off + i * 32];
+                }
 
                 // ---- this digit's count in all earlier tiles: one row, written by the chain CTA
                 if (tid < k_radix)
@@ -630,12 +657,15 @@ namespace glu_b200
                     else
                         s.gbase[tid] = digit_offset[tid] + exclusive - s.tile_start[tid];
                 }
-                __syncthreads(); // all values are in registers
-#pragma unroll
-                for (int i = 0; i < IPT; i += 2)
+                if constexpr (!KEYS_ONLY)
                 {
-                    s.vals[rank2[i / 2] & 0xffffu] = val[i];
-                    s.vals[rank2[i / 2] >> 16] = val[i + 1];
+                    __syncthreads(); // all values are in registers
+#pragma unroll
+                    for (int i = 0; i < IPT; i += 2)
+                    {
+                        s.vals[rank2[i / 2] & 0xffffu] = val[i];
+                        s.vals[rank2[i / 2] >> 16] = val[i + 1];
+                    }
                 }
             }
             __syncthreads(); // tile-sorted keys and values, gbase
@@ -648,16 +678,19 @@ namespace glu_b200
                 {
                     const uint32_t p = tid + k * THREADS;
                     const uint32_t kk = s.keys[p];
-                    const uint32_t vv = s.vals[p];
                     if constexpr (PEER)
                     {
+                        const uint32_t vv = s.vals[p];
                         const uint32_t d = digit_of(kk);
                         s.dst.key[d][p] = kk;
                         s.dst.val[d][p] = vv;
                     }
+                    else if constexpr (KEYS_ONLY)
+                        keys_out[s.gbase[digit_of(kk)] + p] = kk;
                     else
                     {
-                        const uint32_t dst = s.gbase[(kk >> shift) & mask] + p;
+                        const uint32_t vv = s.vals[p];
+                        const uint32_t dst = s.gbase[digit_of(kk)] + p;
                         keys_out[dst] = kk;
                         vals_out[dst] = vv;
                     }
@@ -676,9 +709,10 @@ namespace glu_b200
                     }
                     else
                     {
-                        const uint32_t dst = s.gbase[(kk >> shift) & mask] + p;
+                        const uint32_t dst = s.gbase[digit_of(kk)] + p;
                         keys_out[dst] = kk;
-                        vals_out[dst] = s.vals[p];
+                        if constexpr (!KEYS_ONLY)
+                            vals_out[dst] = s.vals[p];
                     }
                 }
             }
@@ -711,10 +745,11 @@ namespace glu_b200
             return v && *v ? std::atoi(v) : fallback;
         }
 
-        const SweepConfig& select_config(size_t count)
+        // allow_forced = false: the flavoured kernels (glu_radix_sort_u32_ex) exist for the default shapes only
+        const SweepConfig& select_config(size_t count, bool allow_forced = true)
         {
             static const int forced = env_int("GLU_SORT_CONFIG", -1); // tuning sweeps only
-            if (forced >= 0 && forced < k_num_configs)
+            if (allow_forced && forced >= 0 && forced < k_num_configs)
                 return k_configs[forced];
             if (count <= (size_t(1) << 18))
                 return k_configs[5];
@@ -742,9 +777,9 @@ namespace glu_b200
             size_t off_hist, off_lookback, off_keys, off_vals, total;
         };
 
-        TmpLayout make_layout(size_t count)
+        TmpLayout make_layout(size_t count, bool with_values = true, bool allow_forced = true)
         {
-            const SweepConfig& c = select_config(count);
+            const SweepConfig& c = select_config(count, allow_forced);
             TmpLayout l;
             const size_t tile = size_t(c.threads) * c.ipt;
             l.tiles = (count + tile - 1) / tile;
@@ -753,11 +788,11 @@ namespace glu_b200
             l.control_bytes = align_up(l.off_lookback + 2 * k_max_passes * l.tiles * k_radix * sizeof(uint32_t), k_tmp_align);
             l.off_keys = l.control_bytes;
             l.off_vals = l.off_keys + align_up(count * sizeof(uint32_t), k_tmp_align);
-            l.total = l.off_vals + align_up(count * sizeof(uint32_t), k_tmp_align);
+            l.total = l.off_vals + (with_values ? align_up(count * sizeof(uint32_t), k_tmp_align) : 0);
             return l;
         }
 
-        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false>
+        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false, int FLAVOR = 0>
         int launch_sweep(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint32_t n, uint32_t shift,
                          uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback, uint32_t* ticket,
                          unsigned tiles, cudaStream_t s, const uint32_t* d_n = nullptr,
@@ -766,11 +801,11 @@ namespace glu_b200
         {
             // per pass: `tiles` count rows followed by `tiles` prefix rows; grid = tiles + the chain CTAs
             uint32_t* prefix = lookback + size_t(tiles) * k_radix;
-            auto kernel = onesweep_kernel<THREADS, IPT, MIN_BLOCKS, MODE, PEER, DEST>;
-            // TMA bulk copies need 16-byte aligned sources (tiles are multiples of 4 elements)
+            auto kernel = onesweep_kernel<THREADS, IPT, MIN_BLOCKS, MODE, PEER, DEST, FLAVOR>;
+            // TMA bulk copies need 16-byte aligned sources (tiles are multiples of 4 elements); vi is null without values
             const int allow_tma =
                 ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
-            constexpr size_t smem = sizeof(SweepSmem<THREADS, IPT, PEER>);
+            constexpr size_t smem = sizeof(SweepSmem<THREADS, IPT, PEER, (FLAVOR & k_flavor_keys_only) == 0>);
             static const int chain_rows = env_int("GLU_SORT_CHAIN_ROWS", 8);
             // bit 0: skip the look-back (timing experiments, wrong results); bit 1: tile ids from an atomic ticket
             // bits 8..: L2 prefetch distance in tiles (GLU_SORT_PREFETCH; 0 = off).  Default: one tile per SM ahead —
@@ -819,6 +854,27 @@ namespace glu_b200
 #undef GLU_SWEEP_CASE
             }
         }
+
+        // glu_radix_sort_u32_ex: the three default tile shapes (select_config without the tuning override), ballot ranking
+        template<int FLAVOR>
+        int dispatch_sweep_flavor(const SweepConfig& c, const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo,
+                                  uint32_t n, uint32_t shift, uint32_t mask, const uint32_t* digit_offset,
+                                  uint32_t* lookback, uint32_t* ticket, unsigned tiles, cudaStream_t s)
+        {
+            switch (c.id)
+            {
+            case 8:
+                return launch_sweep<320, 24, 3, Rank_Ballot, false, false, FLAVOR>(ki, vi, ko, vo, n, shift, mask, digit_offset,
+                                                                                   lookback, ticket, tiles, s);
+            case 2:
+                return launch_sweep<256, 16, 4, Rank_Ballot, false, false, FLAVOR>(ki, vi, ko, vo, n, shift, mask, digit_offset,
+                                                                                   lookback, ticket, tiles, s);
+            case 5:
+                return launch_sweep<256, 8, 4, Rank_Ballot, false, false, FLAVOR>(ki, vi, ko, vo, n, shift, mask, digit_offset,
+                                                                                  lookback, ticket, tiles, s);
+            default: return GLU_ERROR_INVALID_ARGUMENT;
+            }
+        }
     } // namespace
 } // namespace glu_b200
 
@@ -832,7 +888,7 @@ namespace
     // n: the count, or its upper bound when d_n (device-resident count) is given
     int launch_histogram(const uint32_t* d_keys, uint32_t n, int num_passes, uint32_t pre_shift, uint32_t key_mask,
                          uint32_t* hist, uint32_t* ticket, int make_offsets, int sms, cudaStream_t s,
-                         const uint32_t* d_n = nullptr)
+                         const uint32_t* d_n = nullptr, int descending = 0)
     {
         const uintptr_t addr = reinterpret_cast<uintptr_t>(d_keys);
         const uint32_t head = uint32_t(((16 - (addr & 15)) & 15) / sizeof(uint32_t));
@@ -855,7 +911,7 @@ namespace
         }
         ScopedKernelProfile prof(GLU_KERNEL_SORT_HISTOGRAM, s);
         histogram_kernel<<<unsigned(grid), k_hist_threads, smem, s>>>(d_keys, n, d_n, head, num_passes, pre_shift,
-                                                                       key_mask, hist, ticket, make_offsets);
+                                                                       key_mask, hist, ticket, make_offsets, descending);
         GLU_LAUNCH_CHECK();
         return GLU_SUCCESS;
     }
@@ -874,8 +930,9 @@ namespace
 {
     // count: the number of pairs, or (d_n != nullptr) the bound the grids and the scratch are sized for while the
     // actual number is read from *d_n by the kernels
-    int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* d_n, size_t num_steps, void* d_tmp,
-                  size_t tmp_bytes, glu_stream_t stream);
+    // flavor: k_flavor_* bits (non-zero: glu_radix_sort_u32_ex, d_vals null when keys only)
+    int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* d_n, const PassPlan& plan, int flavor,
+                  void* d_tmp, size_t tmp_bytes, glu_stream_t stream);
 }
 
 extern "C" int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t count, size_t num_steps, void* d_tmp,
@@ -885,7 +942,7 @@ extern "C" int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t c
         return GLU_ERROR_INVALID_ARGUMENT;
     if (count <= 1) // glu/RadixSort.hpp:278-279
         return GLU_SUCCESS;
-    return sort_impl(d_keys, d_vals, count, nullptr, num_steps, d_tmp, tmp_bytes, stream);
+    return sort_impl(d_keys, d_vals, count, nullptr, make_pass_plan(num_steps), 0, d_tmp, tmp_bytes, stream);
 }
 
 extern "C" int glu_radix_sort_u32kv_dyn(uint32_t* d_keys, uint32_t* d_vals, const uint32_t* d_count, size_t max_count,
@@ -897,19 +954,44 @@ extern "C" int glu_radix_sort_u32kv_dyn(uint32_t* d_keys, uint32_t* d_vals, cons
         return GLU_ERROR_MISALIGNED;
     if (max_count <= 1)
         return GLU_SUCCESS;
-    return sort_impl(d_keys, d_vals, max_count, d_count, num_steps, d_tmp, tmp_bytes, stream);
+    return sort_impl(d_keys, d_vals, max_count, d_count, make_pass_plan(num_steps), 0, d_tmp, tmp_bytes, stream);
+}
+
+extern "C" size_t glu_radix_sort_u32_ex_tmp_bytes(size_t count, int with_values)
+{
+    if (count > k_max_count)
+        return 0;
+    if (count <= 1)
+        return k_tmp_align;
+    return make_layout(count, with_values != 0, false).total;
+}
+
+extern "C" int glu_radix_sort_u32_ex(uint32_t* d_keys, uint32_t* d_vals, size_t count, unsigned begin_bit,
+                                     unsigned end_bit, int descending, void* d_tmp, size_t tmp_bytes, glu_stream_t stream)
+{
+    if (!d_keys || begin_bit > end_bit || end_bit > 32)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    if (count <= 1 || begin_bit == end_bit) // no key bit takes part: every pair is "equal", stable = unchanged
+        return GLU_SUCCESS;
+    const int flavor = (d_vals ? 0 : k_flavor_keys_only) | (descending ? k_flavor_descending : 0);
+    return sort_impl(d_keys, d_vals, count, nullptr, make_bit_plan(begin_bit, int(end_bit - begin_bit)), flavor | 0x100,
+                     d_tmp, tmp_bytes, stream);
 }
 
 namespace
 {
-int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* d_n, size_t num_steps, void* d_tmp,
-              size_t tmp_bytes, glu_stream_t stream)
+int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* d_n, const PassPlan& plan, int flavor_arg,
+              void* d_tmp, size_t tmp_bytes, glu_stream_t stream)
 {
+    // bit 8 of flavor_arg: called through glu_radix_sort_u32_ex (default tile shapes, ballot ranking, its own layout)
+    const bool ex = (flavor_arg & 0x100) != 0;
+    const int flavor = flavor_arg & 0xff;
+    const bool with_values = (flavor & k_flavor_keys_only) == 0;
     if (count > k_max_count)
         return GLU_ERROR_COUNT_TOO_LARGE;
     if ((reinterpret_cast<uintptr_t>(d_keys) | reinterpret_cast<uintptr_t>(d_vals)) % sizeof(uint32_t) != 0)
         return GLU_ERROR_MISALIGNED;
-    const TmpLayout l = make_layout(count);
+    const TmpLayout l = make_layout(count, with_values, !ex);
     if (!d_tmp || tmp_bytes < l.total)
         return GLU_ERROR_TMP_TOO_SMALL;
     if (reinterpret_cast<uintptr_t>(d_tmp) % k_tmp_align != 0)
@@ -924,20 +1006,20 @@ int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* 
     uint32_t* hist = reinterpret_cast<uint32_t*>(tmp + l.off_hist);
     uint32_t* lookback = reinterpret_cast<uint32_t*>(tmp + l.off_lookback);
     uint32_t* alt_keys = reinterpret_cast<uint32_t*>(tmp + l.off_keys);
-    uint32_t* alt_vals = reinterpret_cast<uint32_t*>(tmp + l.off_vals);
-    const PassPlan plan = make_pass_plan(num_steps);
+    uint32_t* alt_vals = with_values ? reinterpret_cast<uint32_t*>(tmp + l.off_vals) : nullptr;
     const uint32_t n = uint32_t(count);
 
     const size_t used_control = l.off_lookback + 2 * size_t(plan.num_passes) * l.tiles * k_radix * sizeof(uint32_t);
     GLU_CUDA_TRY(cudaMemsetAsync(tmp, 0, used_control, s));
 
     {
-        const int rc = launch_histogram(d_keys, n, plan.num_passes, 0u, plan.key_mask, hist, tickets + 4, 1, sms, s, d_n);
+        const int rc = launch_histogram(d_keys, n, plan.num_passes, plan.begin_bit, plan.key_mask, hist, tickets + 4, 1, sms,
+                                        s, d_n, (flavor & k_flavor_descending) ? 1 : 0);
         if (rc != GLU_SUCCESS)
             return rc;
     }
 
-    const SweepConfig& cfg = select_config(count);
+    const SweepConfig& cfg = select_config(count, !ex);
     const int mode = rank_mode();
     uint32_t* kbuf[2] = {d_keys, alt_keys};
     uint32_t* vbuf[2] = {d_vals, alt_vals};
@@ -948,6 +1030,26 @@ int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* 
         uint32_t* ko = kbuf[(p + 1) & 1];
         uint32_t* vo = vbuf[(p + 1) & 1];
         uint32_t* lb = lookback + 2 * size_t(p) * l.tiles * k_radix;
+        if (ex)
+        {
+            int rc = GLU_ERROR_INVALID_ARGUMENT;
+            switch (flavor)
+            {
+#define GLU_FLAVOR_CASE(F)                                                                                             \
+    case F:                                                                                                            \
+        rc = dispatch_sweep_flavor<F>(cfg, ki, vi, ko, vo, n, plan.shift[p], plan.mask[p], hist + p * k_radix, lb,     \
+                                      tickets + p, unsigned(l.tiles), s);                                              \
+        break;
+                GLU_FLAVOR_CASE(0)
+                GLU_FLAVOR_CASE(1)
+                GLU_FLAVOR_CASE(2)
+                GLU_FLAVOR_CASE(3)
+#undef GLU_FLAVOR_CASE
+            }
+            if (rc != GLU_SUCCESS)
+                return rc;
+            continue;
+        }
         int rc = mode == Rank_Ballot
                      ? dispatch_sweep<Rank_Ballot>(cfg, ki, vi, ko, vo, n, plan.shift[p], plan.mask[p],
                                                    hist + p * k_radix, lb, tickets + p, unsigned(l.tiles), s, d_n)
@@ -961,7 +1063,8 @@ int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* 
         // an odd number of passes leaves the result in the scratch: bring it home (the reference would
         // leave it there, glu/RadixSort.hpp:315-329 — documented deviation)
         GLU_CUDA_TRY(cudaMemcpyAsync(d_keys, alt_keys, count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
-        GLU_CUDA_TRY(cudaMemcpyAsync(d_vals, alt_vals, count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        if (with_values)
+            GLU_CUDA_TRY(cudaMemcpyAsync(d_vals, alt_vals, count * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
     }
     return GLU_SUCCESS;
 }

@@ -52,6 +52,25 @@ namespace glu
             GLU_CHECK_STATUS(glu_radix_sort_u32kv(static_cast<uint32_t*>(key_buffer), static_cast<uint32_t*>(val_buffer),
                                                   count, num_steps, m_tmp.handle(), m_tmp.size(), m_stream));
         }
+
+        /// Beyond the reference (README.md:88-89 lists the mandatory value buffer as a limitation):
+        /// val_buffer may be null (key-only sort), only key bits [begin_bit, end_bit) take part, descending puts the
+        /// largest key first.  Always stable.  glu_radix_sort_u32_ex.
+        void sort_ex(DevicePtr key_buffer, DevicePtr val_buffer, size_t count, unsigned begin_bit = 0, unsigned end_bit = 32,
+                     bool descending = false)
+        {
+            GLU_CHECK_ARGUMENT(key_buffer, "Invalid key buffer");
+            GLU_CHECK_ARGUMENT(begin_bit <= end_bit && end_bit <= 32, "RadixSort: need begin_bit <= end_bit <= 32");
+            if (count <= 1 || begin_bit == end_bit)
+                return;
+            const size_t need = glu_radix_sort_u32_ex_tmp_bytes(count, val_buffer ? 1 : 0);
+            GLU_CHECK_ARGUMENT(need != 0, "RadixSort: count %zu is too large", count);
+            if (m_tmp.size() < need)
+                m_tmp.resize(need, false);
+            GLU_CHECK_STATUS(glu_radix_sort_u32_ex(static_cast<uint32_t*>(key_buffer), static_cast<uint32_t*>(val_buffer),
+                                                   count, begin_bit, end_bit, descending ? 1 : 0, m_tmp.handle(),
+                                                   m_tmp.size(), m_stream));
+        }
     };
 } // namespace glu
 

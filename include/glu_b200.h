@@ -140,6 +140,20 @@ GLU_API size_t glu_radix_sort_u32kv_tmp_bytes(size_t count);
 GLU_API int glu_radix_sort_u32kv(uint32_t* d_keys, uint32_t* d_vals, size_t count, size_t num_steps, void* d_tmp,
                                  size_t tmp_bytes, glu_stream_t stream);
 
+/* The same stable LSD sort with the knobs the reference's README lists as limitations (README.md:88-89: "the value
+ * buffer is mandatory") and CUB-style callers expect — SURVEY.md §8(f) row 3.  Same kernels, compile-time flavours:
+ *  - d_vals == NULL: key-only sort (no value array is read, written or allocated: 36 B of HBM traffic per key
+ *    instead of 68 B per pair);
+ *  - only key bits [begin_bit, end_bit) take part (0 <= begin_bit <= end_bit <= 32; pairs whose keys agree in those
+ *    bits keep their input order); ceil((end_bit - begin_bit) / 8) passes.  glu_radix_sort_u32kv's num_steps is
+ *    begin_bit = 0, end_bit = 4 * num_steps;  begin_bit == end_bit is a no-op;
+ *  - descending != 0: largest key first, equal keys still in input order (std::stable_sort with greater<>) — the
+ *    passes partition by the complemented digit.
+ * d_tmp is sized by glu_radix_sort_u32_ex_tmp_bytes(count, with_values) (with_values = 0 for d_vals == NULL). */
+GLU_API size_t glu_radix_sort_u32_ex_tmp_bytes(size_t count, int with_values);
+GLU_API int glu_radix_sort_u32_ex(uint32_t* d_keys, uint32_t* d_vals, size_t count, unsigned begin_bit, unsigned end_bit,
+                                  int descending, void* d_tmp, size_t tmp_bytes, glu_stream_t stream);
+
 /* ------------------------------------------------------------------ building blocks of the multi-GPU path
  * Not in the reference (it is single-GPU); these are what gl-radix-sort_b200/distributed.py composes with
  * NCCL / NVLink peer memory (DESIGN.md "Multi-GPU").  Same conventions as above. */

@@ -71,6 +71,7 @@ def lib() -> ctypes.CDLL:
         L.glu_oracle_exclusive_scan_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, sz, sz]
         L.glu_oracle_exclusive_scan_f64.argtypes = [ctypes.c_void_p, ctypes.c_void_p, sz, sz]
         L.glu_oracle_stable_sort_pairs.argtypes = [u32p, u32p, sz, sz, ctypes.c_int]
+        L.glu_oracle_stable_sort_ex.argtypes = [u32p, u32p, sz, ctypes.c_uint, ctypes.c_uint, ctypes.c_int]
         L.glu_oracle_time_stable_sort_pairs.argtypes = [u32p, u32p, sz, ctypes.c_int]
         L.glu_oracle_time_stable_sort_pairs.restype = ctypes.c_double
         L.glu_oracle_lsd_sort_pairs.argtypes = [u32p, u32p, sz, sz]
@@ -161,6 +162,16 @@ def stable_sort_pairs(keys: np.ndarray, vals: np.ndarray, num_steps: int = 0, th
     k = np.array(keys, dtype=np.uint32, copy=True)
     v = np.array(vals, dtype=np.uint32, copy=True)
     lib().glu_oracle_stable_sort_pairs(_u32p(k), _u32p(v), k.size, num_steps, threads)
+    return k, v
+
+
+def stable_sort_ex(keys: np.ndarray, vals: np.ndarray | None, begin_bit: int = 0, end_bit: int = 32,
+                   descending: bool = False):
+    """std::stable_sort comparing key bits [begin_bit, end_bit) only, ascending or descending; vals may be None."""
+    k = np.array(keys, dtype=np.uint32, copy=True)
+    v = None if vals is None else np.array(vals, dtype=np.uint32, copy=True)
+    lib().glu_oracle_stable_sort_ex(_u32p(k), None if v is None else _u32p(v), k.size, begin_bit, end_bit,
+                                    1 if descending else 0)
     return k, v
 
 

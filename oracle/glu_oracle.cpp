@@ -440,6 +440,33 @@ extern "C"
         }
     }
 
+    // Oracle of glu_radix_sort_u32_ex (beyond the reference; PARITY UNPINNED by the reference,
+    // which has neither key-only, bit-range nor descending sorts): std::stable_sort of the pairs comparing only key
+    // bits [begin_bit, end_bit), with std::less (ascending) or std::greater (descending) on those bits.  vals may be
+    // null (keys only).
+    void glu_oracle_stable_sort_ex(uint32_t* keys, uint32_t* vals, size_t n, unsigned begin_bit, unsigned end_bit,
+                                   int descending)
+    {
+        const unsigned bits = end_bit - begin_bit;
+        const uint32_t mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);
+        std::vector<std::pair<uint32_t, uint32_t>> pairs(n);
+        for (size_t i = 0; i < n; i++)
+            pairs[i] = {keys[i], vals ? vals[i] : 0u};
+        auto field = [=](uint32_t k) { return begin_bit >= 32 ? 0u : ((k >> begin_bit) & mask); };
+        if (descending)
+            std::stable_sort(pairs.begin(), pairs.end(),
+                             [=](const auto& a, const auto& b) { return field(a.first) > field(b.first); });
+        else
+            std::stable_sort(pairs.begin(), pairs.end(),
+                             [=](const auto& a, const auto& b) { return field(a.first) < field(b.first); });
+        for (size_t i = 0; i < n; i++)
+        {
+            keys[i] = pairs[i].first;
+            if (vals)
+                vals[i] = pairs[i].second;
+        }
+    }
+
     // Same contract as above with the pair array already built (what bench.py times: the sort only).
     // Returns seconds spent inside stable_sort.
     double glu_oracle_time_stable_sort_pairs(const uint32_t* keys, const uint32_t* vals, size_t n, int threads)

@@ -73,6 +73,15 @@ def test_argument_errors_are_status_codes_not_exits(glu):
     assert L.glu_radix_sort_u32kv(fake, fake, 0, 0, None, 0, None) == 0
     assert L.glu_radix_sort_u32kv(fake, fake, 8, 0, None, 0, None) == 4
     assert L.glu_radix_sort_u32kv(fake, fake, 1 << 31, 0, fake, 1 << 40, None) == 6
+    # glu_radix_sort_u32_ex: values are optional, the bit range must be ordered and inside the key
+    assert L.glu_radix_sort_u32_ex(None, fake, 8, 0, 32, 0, fake, 1 << 20, None) == 1
+    assert L.glu_radix_sort_u32_ex(fake, fake, 8, 9, 8, 0, fake, 1 << 20, None) == 1
+    assert L.glu_radix_sort_u32_ex(fake, fake, 8, 0, 33, 0, fake, 1 << 20, None) == 1
+    assert L.glu_radix_sort_u32_ex(fake, None, 1, 0, 32, 0, None, 0, None) == 0   # count <= 1
+    assert L.glu_radix_sort_u32_ex(fake, None, 8, 7, 7, 1, None, 0, None) == 0    # empty bit range: nothing to do
+    assert L.glu_radix_sort_u32_ex(fake, None, 8, 0, 32, 0, None, 0, None) == 4
+    assert L.glu_radix_sort_u32_ex(fake, None, 1 << 31, 0, 32, 0, fake, 1 << 40, None) == 6
+    assert L.glu_radix_sort_u32_ex(ctypes.c_void_p(0x1002), None, 8, 0, 32, 0, fake, 1 << 20, None) == 5
 
 
 def test_tmp_size_queries(glu):
@@ -85,6 +94,10 @@ def test_tmp_size_queries(glu):
     need = L.glu_radix_sort_u32kv_tmp_bytes(n)
     assert 2 * 4 * n <= need <= 2 * 4 * n + (8 << 20)  # two scratch arrays + O(tiles) control words
     assert L.glu_radix_sort_u32kv_tmp_bytes(1 << 31) == 0
+    # key-only sorts need one scratch array, not two
+    kv, ko = L.glu_radix_sort_u32_ex_tmp_bytes(n, 1), L.glu_radix_sort_u32_ex_tmp_bytes(n, 0)
+    assert 2 * 4 * n <= kv <= 2 * 4 * n + (8 << 20) and 4 * n <= ko <= 4 * n + (8 << 20)
+    assert L.glu_radix_sort_u32_ex_tmp_bytes(1 << 31, 0) == 0
 
 
 def test_python_mirror_validates_like_the_reference(glu):
@@ -103,6 +116,11 @@ def test_python_mirror_validates_like_the_reference(glu):
     with pytest.raises(glu.GluError):
         s(0, 0x1000, 10)
     s(0x1000, 0x1000, 1)  # no-op, never touches the device
+    with pytest.raises(glu.GluError):
+        s.sort_ex(0, None, 10)
+    with pytest.raises(glu.GluError):
+        s.sort_ex(0x1000, None, 10, 8, 4)
+    s.sort_ex(0x1000, None, 10, 5, 5)  # empty bit range: no-op
 
 
 def test_no_product_import_of_oracle(glu):
