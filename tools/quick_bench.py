@@ -86,6 +86,27 @@ if "sort" in args.what:
         assert bool((k64[1:] >= k64[:-1]).all()), "not sorted"
         del k64
 
+if "ex" in args.what.split(","):
+    # glu_radix_sort_u32_ex flavours (uniform keys): key-only (36 B/key), descending pairs, low 24 bits only
+    keys0 = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int32, device=dev, generator=g)
+    vals0 = torch.arange(n, dtype=torch.int32, device=dev)
+    keys, vals = keys0.clone(), vals0.clone()
+    sorter = glu.RadixSort()
+
+    def prep_ex():
+        keys.copy_(keys0)
+        vals.copy_(vals0)
+
+    for name, fn, bytes_per in [
+            ("keys only", lambda: sorter.sort_ex(keys, None, n), 36),
+            ("keys only descending", lambda: sorter.sort_ex(keys, None, n, 0, 32, True), 36),
+            ("pairs descending", lambda: sorter.sort_ex(keys, vals, n, 0, 32, True), 68),
+            ("pairs bits [0,24)", lambda: sorter.sort_ex(keys, vals, n, 0, 24), 52 + 16),  # + the copy back (odd passes)
+            ("pairs bits [8,32)", lambda: sorter.sort_ex(keys, vals, n, 8, 32), 52 + 16)]:
+        med, best = timeit(fn, prep_ex)
+        print(f"sort_ex {name:22s} n=2^{args.log2n}: median {med:.3f} ms  best {best:.3f} ms  {n / med / 1e6:.2f} Gkeys/s  "
+              f"{bytes_per * n / med / 1e6:.0f} GB/s ({bytes_per} B/key)")
+
 if "scan" in args.what:
     data0 = torch.randint(0, 100, (n,), dtype=torch.int32, device=dev, generator=g)
     data = data0.clone()
