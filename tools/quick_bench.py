@@ -123,3 +123,14 @@ if "reduce" in args.what:
     a = torch.empty(n, dtype=torch.int32, device=dev)
     med, best = timeit(lambda: a.copy_(data0))
     print(f"torch copy (read+write) n=2^{args.log2n}: median {med:.3f} ms  {8 * n / med / 1e6:.0f} GB/s")
+
+if "reducef" in args.what.split(","):
+    # BASELINE.json configs[4]: Reduce(Float, Min/Max/Sum) over uniform floats in [-1, 1)
+    f0 = (torch.rand(n, dtype=torch.float32, device=dev, generator=g) * 2 - 1)
+    f = f0.clone()
+    for name, op in [("Sum", glu.ReduceOperator_Sum), ("Min", glu.ReduceOperator_Min), ("Max", glu.ReduceOperator_Max)]:
+        red = glu.Reduce(glu.DataType_Float, op)
+        med, best = timeit(lambda: red(f, n), lambda: f.copy_(f0))
+        want = {"Sum": f0.sum(dtype=torch.float64), "Min": f0.min(), "Max": f0.max()}[name].item()
+        print(f"reduce Float {name} n=2^{args.log2n}: median {med:.3f} ms  best {best:.3f} ms  {4 * n / med / 1e6:.0f} GB/s  "
+              f"result {f[0].item():.9g} (torch {want:.9g})")
