@@ -53,62 +53,115 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
+
+    Sampled in-process through NVML (the library behind nvidia-smi; a query takes well under a millisecond, so even a
+    ~50 ms timed region gets several samples — spawning `nvidia-smi -lms` per rank delivered its first line only after
+    the run was over on an 8-GPU box).  Falls back to an nvidia-smi subprocess if NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
-        self.lines = []
+        self.samples = []   # (sm_mhz, max_mhz, set(reasons))
         self.proc = None
+        self.thread = None
+        self.running = False
+        self.source = None
+
+    # ---- NVML
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:  # CUDA_VISIBLE_DEVICES may renumber the devices: go through the UUID
+            import torch
+
+            uuid = str(torch.cuda.get_device_properties(self.gpu_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+
+    def _nvml_loop(self, nv, h):
+        bits = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while self.running:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                self.samples.append((sm, mx, {name for bit, name in bits if mask & bit}))
+                time.sleep(0.004)
+        except Exception:
+            pass
+
+    # ---- nvidia-smi fallback
+    def _smi_loop(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.strip().split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm, mx = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            self.samples.append((sm, mx, {name for name, v in zip(self.NAMES, parts[5:9])
+                                          if v.lower().startswith("active")}))
 
     def start(self):
         try:
+            nv, h = self._nvml_handle()
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.running = True
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.running = False
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.gpu_index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=self._smi_loop, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
     def mark(self):
         """Number of samples seen so far (call at the start and at the end of the timed region)."""
-        return len(self.lines)
+        return len(self.samples)
 
     def stop(self, first=0, last=None):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        # samples taken inside the timed region (one before and one after included); the sampler itself starts
-        # before the warm-up because nvidia-smi takes a while to deliver its first line
-        window = self.lines[max(0, first - 1):(last + 1 if last is not None else None)] or self.lines[-3:]
-        for line in window:
-            parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 9:
-                continue
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        if self.source == "nvidia-smi" and not self.samples:
+            for _ in range(40):  # its first line can take seconds on a multi-GPU box
+                if self.samples:
+                    break
+                time.sleep(0.1)
+        time.sleep(0.02)
+        self.running = False
+        if self.proc:
+            self.proc.terminate()
             try:
-                sm.append(float(parts[1]))
-                mx = float(parts[2])
-            except ValueError:
-                continue
-            for name, v in zip(names, parts[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        # samples taken inside the timed region (one before and one after included)
+        window = self.samples[max(0, first - 1):(last + 1 if last is not None else None)] or self.samples[-3:]
+        sm = sorted(x[0] for x in window)
+        reasons = set()
+        for x in window:
+            reasons |= x[2]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": window[-1][1] if window else None,
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -398,38 +451,65 @@ def run_b200(args):
         line["cpu_baseline"] = cpu_baseline(args)
     elif world > 1 and not args.no_side_metrics:
         # ---- e2e at N GPUs: every rank uploads its shard from pinned host memory, the job sorts, every rank
-        # downloads its slice of the result; wall clock between barriers, max over ranks
+        # downloads its slice of the result.  Like the single-GPU host queue, consecutive steps are software-pipelined:
+        # the upload of step i+1 (copy stream, second device buffer) runs under the download of step i — PCIe is full
+        # duplex — while every step still pays its own H2D + sort + D2H inside the timed region.  The download stays on
+        # the sorting stream: the next step's partition pass writes into the peers' receive buffers, so it may only
+        # start once everybody's slice has left them.  Wall clock between barriers, max over ranks.
         del inputs[1:]
         torch.cuda.empty_cache()
-        hk = torch.empty(n, dtype=torch.int32).pin_memory()
+        e2e_steps = min(steps, 5)
+        base_k, base_v = inputs[0][0].cpu(), inputs[0][1].cpu()
+        hks = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2)]  # two unsorted shards, used alternately
         hv = torch.empty(n, dtype=torch.int32).pin_memory()
+        hv.copy_(base_v)
+        for i, hk in enumerate(hks):
+            hk.copy_(base_k ^ (0x9E3779B9 * (i + 1) & 0x7FFFFFFF))
         ok_ = torch.empty(dsort.capacity, dtype=torch.int32).pin_memory()
         ov_ = torch.empty(dsort.capacity, dtype=torch.int32).pin_memory()
-        dk = torch.empty(n, dtype=torch.int32, device=dev)
-        dv = torch.empty(n, dtype=torch.int32, device=dev)
-        e2e_steps = min(steps, 5)
-        e2e_t = 0.0
-        for i in range(e2e_steps + 1):
-            hk.copy_(inputs[0][0].cpu() ^ (0x9E3779B9 * (i + 1) & 0x7FFFFFFF))
-            hv.copy_(inputs[0][1].cpu())
-            barrier()
-            t0 = time.perf_counter()
-            dk.copy_(hk, non_blocking=True)
-            dv.copy_(hv, non_blocking=True)
-            sk, sv, m = dsort(dk, dv, n)
-            ok_[:m].copy_(sk, non_blocking=True)
-            ov_[:m].copy_(sv, non_blocking=True)
-            barrier()
-            t1 = time.perf_counter()
-            if i > 0:
-                e2e_t += t1 - t0
+        dks = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
+        dvs = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        main_stream = torch.cuda.current_stream(dev)
+        uploaded = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def upload(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i % 2])  # the sort that read this device buffer two steps ago
+                dks[i % 2].copy_(hks[i % 2], non_blocking=True)
+                dvs[i % 2].copy_(hv, non_blocking=True)
+                uploaded[i % 2].record(copy_stream)
+
+        def run(first, count):
+            upload(first)
+            for i in range(first, first + count):
+                main_stream.wait_event(uploaded[i % 2])
+                if i + 1 < first + count:
+                    upload(i + 1)
+                sk, sv, m = dsort(dks[i % 2], dvs[i % 2], n)
+                consumed[i % 2].record(main_stream)
+                ok_[:m].copy_(sk, non_blocking=True)
+                ov_[:m].copy_(sv, non_blocking=True)
+
+        for ev in consumed:
+            ev.record(main_stream)
+        run(0, 1)  # warm-up step (pinned-copy paths, the copy stream)
+        barrier()
+        t0 = time.perf_counter()
+        run(1, e2e_steps)
+        barrier()
+        e2e_t = time.perf_counter() - t0
+        out64 = ok_[: 1 << 20].to(torch.int64) & 0xFFFFFFFF
+        assert bool((out64[1:] >= out64[:-1]).all()), "e2e output is not sorted"
         t = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_t = float(t.item())
         line["e2e"] = {"value": world * n * e2e_steps / e2e_t / 1e9, "unit": "Gpairs/s",
                        "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * n * world, "steps": e2e_steps,
                        "ms_per_step": 1e3 * e2e_t / e2e_steps,
-                       "api": "DistributedRadixSort (per rank: pinned host shard -> H2D -> sort -> D2H of its slice)"}
+                       "api": "DistributedRadixSort (per rank and step: pinned host shard -> H2D -> sort -> D2H of its "
+                              "slice; the upload of step i+1 overlaps the download of step i)"}
     elif rank == 0:
         line["e2e"] = None
     if rank == 0:
