@@ -7,15 +7,17 @@
 // dispatches per sort and a sync-bound ~53 Mpairs/s plateau.  Here the same stable LSD sort is
 //   1 memset + 1 histogram kernel + ceil(bits/8) "onesweep" kernels   (68 B of HBM traffic per pair):
 //   * histogram_kernel reads the keys ONCE (128-bit streaming loads) and builds the 256-bin
-//     histograms of all digit places in shared memory; warps whose keys mostly share a digit
-//     aggregate with __match_any_sync so skewed inputs do not serialise on one shared-memory bank;
+//     histograms of all digit places in shared memory with one private copy of every bin per lane
+//     (no bank conflicts, no same-address pile-up: skewed inputs cost the same as uniform ones);
 //     the last CTA turns the histograms into exclusive digit offsets;
-//   * onesweep_kernel (one launch per 8-bit digit) processes one tile per CTA: keys are ranked with
-//     warp-wide digit matching against per-warp digit counters (stable: warp-striped order is input
-//     order), the per-tile digit counts are chained across tiles with a decoupled look-back
-//     (status + 30-bit count in one 32-bit word per (tile, digit)), keys and values are reordered
-//     through shared memory so that every digit run leaves the SM as one contiguous, coalesced
-//     store burst.  Tile ids come from an atomic ticket (forward progress by construction).
+//   * onesweep_kernel (one launch per 8-bit digit) processes one tile per CTA: keys and values are staged
+//     by TMA bulk copies, keys are ranked with warp-wide digit matching against per-warp digit counters
+//     (stable: warp-striped order is input order), the per-tile digit counts are published at once and
+//     chained across tiles by a few dedicated CHAIN CTAs (decoupled look-back turned inside out: a tile
+//     reads ONE prefix row instead of walking back over its predecessors; status + count in one 32-bit
+//     word per (tile, digit)), keys and values are reordered through shared memory so that every digit
+//     run leaves the SM as one contiguous, coalesced store burst.  Tile ids are blockIdx.x (an atomic
+//     ticket is optional, GLU_SORT_OPTIONS bit 1).
 // Results are bit-identical to std::stable_sort of the (key, value) pairs by key — and therefore to
 // the reference's 8 x 4-bit passes, which are stable as well (oracle/glu_oracle.cpp radix_sort_glsl).
 #include <cstdlib>
@@ -362,9 +364,9 @@ namespace glu_b200
         }
 
         // One tile per CTA.  digit(key) = (key >> shift) & mask; keys with equal digits keep their order.
-        // A CTA is RANK_THREADS "ranking" threads plus one dedicated look-back warp.
+        // The first 8 (or 4) CTAs of the grid are not tiles but the pass's CHAIN CTAs (chain_cta above).
         //
-        //   1. ticket -> tile id; one thread issues two cp.async.bulk (TMA) copies: the tile's keys and
+        //   1. tile id (blockIdx.x, or a ticket); one thread issues two cp.async.bulk (TMA) copies: the tile's keys and
         //      values land in shared memory asynchronously, completion on an mbarrier each (the last,
         //      partial tile and 16-byte-misaligned inputs take a cooperative ld/st path instead);
         //   2. EARLY COUNTS: every ranking thread takes IPT keys warp-striped (slot = warp*IPT*32 + i*32
@@ -375,9 +377,9 @@ namespace glu_b200
         //   3. ranking: peers = lanes of the warp holding the same digit (one ballot per digit bit);
         //      slot = offset[warp][digit] + popc(peers below me); the key goes straight to its
         //      tile-sorted slot (in place: every key is in registers by now);
-        //   4. MEANWHILE the look-back warp walks back over the earlier tiles' published counts (8 digits
-        //      per lane, several rows in flight) until it meets an inclusive prefix, publishes this
-        //      tile's inclusive prefix and leaves gbase[digit] = global index of tile-sorted slot 0;
+        //   4. MEANWHILE the chain CTAs turn the published counts into prefix rows; thread d of the tile
+        //      reads prefix[tile - 1][d] (one word, written by the chain) and leaves gbase[digit] = global
+        //      index of tile-sorted slot 0;
         //   5. values: staging buffer -> registers -> tile-sorted slot (in place); then slot p of both
         //      arrays goes to global[gbase[digit(key_p)] + p] — neighbouring threads, neighbouring
         //      addresses inside every digit run.
