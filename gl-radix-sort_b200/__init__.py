@@ -53,6 +53,8 @@ ABI = {
     "glu_radix_sort_u32kv": (_int, [_vp, _vp, _sz, _sz, _vp, _sz, _vp]),
     "glu_radix_sort_u32_ex_tmp_bytes": (_sz, [_sz, _int]),
     "glu_radix_sort_u32_ex": (_int, [_vp, _vp, _sz, ctypes.c_uint, ctypes.c_uint, _int, _vp, _sz, _vp]),
+    "glu_radix_sort_wide_tmp_bytes": (_sz, [_sz, _sz, _sz]),
+    "glu_radix_sort_wide": (_int, [_vp, _sz, _vp, _sz, _sz, _int, _vp, _sz, _vp]),
     "glu_reduce_into": (_int, [_vp, _sz, _int, _int, _vp, _vp, _sz, _vp]),
     "glu_scan_exclusive_init": (_int, [_vp, _sz, _sz, _int, _vp, _vp, _sz, _vp]),
     "glu_radix_histogram_u32": (_int, [_vp, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _vp]),
@@ -320,6 +322,30 @@ class RadixSort:
         st = _current_stream(dev) if stream is None else stream
         check(_lib.glu_radix_sort_u32_ex(kptr, vptr, count, begin_bit, end_bit, 1 if descending else 0, tmp, tmp_bytes,
                                          st), "RadixSort.sort_ex")
+
+    def sort_wide(self, key_buffer, val_buffer, count: int, key_bytes: int = 8, value_bytes: int = 4,
+                  descending: bool = False, stream: int | None = None) -> None:
+        """glu_radix_sort_wide: 4- or 8-byte unsigned keys with no (`val_buffer=None`, `value_bytes=0`), 4-, 8- or
+        16-byte values.  Stable, in place."""
+        kptr, kdev = _ptr_and_device(key_buffer)
+        vptr, vdev = _ptr_and_device(val_buffer) if val_buffer is not None else (None, None)
+        if not kptr:
+            raise GluError(1, "Invalid key buffer")
+        if (val_buffer is None) != (value_bytes == 0) or (val_buffer is not None and not vptr):
+            raise GluError(1, "Invalid value buffer / value_bytes")
+        if key_bytes not in (4, 8) or value_bytes not in (0, 4, 8, 16):
+            raise GluError(1, "RadixSort.sort_wide: key_bytes must be 4 or 8, value_bytes 0, 4, 8 or 16")
+        if count <= 1:
+            return
+        dev = _device_of(kdev if kdev is not None else vdev)
+        need = int(_lib.glu_radix_sort_wide_tmp_bytes(count, key_bytes, value_bytes))
+        if need == 0:
+            raise GluError(6, "RadixSort.sort_wide")
+        tmp, tmp_bytes = self._scratch.ensure(need, dev)
+        self._device = dev
+        st = _current_stream(dev) if stream is None else stream
+        check(_lib.glu_radix_sort_wide(kptr, key_bytes, vptr, value_bytes, count, 1 if descending else 0, tmp, tmp_bytes,
+                                       st), "RadixSort.sort_wide")
 
     def sort_device_count(self, key_buffer, val_buffer, count_buffer, max_count: int, num_steps: int = 0,
                           stream: int | None = None) -> None:

@@ -71,6 +71,24 @@ namespace glu
                                                    count, begin_bit, end_bit, descending ? 1 : 0, m_tmp.handle(),
                                                    m_tmp.size(), m_stream));
         }
+
+        /// 64-bit keys and wide payloads (glu_radix_sort_wide): key_bytes 4 or 8, value_bytes 0 (val_buffer null), 4, 8
+        /// or 16.  Stable, in place.
+        void sort_wide(DevicePtr key_buffer, size_t key_bytes, DevicePtr val_buffer, size_t value_bytes, size_t count,
+                       bool descending = false)
+        {
+            GLU_CHECK_ARGUMENT(key_buffer, "Invalid key buffer");
+            GLU_CHECK_ARGUMENT((val_buffer != nullptr) == (value_bytes != 0), "Invalid value buffer / value_bytes");
+            if (count <= 1)
+                return;
+            const size_t need = glu_radix_sort_wide_tmp_bytes(count, key_bytes, value_bytes);
+            GLU_CHECK_ARGUMENT(need != 0, "RadixSort: unsupported element widths (%zu, %zu) or count %zu too large",
+                               key_bytes, value_bytes, count);
+            if (m_tmp.size() < need)
+                m_tmp.resize(need, false);
+            GLU_CHECK_STATUS(glu_radix_sort_wide(key_buffer, key_bytes, val_buffer, value_bytes, count, descending ? 1 : 0,
+                                                 m_tmp.handle(), m_tmp.size(), m_stream));
+        }
     };
 } // namespace glu
 

@@ -154,6 +154,16 @@ GLU_API size_t glu_radix_sort_u32_ex_tmp_bytes(size_t count, int with_values);
 GLU_API int glu_radix_sort_u32_ex(uint32_t* d_keys, uint32_t* d_vals, size_t count, unsigned begin_bit, unsigned end_bit,
                                   int descending, void* d_tmp, size_t tmp_bytes, glu_stream_t stream);
 
+/* 64-bit keys and payloads wider than 32 bits, stable, ascending or descending, in place:
+ * key_bytes is 4 or 8 (unsigned integers), value_bytes is 0 (d_vals == NULL: keys only), 4, 8 or 16 (opaque
+ * elements, e.g. uint64 / double / a vec4).  Built on the 32-bit sort: (key word, element index) pairs are sorted —
+ * twice for 8-byte keys, low word then high word — and the wide keys and values are moved once through the
+ * resulting permutation (gl-radix-sort_b200/csrc/glu_radix_sort_wide.cu).  key_bytes == 4 with value_bytes <= 4 is
+ * glu_radix_sort_u32_ex itself.  d_keys / d_vals must be aligned to their element size; count < 2^31. */
+GLU_API size_t glu_radix_sort_wide_tmp_bytes(size_t count, size_t key_bytes, size_t value_bytes);
+GLU_API int glu_radix_sort_wide(void* d_keys, size_t key_bytes, void* d_vals, size_t value_bytes, size_t count,
+                                int descending, void* d_tmp, size_t tmp_bytes, glu_stream_t stream);
+
 /* ------------------------------------------------------------------ building blocks of the multi-GPU path
  * Not in the reference (it is single-GPU); these are what gl-radix-sort_b200/distributed.py composes with
  * NCCL / NVLink peer memory (DESIGN.md "Multi-GPU").  Same conventions as above. */

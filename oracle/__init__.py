@@ -175,6 +175,15 @@ def stable_sort_ex(keys: np.ndarray, vals: np.ndarray | None, begin_bit: int = 0
     return k, v
 
 
+def stable_sort_wide(keys: np.ndarray, vals: np.ndarray | None, descending: bool = False):
+    """Oracle of glu_radix_sort_wide (beyond the reference, parity unpinned by it): stable sort of uint32 / uint64 keys,
+    ascending or descending, the rows of `vals` (any element width) carried along.  numpy's stable argsort on the
+    (complemented, for descending) keys == std::stable_sort with less<> / greater<>."""
+    assert keys.dtype in (np.uint32, np.uint64) and keys.ndim == 1
+    order = np.argsort(~keys if descending else keys, kind="stable")
+    return keys[order], (None if vals is None else vals[order])
+
+
 def time_stable_sort_pairs(keys: np.ndarray, vals: np.ndarray, threads: int = 1) -> float:
     """Seconds spent in std::stable_sort (threads==1) / __gnu_parallel::stable_sort on the pairs."""
     return float(lib().glu_oracle_time_stable_sort_pairs(_u32p(keys), _u32p(vals), keys.size, threads))

@@ -82,6 +82,17 @@ def test_argument_errors_are_status_codes_not_exits(glu):
     assert L.glu_radix_sort_u32_ex(fake, None, 8, 0, 32, 0, None, 0, None) == 4
     assert L.glu_radix_sort_u32_ex(fake, None, 1 << 31, 0, 32, 0, fake, 1 << 40, None) == 6
     assert L.glu_radix_sort_u32_ex(ctypes.c_void_p(0x1002), None, 8, 0, 32, 0, fake, 1 << 20, None) == 5
+    # glu_radix_sort_wide: element widths, value pointer <-> value_bytes, alignment to the element size
+    assert L.glu_radix_sort_wide(None, 8, fake, 4, 8, 0, fake, 1 << 20, None) == 1
+    assert L.glu_radix_sort_wide(fake, 3, fake, 4, 8, 0, fake, 1 << 20, None) == 1
+    assert L.glu_radix_sort_wide(fake, 8, fake, 12, 8, 0, fake, 1 << 20, None) == 1
+    assert L.glu_radix_sort_wide(fake, 8, None, 4, 8, 0, fake, 1 << 20, None) == 1
+    assert L.glu_radix_sort_wide(fake, 8, fake, 0, 8, 0, fake, 1 << 20, None) == 1
+    assert L.glu_radix_sort_wide(fake, 8, fake, 8, 1, 0, None, 0, None) == 0  # count <= 1
+    assert L.glu_radix_sort_wide(ctypes.c_void_p(0x1004), 8, None, 0, 8, 0, fake, 1 << 20, None) == 5
+    assert L.glu_radix_sort_wide(fake, 8, ctypes.c_void_p(0x1008), 16, 8, 0, fake, 1 << 20, None) == 5
+    assert L.glu_radix_sort_wide(fake, 8, fake, 8, 8, 0, None, 0, None) == 4
+    assert L.glu_radix_sort_wide(fake, 8, None, 0, 1 << 31, 0, fake, 1 << 40, None) == 6
 
 
 def test_tmp_size_queries(glu):
@@ -98,6 +109,12 @@ def test_tmp_size_queries(glu):
     kv, ko = L.glu_radix_sort_u32_ex_tmp_bytes(n, 1), L.glu_radix_sort_u32_ex_tmp_bytes(n, 0)
     assert 2 * 4 * n <= kv <= 2 * 4 * n + (8 << 20) and 4 * n <= ko <= 4 * n + (8 << 20)
     assert L.glu_radix_sort_u32_ex_tmp_bytes(1 << 31, 0) == 0
+    # wide sort: index + key word + permuted keys + permuted values + the 32-bit sort's own scratch
+    w = L.glu_radix_sort_wide_tmp_bytes(n, 8, 16)
+    assert w >= 4 * n + 4 * n + 8 * n + 16 * n + kv and w <= 32 * n + kv + (1 << 20)
+    assert L.glu_radix_sort_wide_tmp_bytes(n, 4, 4) == kv and L.glu_radix_sort_wide_tmp_bytes(n, 4, 0) == ko
+    assert L.glu_radix_sort_wide_tmp_bytes(n, 8, 3) == 0 and L.glu_radix_sort_wide_tmp_bytes(n, 2, 4) == 0
+    assert L.glu_radix_sort_wide_tmp_bytes(1 << 31, 8, 0) == 0
 
 
 def test_python_mirror_validates_like_the_reference(glu):

@@ -107,6 +107,26 @@ if "ex" in args.what.split(","):
         print(f"sort_ex {name:22s} n=2^{args.log2n}: median {med:.3f} ms  best {best:.3f} ms  {n / med / 1e6:.2f} Gkeys/s  "
               f"{bytes_per * n / med / 1e6:.0f} GB/s ({bytes_per} B/key)")
 
+if "wide" in args.what.split(","):
+    # glu_radix_sort_wide: 64-bit keys / wide payloads through the (key word, index) permutation
+    sorter = glu.RadixSort()
+    for name, kb, vb in [("u64 keys only", 8, 0), ("u64 keys + u32 values", 8, 4), ("u64 keys + u64 values", 8, 8),
+                         ("u32 keys + 16-byte values", 4, 16)]:
+        if kb == 8:
+            k0 = torch.randint(-(1 << 62), 1 << 62, (n,), dtype=torch.int64, device=dev, generator=g) * 2
+        else:
+            k0 = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int32, device=dev, generator=g)
+        v0 = None if vb == 0 else torch.zeros((n, vb // 4), dtype=torch.int32, device=dev)
+        k = k0.clone()
+        v = None if v0 is None else v0.clone()
+
+        def prep_w():
+            k.copy_(k0)
+
+        med, best = timeit(lambda: sorter.sort_wide(k, v, n, kb, vb), prep_w, reps=min(args.reps, 3))
+        print(f"sort_wide {name:26s} n=2^{args.log2n}: median {med:.3f} ms  best {best:.3f} ms  {n / med / 1e6:.2f} Gkeys/s")
+        del k0, v0, k, v
+
 if "scan" in args.what:
     data0 = torch.randint(0, 100, (n,), dtype=torch.int32, device=dev, generator=g)
     data = data0.clone()
