@@ -1,18 +1,21 @@
 // glu_radix_sort_wide.cu — glu_radix_sort_wide(): 64-bit keys and payloads wider than 32 bits (SURVEY.md §8f row 3;
 // the reference sorts uint32 keys with a mandatory uint32 value only, README.md:88-89, glu/RadixSort.hpp:273).
 //
-// Built ON the 32-bit onesweep sort instead of beside it: what is sorted is always a (32-bit key word, 32-bit element
-// index) pair array — the shape the tuned kernels of glu_radix_sort.cu are written for — and the wide data moves
-// exactly once, at the end, through the resulting permutation:
-//   8-byte keys : idx = 0..n-1, w = low word  -> stable sort (w, idx)     [4 digit passes]
-//                 w[i] = high word of key[idx[i]]                          [gather]
-//                 stable sort (w, idx) again                               [4 digit passes; LSD over two 32-bit "digits"]
-//                 keys'[i] = keys[idx[i]], vals'[i] = vals[idx[i]]         [gathers into scratch, copied back]
-//   4-byte keys with 8/16-byte values: sort (key, idx) directly, then gather the values.
-// Stable (both sorts are), ascending or descending (both sorts complement their digits).
-// HBM traffic for 8-byte keys + 4-byte values is ~300 B per pair (two 68 B/pair sorts, the split, three random
-// gathers whose 4..16-byte reads cost a 32-byte sector each, the copy back) against ~200 B per pair for a native
-// 8-pass sort of 12-byte pairs; the permutation approach is what lets payloads of any width ride along unchanged.
+// Built ON the 32-bit onesweep sort instead of beside it: what is sorted is always a (32-bit key word, 32-bit payload)
+// pair array — the shape the tuned kernels of glu_radix_sort.cu are written for.  A 64-bit key is two 32-bit "digits":
+// a stable sort by the low word followed by a stable sort by the high word (LSD).
+//   8-byte keys, no values   : the two words are each other's payload — sort (low, high), sort (high, low), zip.
+//                              No random access at all: 25.0 Gkeys/s at 2^27 (B200).
+//   8-byte keys, 4-byte value: the value rides through the same two sorts in two extra sorts on copies of the same
+//                              sort keys (equal keys + stability = the same permutation): four coalesced sorts,
+//                              13.0 Gpairs/s at 2^27 (two sorts + three random gathers measured 8.7).
+//   any other combination    : the general path — sort (key word, element index), twice for 8-byte keys with a gather
+//                              of the high words in between, and move the wide keys / values ONCE through the final
+//                              permutation (gathers into scratch, copied back).  Payloads of 8 or 16 bytes ride along
+//                              unchanged; the random gathers cost a 32-byte sector per element (8.3 Gpairs/s for
+//                              8-byte keys + 8-byte values, 19.3 Gpairs/s for 4-byte keys + 16-byte values at 2^27).
+// Stable (every sort is), ascending or descending (every sort complements its digits).  A native 8-pass onesweep over
+// 12..16-byte pairs would move ~200 B per pair against ~300 B here; it is listed as future work in DESIGN.md §8.
 #include "glu_common.cuh"
 
 namespace glu_b200
@@ -39,6 +42,28 @@ namespace glu_b200
                 if (keys)
                     word[i] = uint32_t(keys[i]);
             }
+        }
+
+        // low[i], high[i] = the two words of keys[i]
+        __global__ void __launch_bounds__(k_wide_threads)
+            wide_unzip_kernel(const uint64_t* __restrict__ keys, uint32_t* __restrict__ low, uint32_t* __restrict__ high,
+                              size_t n)
+        {
+            for (size_t i = size_t(blockIdx.x) * k_wide_threads + threadIdx.x; i < n; i += size_t(gridDim.x) * k_wide_threads)
+            {
+                const uint64_t k = keys[i];
+                low[i] = uint32_t(k);
+                high[i] = uint32_t(k >> 32);
+            }
+        }
+
+        // keys[i] = high[i] : low[i]
+        __global__ void __launch_bounds__(k_wide_threads)
+            wide_zip_kernel(const uint32_t* __restrict__ low, const uint32_t* __restrict__ high, uint64_t* __restrict__ keys,
+                            size_t n)
+        {
+            for (size_t i = size_t(blockIdx.x) * k_wide_threads + threadIdx.x; i < n; i += size_t(gridDim.x) * k_wide_threads)
+                keys[i] = (uint64_t(high[i]) << 32) | low[i];
         }
 
         // word[i] = high 32 bits of keys[idx[i]]
@@ -103,7 +128,8 @@ namespace glu_b200
             l.off_idx = 0;
             l.off_word = l.off_idx + align_up(count * sizeof(uint32_t), k_tmp_align);
             l.off_keys = l.off_word + (key_bytes == 8 ? align_up(count * sizeof(uint32_t), k_tmp_align) : 0);
-            l.off_vals = l.off_keys + (key_bytes == 8 ? align_up(count * key_bytes, k_tmp_align) : 0);
+            // (8-byte keys without values: [low words][high words][sort scratch], no permuted copy of the keys)
+            l.off_vals = l.off_keys + (key_bytes == 8 && value_bytes != 0 ? align_up(count * key_bytes, k_tmp_align) : 0);
             l.off_sort = l.off_vals + align_up(count * value_bytes, k_tmp_align);
             l.sort_bytes = glu_radix_sort_u32_ex_tmp_bytes(count, 1);
             l.total = l.off_sort + l.sort_bytes;
@@ -158,6 +184,52 @@ extern "C" int glu_radix_sort_wide(void* d_keys, size_t key_bytes, void* d_vals,
     const unsigned grid = wide_grid(count, sms);
     int rc = GLU_SUCCESS;
 
+    if (key_bytes == 8 && value_bytes == 0)
+    {
+        uint32_t* low = idx; // the "index" array holds the low words here
+        uint32_t* high = reinterpret_cast<uint32_t*>(tmp + l.off_word);
+        wide_unzip_kernel<<<grid, k_wide_threads, 0, s>>>(static_cast<const uint64_t*>(d_keys), low, high, count);
+        GLU_LAUNCH_CHECK();
+        rc = glu_radix_sort_u32_ex(low, high, count, 0, 32, descending, sort_tmp, l.sort_bytes, stream);
+        if (rc != GLU_SUCCESS)
+            return rc;
+        rc = glu_radix_sort_u32_ex(high, low, count, 0, 32, descending, sort_tmp, l.sort_bytes, stream);
+        if (rc != GLU_SUCCESS)
+            return rc;
+        wide_zip_kernel<<<grid, k_wide_threads, 0, s>>>(low, high, static_cast<uint64_t*>(d_keys), count);
+        GLU_LAUNCH_CHECK();
+        return GLU_SUCCESS;
+    }
+    if (key_bytes == 8 && value_bytes == 4)
+    {
+        // 8-byte keys with a 4-byte value: still no random access.  The value rides through the same two stable sorts
+        // as the other key word, in two extra sorts on copies of the same sort keys (equal keys + stability = the same
+        // permutation): four coalesced 68 B/pair sorts beat two sorts plus three random gathers (15.4 -> ~10 ms at 2^27).
+        uint32_t* low = idx;
+        uint32_t* high = reinterpret_cast<uint32_t*>(tmp + l.off_word);
+        uint32_t* dup = reinterpret_cast<uint32_t*>(tmp + l.off_keys); // count * 8 bytes are reserved there
+        uint32_t* vals = static_cast<uint32_t*>(d_vals);
+        const size_t bytes = count * sizeof(uint32_t);
+        wide_unzip_kernel<<<grid, k_wide_threads, 0, s>>>(static_cast<const uint64_t*>(d_keys), low, high, count);
+        GLU_LAUNCH_CHECK();
+        GLU_CUDA_TRY(cudaMemcpyAsync(dup, low, bytes, cudaMemcpyDeviceToDevice, s));
+        rc = glu_radix_sort_u32_ex(low, high, count, 0, 32, descending, sort_tmp, l.sort_bytes, stream);
+        if (rc != GLU_SUCCESS)
+            return rc;
+        rc = glu_radix_sort_u32_ex(dup, vals, count, 0, 32, descending, sort_tmp, l.sort_bytes, stream);
+        if (rc != GLU_SUCCESS)
+            return rc;
+        GLU_CUDA_TRY(cudaMemcpyAsync(dup, high, bytes, cudaMemcpyDeviceToDevice, s));
+        rc = glu_radix_sort_u32_ex(high, low, count, 0, 32, descending, sort_tmp, l.sort_bytes, stream);
+        if (rc != GLU_SUCCESS)
+            return rc;
+        rc = glu_radix_sort_u32_ex(dup, vals, count, 0, 32, descending, sort_tmp, l.sort_bytes, stream);
+        if (rc != GLU_SUCCESS)
+            return rc;
+        wide_zip_kernel<<<grid, k_wide_threads, 0, s>>>(low, high, static_cast<uint64_t*>(d_keys), count);
+        GLU_LAUNCH_CHECK();
+        return GLU_SUCCESS;
+    }
     if (key_bytes == 8)
     {
         const uint64_t* keys = static_cast<const uint64_t*>(d_keys);
