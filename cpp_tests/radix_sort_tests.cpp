@@ -168,6 +168,60 @@ TEST_CASE("RadixSort-ex-keys-only-bit-range-descending", "")
     }
 }
 
+// Beyond the reference: 64-bit keys and payloads wider than 32 bits through RadixSort::sort_wide.
+TEST_CASE("RadixSort-wide-u64-keys-and-wide-values", "")
+{
+    std::mt19937_64 engine(11);
+    for (size_t n : {2500, 400003})
+    {
+        std::vector<uint64_t> keys(n);
+        for (uint64_t& k : keys)
+            k = engine() >> (engine() % 3 == 0 ? 40 : 0); // mixed magnitudes, many equal high words
+        struct Wide
+        {
+            uint64_t a, b;
+            bool operator==(const Wide& o) const { return a == o.a && b == o.b; }
+        };
+        std::vector<Wide> vals(n);
+        std::vector<uint32_t> vals32(n);
+        for (size_t i = 0; i < n; i++)
+        {
+            vals[i] = {i, ~uint64_t(i)};
+            vals32[i] = uint32_t(i);
+        }
+        RadixSort radix_sort;
+        for (bool descending : {false, true})
+        {
+            std::vector<size_t> order(n);
+            std::iota(order.begin(), order.end(), size_t(0));
+            std::stable_sort(order.begin(), order.end(),
+                             [&](size_t x, size_t y) { return descending ? keys[x] > keys[y] : keys[x] < keys[y]; });
+            { // 8-byte keys + 16-byte values (general permutation path)
+                DeviceBuffer key_buffer(keys), val_buffer(vals);
+                radix_sort.sort_wide(key_buffer.handle(), 8, val_buffer.handle(), 16, n, descending);
+                const std::vector<uint64_t> k = key_buffer.get_data<uint64_t>();
+                const std::vector<Wide> v = val_buffer.get_data<Wide>();
+                bool equal = true;
+                for (size_t i = 0; i < n && equal; i++)
+                    equal = k[i] == keys[order[i]] && v[i] == vals[order[i]];
+                CHECK(equal);
+            }
+            { // 8-byte keys + 4-byte values (four-sort path), 8-byte keys alone (two-sort path)
+                DeviceBuffer key_buffer(keys), val_buffer(vals32), key_only(keys);
+                radix_sort.sort_wide(key_buffer.handle(), 8, val_buffer.handle(), 4, n, descending);
+                radix_sort.sort_wide(key_only.handle(), 8, nullptr, 0, n, descending);
+                const std::vector<uint64_t> k = key_buffer.get_data<uint64_t>();
+                const std::vector<uint64_t> k2 = key_only.get_data<uint64_t>();
+                const std::vector<uint32_t> v = val_buffer.get_data<uint32_t>();
+                bool equal = true;
+                for (size_t i = 0; i < n && equal; i++)
+                    equal = k[i] == keys[order[i]] && k2[i] == k[i] && v[i] == vals32[order[i]];
+                CHECK(equal);
+            }
+        }
+    }
+}
+
 TEST_CASE("RadixSort-benchmark", "[.][benchmark]")
 {
     for (size_t k_num_elements : {1024, 16384, 65536, 131072, 524288, 1048576, 2097152, 4194304, 8388608, 16777216,
