@@ -460,15 +460,29 @@ def run_b200(args):
         torch.cuda.empty_cache()
         e2e_steps = min(steps, 5)
         base_k, base_v = inputs[0][0].cpu(), inputs[0][1].cpu()
-        hks = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2)]  # two unsorted shards, used alternately
-        hv = torch.empty(n, dtype=torch.int32).pin_memory()
-        hv.copy_(base_v)
-        for i, hk in enumerate(hks):
-            hk.copy_(base_k ^ (0x9E3779B9 * (i + 1) & 0x7FFFFFFF))
-        ok_ = torch.empty(dsort.capacity, dtype=torch.int32).pin_memory()
-        ov_ = torch.empty(dsort.capacity, dtype=torch.int32).pin_memory()
-        dks = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
-        dvs = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
+        try:  # 5.5 GiB of pinned host memory and 4 GiB of HBM per rank at 2^28 pairs
+            hks = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2)]  # two unsorted shards, alternating
+            hv = torch.empty(n, dtype=torch.int32).pin_memory()
+            hv.copy_(base_v)
+            for i, hk in enumerate(hks):
+                hk.copy_(base_k ^ (0x9E3779B9 * (i + 1) & 0x7FFFFFFF))
+            ok_ = torch.empty(dsort.capacity, dtype=torch.int32).pin_memory()
+            ov_ = torch.empty(dsort.capacity, dtype=torch.int32).pin_memory()
+            dks = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
+            dvs = [torch.empty(n, dtype=torch.int32, device=dev) for _ in range(2)]
+            allocated = 1
+        except RuntimeError as e:  # e.g. the host cannot pin that much for every rank
+            allocated = 0
+            sys.stderr.write(f"[bench rank {rank}] e2e buffers: {e}\n")
+        flag = torch.tensor([allocated], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # all ranks run the e2e leg or none does (it contains collectives)
+        if int(flag.item()) == 0:
+            line["e2e"] = None
+            line["e2e_skipped"] = "a rank could not allocate the pinned host / device buffers of the e2e leg"
+            if rank == 0:
+                print(json.dumps(line), flush=True)
+            dist.destroy_process_group()
+            return
         copy_stream = torch.cuda.Stream(device=dev)
         main_stream = torch.cuda.current_stream(dev)
         uploaded = [torch.cuda.Event(), torch.cuda.Event()]
