@@ -200,8 +200,12 @@ def run_reference(args):
         "impl": "reference", "metric": "radix_sort_u32_key_value_throughput", "value": value, "unit": "Gpairs/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": min(warmup, 1), "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"std::stable_sort of (uint32 key, uint32 value) pairs on the host, each step a "
-                               f"2^{args.cpu_sample_log2}-pair uniform-random (mt19937) sample of the 2^28-pair sort"},
+        "config": {"workload": f"RadixSort of 2^{args.log2_pairs} uniform-random uint32 key/value pairs per GPU "
+                               f"(BASELINE.json configs[2]), values = input index, one fresh unsorted input per step",
+                   "pairs_per_gpu": 1 << args.log2_pairs,
+                   "reference_arm": f"std::stable_sort of the (key, value) pairs on the host (the reference test-suite's "
+                                    f"oracle; its GLSL path needs OpenGL 4.6), each step a 2^{args.cpu_sample_log2}-pair "
+                                    f"uniform-random (mt19937) sample of that workload"},
         "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": threads, "kind": "port",
                          "sample": f"2^{args.cpu_sample_log2} pairs per step, __gnu_parallel::stable_sort, "
                                    f"{threads} threads"},
