@@ -425,4 +425,5 @@ class HostSortQueue:
 
 
 from . import distributed  # noqa: E402  (multi-GPU composition; imports torch lazily)
-from .distributed import DistributedBlellochScan, DistributedRadixSort, DistributedReduce  # noqa: E402,F401
+from .distributed import (DistributedBlellochScan, DistributedRadixSort, DistributedReduce,  # noqa: E402,F401
+                          DistributedSortPipeline)

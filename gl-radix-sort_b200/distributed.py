@@ -478,3 +478,110 @@ class DistributedRadixSort:
         if self.last_plan is None and self._last_hist is not None:
             self.last_plan = plan_exchange(self._last_hist.copy())
         return self.last_plan
+
+
+class DistributedSortPipeline:
+    """A stream of independent distributed sorts with the NVLink-bound exchange of job k+1 overlapping the local sort of
+    job k.  EXPERIMENTAL: written at the end of round 1, after the round's GPU time was spent — it composes only
+    kernels and collectives that `DistributedRadixSort` already uses, but it has NOT been run on GPUs yet, is not used
+    by default anywhere, and has no place in the numbers of DESIGN.md.
+
+    Why: at 8 GPUs a sort step is 0.24 ms histogram / plan + 3.5 ms partition-and-exchange (a onesweep pass that costs
+    1.07 ms on local memory: its SMs mostly wait for NVLink) + 4.5 ms local sort (SM-bound) = 8.3 ms.  Two lanes — each
+    a complete `DistributedRadixSort` with its own receive buffers — and two streams turn that into max(exchange,
+    local sort) per job in the steady state.
+
+        pipe = DistributedSortPipeline(max_count)
+        t0 = pipe.submit(keys0, vals0, n)        # enqueues, returns a ticket
+        t1 = pipe.submit(keys1, vals1, n)        # its exchange runs under job 0's local sort
+        sk, sv, m = pipe.result(t0)              # valid until the submit after next (lane reuse)
+
+    Ordering.  Job k uses lane k % 2.  Stream X carries histogram -> all-gather -> plan -> partition (peer stores) ->
+    all-reduce barrier, stream S the local sort.  Before job k's all-gather, X waits for this rank's local sort of job
+    k - 2 (same lane) and for everything the caller's stream had enqueued at submit time (its consumption of result
+    k - 2); the all-gather completes only when every rank has got that far, so nobody's receive buffers of the lane are
+    overwritten while still in use.  All collectives are issued on X, in the same order on every rank."""
+
+    def __init__(self, max_count: int, group=None, capacity_factor: float = 1.25, split_shift: int = 32 - RADIX_BITS):
+        import torch
+
+        glu = _glu()
+        self.lanes = [DistributedRadixSort(max_count, group=group, capacity_factor=capacity_factor, exchange="p2p",
+                                           split_shift=int(split_shift), plan="device") for _ in range(2)]
+        self.device = self.lanes[0].device
+        self.stream_x = torch.cuda.Stream(device=self.device)
+        self.stream_s = torch.cuda.Stream(device=self.device)
+        self._exchanged = [torch.cuda.Event(), torch.cuda.Event()]
+        self._sorted = [torch.cuda.Event(), torch.cuda.Event()]
+        self._submitted = 0
+        self._glu = glu
+
+    def submit(self, key_buffer, val_buffer, count: int) -> int:
+        import torch
+
+        glu, dist = self._glu, _dist()
+        k = self._submitted
+        lane = self.lanes[k % 2]
+        kptr, _ = glu._ptr_and_device(key_buffer)
+        vptr, _ = glu._ptr_and_device(val_buffer)
+        if not kptr or not vptr:
+            raise glu.GluError(1, "Invalid key / value buffer")
+        if count < 1 or count > lane.max_count:
+            raise glu.GluError(1, f"count must be in [1, {lane.max_count}]")
+        shift = int(lane.split_shift)
+        world, rank = lane.world, lane.rank
+        self.stream_x.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream_x):
+            if k >= 2:
+                self.stream_x.wait_event(self._sorted[k % 2])
+            st = self.stream_x.cuda_stream
+            glu.check(glu.lib.glu_radix_histogram_u32(kptr, count, shift, RADIX_BITS, lane._hist.data_ptr(), st),
+                      "glu_radix_histogram_u32")
+            dist.all_gather_into_tensor(lane._hist_all, lane._hist, group=lane.group)
+            tptr, pptr = lane._tables.data_ptr(), lane._peers_dev.data_ptr()
+            glu.check(glu.lib.glu_radix_exchange_plan(lane._hist_all.data_ptr(), world, rank, count, lane.capacity, pptr,
+                                                      pptr + 8 * world, tptr, tptr + 8 * RADIX, tptr + 16 * RADIX,
+                                                      lane._counts_dev.data_ptr(), lane._info_dev.data_ptr(), st),
+                      "glu_radix_exchange_plan")
+            lane._info_host.copy_(lane._info_dev, non_blocking=True)
+            lane._plan_event.record(self.stream_x)
+            cptr = lane._counts_dev.data_ptr()
+            glu.check(glu.lib.glu_radix_partition_by_dest_u32kv_dyn(kptr, vptr, cptr, count, shift, RADIX_BITS,
+                                                                    tptr + 16 * RADIX, tptr, tptr + 8 * RADIX,
+                                                                    lane._part_tmp.data_ptr(), lane._part_tmp.numel(), st),
+                      "glu_radix_partition_by_dest_u32kv_dyn")
+            dist.all_reduce(lane._token, group=lane.group)  # every rank's peer stores of this job have landed
+            self._exchanged[k % 2].record(self.stream_x)
+        with torch.cuda.stream(self.stream_s):
+            self.stream_s.wait_event(self._exchanged[k % 2])
+            lane._sorter.sort_device_count(lane._recv_keys.tensor, lane._recv_vals.tensor, cptr + 4, lane.capacity,
+                                           stream=self.stream_s.cuda_stream)
+            self._sorted[k % 2].record(self.stream_s)
+        self._submitted = k + 1
+        return k
+
+    def result(self, ticket: int):
+        """(sorted_keys, sorted_vals, m) of job `ticket`; call before the submit after next reuses its lane.  The
+        returned views are ready on the CALLER's current stream (it is made to wait for the job's local sort)."""
+        import torch
+
+        glu = self._glu
+        if not (self._submitted - 2 <= ticket < self._submitted) or ticket < 0:
+            raise glu.GluError(1, "DistributedSortPipeline.result: the job's lane has been reused (or never submitted)")
+        lane = self.lanes[ticket % 2]
+        torch.cuda.current_stream(self.device).wait_event(self._sorted[ticket % 2])
+        lane._plan_event.synchronize()
+        info = lane._info_host.numpy()
+        if int(info[lane.world + 1]) != 0:
+            raise glu.GluError(6, f"DistributedSortPipeline: a rank would receive {int(info[:lane.world].max())} pairs, "
+                                  f"capacity is {lane.capacity}")
+        m = int(info[lane.world])
+        return lane._recv_keys.tensor[:m], lane._recv_vals.tensor[:m], m
+
+    def flush(self) -> None:
+        """Make the caller's current stream wait for everything submitted so far (e.g. before recording a timing event)."""
+        import torch
+
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.stream_x)
+        cur.wait_stream(self.stream_s)
