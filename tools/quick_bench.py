@@ -80,8 +80,8 @@ if "sort" in args.what:
           f"{n / med / 1e6:.2f} Gpairs/s  {68 * n / med / 1e6:.0f} GB/s(68B/pair)  "
           f"cfg={os.environ.get('GLU_SORT_CONFIG', 'auto')} rank={os.environ.get('GLU_SORT_RANK', '0')} "
           f"tma={os.environ.get('GLU_SORT_TMA', '1')} prefetch={os.environ.get('GLU_SORT_PREFETCH', 'auto')} "
-          f"debug={os.environ.get('GLU_SORT_DEBUG_NO_LOOKBACK', '0')}")
-    if not int(os.environ.get("GLU_SORT_DEBUG_NO_LOOKBACK", "0")) & 1:
+          f"options={os.environ.get('GLU_SORT_OPTIONS', '0')}")
+    if not int(os.environ.get("GLU_SORT_OPTIONS", "0")) & 1:  # bit 0 = look-back skipped (timing experiment, wrong results)
         k64 = keys.to(torch.int64) & 0xFFFFFFFF
         assert bool((k64[1:] >= k64[:-1]).all()), "not sorted"
         del k64
