@@ -361,6 +361,7 @@ def run_b200(args):
 
     value = world * n * steps / (ms_total * 1e-3) / 1e9
     # roofline of the dominant kernel (onesweep pass): algorithmic 16 B per pair per launch
+    step_bytes = SORT_BYTES_PER_PAIR if world == 1 else SORT_BYTES_PER_PAIR + 4 + PASS_BYTES_PER_PAIR
     per_launch_ms = sweep_ms / max(1, sweep_launches)
     pairs_per_launch = n  # single GPU: every launch sweeps the whole array
     achieved = PASS_BYTES_PER_PAIR * pairs_per_launch / (per_launch_ms * 1e-3) / 1e9 if sweep_launches else None
@@ -371,9 +372,11 @@ def run_b200(args):
                 "kernel_share_of_step": sweep_ms / ms_total,
                 "histogram_ms_per_launch": hist_ms / max(1, hist_launches),
                 "partition_exchange_ms_per_launch": (part_ms / part_launches) if part_launches else None,
-                "whole_sort": {"bytes_per_pair": SORT_BYTES_PER_PAIR,
-                               "achieved_GB/s": SORT_BYTES_PER_PAIR * world * n * steps / (ms_total * 1e-3) / 1e9 / world,
-                               "frac": SORT_BYTES_PER_PAIR * n * steps / (ms_total * 1e-3) / 1e9 / peak}}
+                # per GPU and pair: the local sort's 68 B, plus at N > 1 the split-digit histogram (4 B) and the
+                # partition pass (8 B read, 8 B written to local or peer memory)
+                "whole_sort": {"bytes_per_pair": step_bytes,
+                               "achieved_GB/s": step_bytes * n * steps / (ms_total * 1e-3) / 1e9,
+                               "frac": step_bytes * n * steps / (ms_total * 1e-3) / 1e9 / peak}}
     traffic_file = os.path.join(ROOT, "profiles", "onesweep_traffic.json")
     if os.path.exists(traffic_file):
         try:
