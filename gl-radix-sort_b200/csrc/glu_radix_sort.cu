@@ -720,12 +720,15 @@ namespace glu_b200
             }
         }
 
+#include "glu_onesweep_ring.cuh"
+
         // ------------------------------------------------------------------------------------ host side
 
         struct SweepConfig
         {
             int id;
             int threads, ipt;
+            int ring = 0; // 1: onesweep_ring_kernel (persistent CTAs, two-deep key ring), 2: the same with RATOM
         };
         constexpr SweepConfig k_configs[] = {
             // {id, threads, keys per thread}: tile = threads * ipt
@@ -738,6 +741,17 @@ namespace glu_b200
             {6, 384, 16}, // 6144, 3 CTAs/SM
             {7, 320, 18}, // 5760, 4 CTAs/SM
             {8, 320, 24}, // 7680, 3 CTAs/SM with 64 registers per thread
+            // persistent ring kernel (glu_onesweep_ring.cuh): 12 B of shared memory per pair + the counters
+            {9, 320, 16, 1},  // 5120, 3 CTAs/SM
+            {10, 480, 16, 1}, // 7680, 2 CTAs/SM
+            {11, 512, 14, 1}, // 7168, 2 CTAs/SM
+            {12, 384, 20, 1}, // 7680, 2 CTAs/SM
+            {13, 416, 18, 1}, // 7488, 2 CTAs/SM
+            {14, 320, 16, 2}, // as 9..13 with the returning-atomic ranking loop
+            {15, 480, 16, 2},
+            {16, 512, 14, 2},
+            {17, 384, 20, 2},
+            {18, 416, 18, 2},
             // (4 CTAs/SM at 64 registers — 256 x 22 and 256 x 20 — measured 1.17 / 1.26 ms per pass against 1.09 ms:
             //  the per-tile fixed work, 256-digit scan + chain rows, outweighs the extra resident CTA)
         };
@@ -750,10 +764,11 @@ namespace glu_b200
         }
 
         // allow_forced = false: the flavoured kernels (glu_radix_sort_u32_ex) exist for the default shapes only
-        const SweepConfig& select_config(size_t count, bool allow_forced = true)
+        // allow_ring = false: callers whose count lives in device memory (*_dyn) keep the one-tile-per-CTA kernel
+        const SweepConfig& select_config(size_t count, bool allow_forced = true, bool allow_ring = true)
         {
             static const int forced = env_int("GLU_SORT_CONFIG", -1); // tuning sweeps only
-            if (allow_forced && forced >= 0 && forced < k_num_configs)
+            if (allow_forced && forced >= 0 && forced < k_num_configs && (allow_ring || !k_configs[forced].ring))
                 return k_configs[forced];
             if (count <= (size_t(1) << 18))
                 return k_configs[5];
@@ -781,9 +796,9 @@ namespace glu_b200
             size_t off_hist, off_lookback, off_keys, off_vals, total;
         };
 
-        TmpLayout make_layout(size_t count, bool with_values = true, bool allow_forced = true)
+        TmpLayout make_layout(size_t count, bool with_values = true, bool allow_forced = true, bool allow_ring = true)
         {
-            const SweepConfig& c = select_config(count, allow_forced);
+            const SweepConfig& c = select_config(count, allow_forced, allow_ring);
             TmpLayout l;
             const size_t tile = size_t(c.threads) * c.ipt;
             l.tiles = (count + tile - 1) / tile;
@@ -837,6 +852,47 @@ namespace glu_b200
             return GLU_SUCCESS;
         }
 
+
+        // onesweep_ring_kernel: a persistent grid — the chain CTAs plus as many tile CTAs as are resident at once
+        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, int RATOM, int FLAVOR = 0>
+        int launch_ring(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint32_t n, uint32_t shift,
+                        uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback, uint32_t* ticket, unsigned tiles,
+                        cudaStream_t s)
+        {
+            uint32_t* prefix = lookback + size_t(tiles) * k_radix;
+            auto kernel = onesweep_ring_kernel<THREADS, IPT, MIN_BLOCKS, MODE, RATOM, FLAVOR>;
+            const int allow_tma =
+                ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
+            constexpr size_t smem = sizeof(RingSmem<THREADS, IPT, (FLAVOR & k_flavor_keys_only) == 0>);
+            static const int chain_rows = env_int("GLU_SORT_CHAIN_ROWS", 8);
+            static const int options = env_int("GLU_SORT_OPTIONS", 0) & 0xff;
+            static std::atomic<int> resident[64]; // CTAs per SM the hardware really grants, per device (0 = not asked yet)
+            int dev = 0;
+            GLU_CUDA_TRY(cudaGetDevice(&dev));
+            if (dev >= 64)
+                return GLU_ERROR_INVALID_ARGUMENT;
+            int per_sm = resident[dev].load(std::memory_order_acquire);
+            if (per_sm == 0)
+            {
+                GLU_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+                GLU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
+                if (per_sm < 1)
+                    return GLU_ERROR_CUDA;
+                resident[dev].store(per_sm, std::memory_order_release);
+            }
+            const unsigned chain = chain_rows >= 100 ? 4 : 8;
+            const unsigned capacity = unsigned(current_sm_count()) * unsigned(per_sm);
+            // two tiles per ticket draw at start-up: no point in more CTAs than pairs of tiles
+            unsigned workers = capacity > chain ? capacity - chain : 1;
+            if (workers > (tiles + 1) / 2)
+                workers = (tiles + 1) / 2;
+            ScopedKernelProfile prof(GLU_KERNEL_SORT_ONESWEEP, s);
+            kernel<<<chain + workers, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix,
+                                                          ticket, tiles, allow_tma, chain_rows, options);
+            GLU_LAUNCH_CHECK();
+            return GLU_SUCCESS;
+        }
+
         template<int MODE>
         int dispatch_sweep(const SweepConfig& c, const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo,
                            uint32_t n, uint32_t shift, uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback,
@@ -854,6 +910,20 @@ namespace glu_b200
                 GLU_SWEEP_CASE(6, 384, 16, 3)
                 GLU_SWEEP_CASE(7, 320, 18, 4)
                 GLU_SWEEP_CASE(8, 320, 24, 3)
+#define GLU_RING_CASE(ID, T, I, B, A)                                                                                  \
+    case ID: /* never with d_n: select_config(.., allow_ring = false) */                                               \
+        return launch_ring<T, I, B, MODE, A>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+                GLU_RING_CASE(9, 320, 16, 3, 0)
+                GLU_RING_CASE(10, 480, 16, 2, 0)
+                GLU_RING_CASE(11, 512, 14, 2, 0)
+                GLU_RING_CASE(12, 384, 20, 2, 0)
+                GLU_RING_CASE(13, 416, 18, 2, 0)
+                GLU_RING_CASE(14, 320, 16, 3, 1)
+                GLU_RING_CASE(15, 480, 16, 2, 1)
+                GLU_RING_CASE(16, 512, 14, 2, 1)
+                GLU_RING_CASE(17, 384, 20, 2, 1)
+                GLU_RING_CASE(18, 416, 18, 2, 1)
+#undef GLU_RING_CASE
             default: return launch_sweep<256, 8, 4, MODE>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s, d_n);
 #undef GLU_SWEEP_CASE
             }
@@ -927,7 +997,9 @@ extern "C" size_t glu_radix_sort_u32kv_tmp_bytes(size_t count)
         return 0;
     if (count <= 1)
         return k_tmp_align;
-    return make_layout(count).total;
+    // enough for either kernel form: glu_radix_sort_u32kv_dyn keeps the one-tile-per-CTA tile shape
+    const size_t a = make_layout(count).total, b = make_layout(count, true, true, false).total;
+    return a > b ? a : b;
 }
 
 namespace
@@ -995,7 +1067,7 @@ int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* 
         return GLU_ERROR_COUNT_TOO_LARGE;
     if ((reinterpret_cast<uintptr_t>(d_keys) | reinterpret_cast<uintptr_t>(d_vals)) % sizeof(uint32_t) != 0)
         return GLU_ERROR_MISALIGNED;
-    const TmpLayout l = make_layout(count, with_values, !ex);
+    const TmpLayout l = make_layout(count, with_values, !ex, d_n == nullptr);
     if (!d_tmp || tmp_bytes < l.total)
         return GLU_ERROR_TMP_TOO_SMALL;
     if (reinterpret_cast<uintptr_t>(d_tmp) % k_tmp_align != 0)
@@ -1025,7 +1097,7 @@ int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* 
             return rc;
     }
 
-    const SweepConfig& cfg = select_config(count, !ex);
+    const SweepConfig& cfg = select_config(count, !ex, d_n == nullptr);
     const int mode = rank_mode();
     uint32_t* kbuf[2] = {d_keys, alt_keys};
     uint32_t* vbuf[2] = {d_vals, alt_vals};
