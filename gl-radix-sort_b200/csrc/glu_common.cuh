@@ -40,23 +40,21 @@ namespace glu_b200
 
     // Optional event bracketing of a launch (glu_profile_enable): construct before <<<>>>, destroyed after.
     extern std::atomic<int> g_profile_on;
-    void profile_begin(int kernel_id, cudaStream_t s);
-    void profile_end(int kernel_id, cudaStream_t s);
+    cudaEvent_t profile_begin(int kernel_id, cudaStream_t s); // returns the span's stop event
+    void profile_end(cudaEvent_t stop, cudaStream_t s);
     struct ScopedKernelProfile
     {
-        int id;
+        cudaEvent_t stop = nullptr;
         cudaStream_t s;
-        bool on;
-        ScopedKernelProfile(int kernel_id, cudaStream_t stream)
-            : id(kernel_id), s(stream), on(g_profile_on.load(std::memory_order_relaxed) != 0)
+        ScopedKernelProfile(int kernel_id, cudaStream_t stream) : s(stream)
         {
-            if (on)
-                profile_begin(id, s);
+            if (g_profile_on.load(std::memory_order_relaxed) != 0)
+                stop = profile_begin(kernel_id, s);
         }
         ~ScopedKernelProfile()
         {
-            if (on)
-                profile_end(id, s);
+            if (stop)
+                profile_end(stop, s);
         }
     };
 

@@ -7,13 +7,14 @@
 // stays resident and walks over tiles it draws from an atomic ticket, with a two-deep ring of KEY staging buffers:
 //
 //     iteration k (tile k's keys in keys[k & 1], its digit counts already in warp_hist, its keys already in registers)
-//       1. digit threads: tile totals -> PUBLISH the count row of tile k -> scan -> per-warp slot offsets
+//       1. digit threads: scan of the tile's digit counts -> per-warp slot offsets
 //       2. ranking warps: ballot match, keys straight to their tile-sorted slot (in place); each warp clears its
 //          own counter row when it is done with it
 //       3. values (bulk copy issued one iteration ago) -> registers; digit threads read ONE prefix row -> gbase;
 //          values -> tile-sorted slot (in place)
 //       4. EARLY COUNTS of tile k + 1: its keys (bulk copy issued one iteration ago into the other ring slot) go to
-//          registers and into the warp's counters — long before tile k + 1 is processed
+//          registers and into the warp's counters, and its count row is PUBLISHED — long before tile k + 1 is
+//          processed, and after tile k's look-back (chain_cta: prefix row t depends on count rows <= t only)
 //       5. tile k leaves: consecutive threads, consecutive addresses inside every digit run
 //       6. one thread refills: values of tile k + 1, keys of tile k + 2 (ticket drawn an iteration earlier), L2
 //          prefetch of the values of tile k + 2
@@ -46,7 +47,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     onesweep_ring_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                          uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, uint32_t shift,
                          uint32_t mask, const uint32_t* __restrict__ digit_offset, uint32_t* lookback, uint32_t* prefix,
-                         uint32_t* ticket, uint32_t num_tiles, int allow_tma, int chain_rows, int options)
+                         uint32_t* ticket, uint32_t num_tiles, int allow_tma, int chain_rows, int options,
+                         const uint32_t* __restrict__ d_n = nullptr)
 {
     static_assert(THREADS >= k_radix && THREADS % 32 == 0, "one thread per digit");
     static_assert(IPT % 2 == 0, "ranks are packed two per register");
@@ -63,6 +65,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t chain_ctas = chain_rows >= 100 ? 4u : 8u;
+    if (d_n)
+    {
+        // *_dyn entry points: the count is device-resident (<= the n the scratch was sized for)
+        n = __ldg(d_n);
+        num_tiles = (n + uint32_t(TILE) - 1) / uint32_t(TILE);
+    }
 
     for (int i = tid; i < WARPS * k_radix / 4; i += THREADS)
         reinterpret_cast<uint4*>(&s.warp_hist[0][0])[i] = make_uint4(0, 0, 0, 0);
@@ -173,8 +181,25 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         }
     };
 
+    // digit threads: the tile's digit counts summed over the warps, PUBLISHED for the chain CTAs at once
+    auto publish = [&](uint32_t t) -> uint32_t {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++)
+            tot += s.warp_hist[w][tid];
+        const uint32_t base = t * uint32_t(TILE);
+        const uint32_t valid_t = n - base < uint32_t(TILE) ? n - base : uint32_t(TILE);
+        // padding slots all carry the digit of the padding key
+        const uint32_t count_valid = tot - (tid == digit_of(PAD_KEY) ? uint32_t(TILE) - valid_t : 0u);
+        st_relaxed_u32(&lookback[size_t(t) * k_radix + tid], k_lb_local | count_valid);
+        return tot;
+    };
+
     load_and_count(0, cur);
     __syncthreads();
+    uint32_t total = 0; // digit threads: digit count of the current tile (padding included)
+    if (tid < k_radix)
+        total = publish(cur);
 
     for (uint32_t it = 0;; it++)
     {
@@ -186,15 +211,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         const bool use_tma = tma_ok(tile);
         uint32_t* skeys = s.keys[b];
 
-        // ---- 1. per digit: tile count -> look-back publication; slot offsets of each warp
-        uint32_t total = 0, inc = 0;
+        // ---- 1. per digit: scan of the tile's digit counts; slot offsets of each warp
+        uint32_t inc = 0;
         if (tid < k_radix)
         {
-#pragma unroll
-            for (int w = 0; w < WARPS; w++)
-                total += s.warp_hist[w][tid];
-            const uint32_t count_valid = total - (tid == digit_of(PAD_KEY) ? uint32_t(TILE) - valid : 0u);
-            st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid], k_lb_local | count_valid);
             inc = total;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1)
@@ -306,13 +326,15 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 }
             }
         }
-        __syncthreads(); // tile-sorted keys and values, gbase
-
-        // ---- 4. early counts of the next tile (its keys stay in registers until iteration it + 1 ranks them)
+        // ---- 4. early counts of the next tile (its keys stay in registers until iteration it + 1 ranks them),
+        //         published right away: its successors' look-back never waits for this CTA to get there
         const uint32_t nxt = s.tile_of[b ^ 1u];
         const bool has_next = nxt < num_tiles;
         if (has_next)
             load_and_count(b ^ 1u, nxt);
+        __syncthreads(); // tile-sorted keys and values, gbase; the next tile's counts
+        if (has_next && tid < k_radix)
+            total = publish(nxt);
 
         // ---- 5. out: consecutive threads write consecutive addresses inside each digit run
         if (full)
@@ -346,7 +368,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         }
         if (!has_next)
             break;
-        __syncthreads(); // the tile has left shared memory; the next tile's counts are final
+        __syncthreads(); // the tile has left shared memory
 
         // ---- 6. refill: values of the next tile, keys of the tile after next
         if (tid == 0)

@@ -284,11 +284,11 @@ namespace glu_b200
         // ("count rows") of digits [32 * GROUPS * c, ...) into running prefixes ("prefix rows").  A group of WPG
         // warps owns 32 digits (one per lane) and walks the rows in batches of WPG * ROWS: warp w takes ROWS
         // consecutive rows of the batch, requests them all at once (late rows are asked for again TOGETHER: one L2
-        // round trip per polling round however many are late), sums them, takes the running total of everything
-        // before its rows from its predecessor warp through shared memory (a ring: warp 0 continues from the last
-        // warp of the previous batch), hands its own running total on, and only then writes its prefix rows.
-        // prefix[t] therefore depends on count rows <= t only — never on a later tile — and the next batch's
-        // requests are already in flight while this one is combined.
+        // round trip per polling round however many are late), takes the running total of everything before its
+        // rows from its predecessor warp through shared memory (a ring: warp 0 continues from the last warp of the
+        // previous batch), walks its rows in order — prefix row t is written the moment count rows <= t are known,
+        // so prefix[t] NEVER depends on a later tile (the ring kernel publishes tile t + 1's counts only after tile
+        // t's look-back) — and hands its own running total on.  The next batch's requests are in flight meanwhile.
         template<int WARPS, int ROWS, int GROUPS>
         __device__ __noinline__ void chain_cta(uint32_t* smem, uint32_t chain_id, const uint32_t* lookback,
                                                uint32_t* prefix, uint32_t num_tiles)
@@ -316,30 +316,11 @@ namespace glu_b200
 #pragma unroll
                 for (int j = 0; j < ROWS; j++)
                     p[j] = q[j];
-                while (true)
-                {
-                    uint32_t all = k_lb_local;
-#pragma unroll
-                    for (int j = 0; j < ROWS; j++)
-                        all &= p[j];
-                    if (all & k_lb_local)
-                        break;
-#pragma unroll
-                    for (int j = 0; j < ROWS; j++)
-                        if ((p[j] & k_lb_local) == 0)
-                            p[j] = ld_relaxed_u32(col + size_t(r0 + j) * k_radix);
-                }
+                // the next batch's rows are requested before this one is combined
 #pragma unroll
                 for (int j = 0; j < ROWS; j++)
                     q[j] = r0 + BATCH + j < num_tiles ? ld_relaxed_u32(col + size_t(r0 + BATCH + j) * k_radix) : k_lb_local;
-                uint32_t run = 0;
-#pragma unroll
-                for (int j = 0; j < ROWS; j++)
-                {
-                    run += p[j] & k_lb_value_mask;
-                    p[j] = run;
-                }
-                // running total of all rows before mine
+                // running total of all rows before mine (it depends on earlier rows only)
                 uint32_t in = 0;
                 if (w > 0 || batch > 0)
                 {
@@ -351,15 +332,27 @@ namespace glu_b200
                     __threadfence_block();
                     in = *const_cast<volatile uint32_t*>(&carry[pb & 1][g][pw][lane]);
                 }
-                *const_cast<volatile uint32_t*>(&carry[batch & 1][g][w][lane]) = in + run;
+                // my rows in order: prefix row r0 + j is written as soon as count rows <= r0 + j are known
+                uint32_t run = in;
+#pragma unroll
+                for (int j = 0; j < ROWS; j++)
+                {
+                    while ((p[j] & k_lb_local) == 0)
+                    {
+#pragma unroll
+                        for (int jj = j; jj < ROWS; jj++) // late rows are asked for again TOGETHER
+                            if ((p[jj] & k_lb_local) == 0)
+                                p[jj] = ld_relaxed_u32(col + size_t(r0 + jj) * k_radix);
+                    }
+                    run += p[j] & k_lb_value_mask;
+                    if (r0 + j < num_tiles)
+                        st_relaxed_u32(prefix + size_t(r0 + j) * k_radix + d, k_lb_inclusive | run);
+                }
+                *const_cast<volatile uint32_t*>(&carry[batch & 1][g][w][lane]) = run;
                 __threadfence_block();
                 __syncwarp();
                 if (lane == 0)
                     seq[g * WPG + w] = batch + 1;
-#pragma unroll
-                for (int j = 0; j < ROWS; j++)
-                    if (r0 + j < num_tiles)
-                        st_relaxed_u32(prefix + size_t(r0 + j) * k_radix + d, k_lb_inclusive | (in + p[j]));
             }
         }
 
@@ -515,6 +508,18 @@ namespace glu_b200
                 __syncthreads();
             }
 
+            // what item i of this thread is partitioned by.  DEST: the padding slots of the partial last tile get the
+            // largest destination id whatever dest_lut holds, so they rank after every real pair of the tile (a
+            // non-monotone table must not move them into the middle of the tile-sorted order)
+            constexpr uint32_t PAD_DEST = 15u;
+            auto digit_at = [&](int i, uint32_t k) -> uint32_t {
+                if constexpr (DEST)
+                    return (full || my_off + uint32_t(i) * 32u < valid) ? digit_of(k) : PAD_DEST;
+                else
+                    return digit_of(k);
+            };
+            const uint32_t pad_digit = DEST ? PAD_DEST : digit_of(PAD_KEY);
+
             // ---- early counts: the warp's digit histogram
             uint32_t key[IPT];
             uint32_t* wh = s.warp_hist[warp];
@@ -532,7 +537,7 @@ namespace glu_b200
 #pragma unroll
                     for (int i = 0; i < IPT; i++)
                     {
-                        const uint32_t d = digit_of(key[i]);
+                        const uint32_t d = digit_at(i, key[i]);
                         const uint32_t peers = match_low4(d);
                         if ((peers & lt_) == 0)
                             atomicAdd(&wh[d], uint32_t(__popc(peers)));
@@ -576,7 +581,7 @@ namespace glu_b200
                 for (int w = 0; w < WARPS; w++)
                     total += s.warp_hist[w][tid];
                 // padding slots all carry the digit of the padding key
-                const uint32_t count_valid = total - (tid == digit_of(PAD_KEY) ? uint32_t(TILE) - valid : 0u);
+                const uint32_t count_valid = total - (tid == pad_digit ? uint32_t(TILE) - valid : 0u);
                 st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid], k_lb_local | count_valid);
                 inc = total;
 #pragma unroll
@@ -614,7 +619,7 @@ namespace glu_b200
 #pragma unroll
                 for (int i = 0; i < IPT; i++)
                 {
-                    const uint32_t d = digit_of(key[i]);
+                    const uint32_t d = digit_at(i, key[i]);
                     const uint32_t peers = DEST ? match_low4(d) : match_digit<MODE>(d);
                     const uint32_t before = wh[d];
                     __syncwarp();
@@ -652,9 +657,12 @@ namespace glu_b200
                     }
                     if constexpr (PEER)
                     {
+                        // only table entries that can be a destination are read: 1 << bits pointers (by digit) or
+                        // the first 16 (by destination id) — include/glu_b200.h
                         const ptrdiff_t off = ptrdiff_t(exclusive) - ptrdiff_t(s.tile_start[tid]);
-                        s.dst.key[tid] = key_dst[tid] + off;
-                        s.dst.val[tid] = val_dst[tid] + off;
+                        const bool in_table = DEST ? tid <= PAD_DEST : tid <= mask;
+                        s.dst.key[tid] = in_table ? key_dst[tid] + off : nullptr;
+                        s.dst.val[tid] = in_table ? val_dst[tid] + off : nullptr;
                     }
                     else
                         s.gbase[tid] = digit_offset[tid] + exclusive - s.tile_start[tid];
@@ -763,12 +771,19 @@ namespace glu_b200
             return v && *v ? std::atoi(v) : fallback;
         }
 
+        // GLU_SORT_CHAIN_ROWS: rows per lane of a chain batch (2, 4, 8), +100 = 64 digits per chain CTA (4 chain CTAs
+        // instead of 8).  Anything else would pair a chain shape with the wrong number of chain CTAs: default.
+        int chain_rows_env()
+        {
+            static const int v = env_int("GLU_SORT_CHAIN_ROWS", 8);
+            return (v == 2 || v == 4 || v == 8 || v == 104 || v == 108) ? v : 8;
+        }
+
         // allow_forced = false: the flavoured kernels (glu_radix_sort_u32_ex) exist for the default shapes only
-        // allow_ring = false: callers whose count lives in device memory (*_dyn) keep the one-tile-per-CTA kernel
-        const SweepConfig& select_config(size_t count, bool allow_forced = true, bool allow_ring = true)
+        const SweepConfig& select_config(size_t count, bool allow_forced = true)
         {
             static const int forced = env_int("GLU_SORT_CONFIG", -1); // tuning sweeps only
-            if (allow_forced && forced >= 0 && forced < k_num_configs && (allow_ring || !k_configs[forced].ring))
+            if (allow_forced && forced >= 0 && forced < k_num_configs)
                 return k_configs[forced];
             if (count <= (size_t(1) << 18))
                 return k_configs[5];
@@ -796,9 +811,9 @@ namespace glu_b200
             size_t off_hist, off_lookback, off_keys, off_vals, total;
         };
 
-        TmpLayout make_layout(size_t count, bool with_values = true, bool allow_forced = true, bool allow_ring = true)
+        TmpLayout make_layout(size_t count, bool with_values = true, bool allow_forced = true)
         {
-            const SweepConfig& c = select_config(count, allow_forced, allow_ring);
+            const SweepConfig& c = select_config(count, allow_forced);
             TmpLayout l;
             const size_t tile = size_t(c.threads) * c.ipt;
             l.tiles = (count + tile - 1) / tile;
@@ -825,7 +840,7 @@ namespace glu_b200
             const int allow_tma =
                 ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
             constexpr size_t smem = sizeof(SweepSmem<THREADS, IPT, PEER, (FLAVOR & k_flavor_keys_only) == 0>);
-            static const int chain_rows = env_int("GLU_SORT_CHAIN_ROWS", 8);
+            const int chain_rows = chain_rows_env();
             // bit 0: skip the look-back (timing experiments, wrong results); bit 1: tile ids from an atomic ticket
             // bits 8..: L2 prefetch distance in tiles (GLU_SORT_PREFETCH; 0 = off).  Default: one tile per SM ahead —
             // a third of the resident wave at 3 CTAs per SM; 74..444 measured within 1 % of each other at 2^28,
@@ -834,15 +849,15 @@ namespace glu_b200
             const int prefetch_tiles = prefetch_env >= 0 ? (prefetch_env > 0xffff ? 0xffff : prefetch_env) : current_sm_count();
             static const int options_env = env_int("GLU_SORT_OPTIONS", 0) & 0xff;
             const int options = options_env | (prefetch_tiles << 8);
-            static bool configured[64] = {};
+            static std::atomic<bool> configured[64]; // per device; set after the attribute call (idempotent, so a race only repeats it)
             int dev = 0;
             GLU_CUDA_TRY(cudaGetDevice(&dev));
             if (dev >= 64)
                 return GLU_ERROR_INVALID_ARGUMENT;
-            if (!configured[dev])
+            if (!configured[dev].load(std::memory_order_acquire))
             {
                 GLU_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-                configured[dev] = true;
+                configured[dev].store(true, std::memory_order_release);
             }
             const unsigned grid = tiles + (chain_rows >= 100 ? 4 : 8);
             ScopedKernelProfile prof(PEER ? GLU_KERNEL_SORT_PARTITION : GLU_KERNEL_SORT_ONESWEEP, s);
@@ -857,14 +872,14 @@ namespace glu_b200
         template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, int RATOM, int FLAVOR = 0>
         int launch_ring(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint32_t n, uint32_t shift,
                         uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback, uint32_t* ticket, unsigned tiles,
-                        cudaStream_t s)
+                        cudaStream_t s, const uint32_t* d_n = nullptr)
         {
             uint32_t* prefix = lookback + size_t(tiles) * k_radix;
             auto kernel = onesweep_ring_kernel<THREADS, IPT, MIN_BLOCKS, MODE, RATOM, FLAVOR>;
             const int allow_tma =
                 ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
             constexpr size_t smem = sizeof(RingSmem<THREADS, IPT, (FLAVOR & k_flavor_keys_only) == 0>);
-            static const int chain_rows = env_int("GLU_SORT_CHAIN_ROWS", 8);
+            const int chain_rows = chain_rows_env();
             static const int options = env_int("GLU_SORT_OPTIONS", 0) & 0xff;
             static std::atomic<int> resident[64]; // CTAs per SM the hardware really grants, per device (0 = not asked yet)
             int dev = 0;
@@ -888,7 +903,7 @@ namespace glu_b200
                 workers = (tiles + 1) / 2;
             ScopedKernelProfile prof(GLU_KERNEL_SORT_ONESWEEP, s);
             kernel<<<chain + workers, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix,
-                                                          ticket, tiles, allow_tma, chain_rows, options);
+                                                          ticket, tiles, allow_tma, chain_rows, options, d_n);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
@@ -911,8 +926,8 @@ namespace glu_b200
                 GLU_SWEEP_CASE(7, 320, 18, 4)
                 GLU_SWEEP_CASE(8, 320, 24, 3)
 #define GLU_RING_CASE(ID, T, I, B, A)                                                                                  \
-    case ID: /* never with d_n: select_config(.., allow_ring = false) */                                               \
-        return launch_ring<T, I, B, MODE, A>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s);
+    case ID:                                                                                                           \
+        return launch_ring<T, I, B, MODE, A>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, ticket, tiles, s, d_n);
                 GLU_RING_CASE(9, 320, 16, 3, 0)
                 GLU_RING_CASE(10, 480, 16, 2, 0)
                 GLU_RING_CASE(11, 512, 14, 2, 0)
@@ -972,16 +987,16 @@ namespace
         const size_t cap = size_t(sms) * k_hist_blocks_per_sm;
         grid = grid < 1 ? 1 : (grid > cap ? cap : grid);
         const size_t smem = size_t(num_passes) * k_radix * k_hist_copies * sizeof(uint32_t);
-        static bool configured[64] = {};
+        static std::atomic<bool> configured[64]; // per device; set after the attribute call (idempotent, so a race only repeats it)
         int dev = 0;
         GLU_CUDA_TRY(cudaGetDevice(&dev));
         if (dev >= 64)
             return GLU_ERROR_INVALID_ARGUMENT;
-        if (!configured[dev])
+        if (!configured[dev].load(std::memory_order_acquire))
         {
             GLU_CUDA_TRY(cudaFuncSetAttribute(histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               int(k_max_passes * k_radix * k_hist_copies * sizeof(uint32_t))));
-            configured[dev] = true;
+            configured[dev].store(true, std::memory_order_release);
         }
         ScopedKernelProfile prof(GLU_KERNEL_SORT_HISTOGRAM, s);
         histogram_kernel<<<unsigned(grid), k_hist_threads, smem, s>>>(d_keys, n, d_n, head, num_passes, pre_shift,
@@ -997,9 +1012,7 @@ extern "C" size_t glu_radix_sort_u32kv_tmp_bytes(size_t count)
         return 0;
     if (count <= 1)
         return k_tmp_align;
-    // enough for either kernel form: glu_radix_sort_u32kv_dyn keeps the one-tile-per-CTA tile shape
-    const size_t a = make_layout(count).total, b = make_layout(count, true, true, false).total;
-    return a > b ? a : b;
+    return make_layout(count).total;
 }
 
 namespace
@@ -1067,7 +1080,7 @@ int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* 
         return GLU_ERROR_COUNT_TOO_LARGE;
     if ((reinterpret_cast<uintptr_t>(d_keys) | reinterpret_cast<uintptr_t>(d_vals)) % sizeof(uint32_t) != 0)
         return GLU_ERROR_MISALIGNED;
-    const TmpLayout l = make_layout(count, with_values, !ex, d_n == nullptr);
+    const TmpLayout l = make_layout(count, with_values, !ex);
     if (!d_tmp || tmp_bytes < l.total)
         return GLU_ERROR_TMP_TOO_SMALL;
     if (reinterpret_cast<uintptr_t>(d_tmp) % k_tmp_align != 0)
@@ -1097,7 +1110,7 @@ int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* 
             return rc;
     }
 
-    const SweepConfig& cfg = select_config(count, !ex, d_n == nullptr);
+    const SweepConfig& cfg = select_config(count, !ex);
     const int mode = rank_mode();
     uint32_t* kbuf[2] = {d_keys, alt_keys};
     uint32_t* vbuf[2] = {d_vals, alt_vals};

@@ -169,8 +169,8 @@ namespace glu_b200
         // n_scalars : count * NCOMP
         template<typename S, int NCOMP, int OP, int THREADS, int UNROLL>
         __global__ void __launch_bounds__(THREADS)
-            reduce_kernel(const S* __restrict__ data, S* __restrict__ out, size_t n_scalars, unsigned head, size_t n_units,
-                          S* partials, unsigned* ticket)
+            reduce_kernel(const S* data, S* out, // no __restrict__: out == data for the in-place glu_reduce
+                          size_t n_scalars, unsigned head, size_t n_units, S* partials, unsigned* ticket)
         {
             using Opr = Operator<S, OP>;
             constexpr int L = Unit<S>::L;

@@ -40,23 +40,21 @@ namespace glu_b200
         }
     } // namespace
 
-    void profile_begin(int kernel_id, cudaStream_t s)
+    // returns the span's stop event: the caller records it after its launch (ScopedKernelProfile), so spans opened
+    // concurrently on two streams — or by two threads — can never be paired with each other's launches
+    cudaEvent_t profile_begin(int kernel_id, cudaStream_t s)
     {
         std::lock_guard<std::mutex> lock(g_profile_mutex);
         ProfileSpan span{kernel_id, profile_event(), profile_event()};
         cudaEventRecord(span.start, s);
         g_profile_spans.push_back(span);
+        return span.stop;
     }
 
-    void profile_end(int kernel_id, cudaStream_t s)
+    void profile_end(cudaEvent_t stop, cudaStream_t s)
     {
-        std::lock_guard<std::mutex> lock(g_profile_mutex);
-        for (size_t i = g_profile_spans.size(); i-- > 0;)
-            if (g_profile_spans[i].id == kernel_id)
-            {
-                cudaEventRecord(g_profile_spans[i].stop, s);
-                break;
-            }
+        if (stop)
+            cudaEventRecord(stop, s);
     }
 
     int current_sm_count()
@@ -290,8 +288,11 @@ extern "C"
     {
         if (!stream)
             return GLU_ERROR_INVALID_ARGUMENT;
+        // a BLOCKING stream: the legacy default stream (what glu::DeviceBuffer's upload / download / clear use,
+        // include/glu/device_utils.hpp) synchronises with it, so get_data() after a call enqueued on this stream
+        // returns that call's result, as a GL buffer read-back after a dispatch does
         cudaStream_t s;
-        GLU_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        GLU_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamDefault));
         *stream = s;
         return GLU_SUCCESS;
     }

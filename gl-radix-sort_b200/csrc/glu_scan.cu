@@ -895,17 +895,17 @@ namespace glu_b200
         {
             auto kernel = scan_b32_tma_kernel<T, THREADS, VPT, STAGES>;
             constexpr size_t smem = size_t(STAGES) * THREADS * VPT * 16;
-            static bool configured[64] = {};
+            static std::atomic<bool> configured[64]; // per device; set after the attribute call (idempotent, so a race only repeats it)
             static int ctas_per_sm[64] = {};
             int dev = 0;
             GLU_CUDA_TRY(cudaGetDevice(&dev));
             if (dev >= 64)
                 return GLU_ERROR_INVALID_ARGUMENT;
-            if (!configured[dev])
+            if (!configured[dev].load(std::memory_order_acquire))
             {
                 GLU_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
                 GLU_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm[dev], kernel, THREADS + 128, smem));
-                configured[dev] = true;
+                configured[dev].store(true, std::memory_order_release);
             }
             const uint64_t resident = uint64_t(current_sm_count()) * uint64_t(ctas_per_sm[dev] > 0 ? ctas_per_sm[dev] : 1);
             const unsigned grid = unsigned(p.total_tiles < resident ? p.total_tiles : resident);

@@ -270,6 +270,7 @@ class DistributedRadixSort:
         self.last_plan = None
         self._last_hist = None
         self.timing = None  # set to a dict to get per-phase wall times in ms (synchronises after every phase)
+        self._closed = False
 
     # -- peer mappings (CUDA IPC): rank g's receive buffers mapped into this process
     def _setup_exchange(self, exchange: str) -> str:
@@ -473,6 +474,38 @@ class DistributedRadixSort:
         m = int(info[world])
         return rk[:m], rv[:m], m
 
+    def close(self, collective: bool = True) -> None:
+        """Release the receive arrays and the CUDA IPC mappings of the peers' arrays.  Collective by default: a barrier
+        first, so that no rank unmaps or frees memory a peer's partition pass may still be writing to."""
+        if getattr(self, "_closed", True):
+            return
+        self._closed = True
+        glu = _glu()
+        try:
+            import torch
+
+            torch.cuda.synchronize(self.device)
+            if collective:
+                _dist().barrier(group=self.group)
+        except Exception:  # pragma: no cover - interpreter shutdown / process group already destroyed
+            pass
+        if self._peer_keys is not None:
+            for g in range(self.world):
+                if g != self.rank:
+                    glu.lib.glu_ipc_close_handle(ctypes.c_void_p(int(self._peer_keys[g])))
+                    glu.lib.glu_ipc_close_handle(ctypes.c_void_p(int(self._peer_vals[g])))
+            self._peer_keys = self._peer_vals = None
+        self._recv_keys.free()
+        self._recv_vals.free()
+        self._sorter = None
+        self._part_tmp = None
+
+    def __del__(self):
+        try:
+            self.close(collective=False)
+        except Exception:  # pragma: no cover
+            pass
+
     def plan_of_last_call(self) -> ExchangePlan:
         """The exchange plan of the last call (host restatement of what the device computed, for inspection/tests)."""
         if self.last_plan is None and self._last_hist is not None:
@@ -585,3 +618,11 @@ class DistributedSortPipeline:
         cur = torch.cuda.current_stream(self.device)
         cur.wait_stream(self.stream_x)
         cur.wait_stream(self.stream_s)
+
+    def close(self) -> None:
+        """Collective: releases both lanes (receive arrays, peer mappings)."""
+        import torch
+
+        torch.cuda.synchronize(self.device)
+        for lane in self.lanes:
+            lane.close()

@@ -126,7 +126,9 @@ namespace glu
             GLU_CHECK_STATUS(glu_stream_synchronize(nullptr));
         }
 
-        /// Downloads the whole buffer (synchronises with the default stream first).
+        /// Downloads the whole buffer.  Uploads, downloads and clears run on the legacy default stream, which is
+        /// ordered with every stream made by glu_stream_create (blocking streams) — the stream `set_stream` takes.
+        /// Work enqueued on a cudaStreamNonBlocking stream of the caller's own must be synchronised by the caller.
         template<typename T> std::vector<T> get_data() const
         {
             GLU_CHECK_ARGUMENT(m_size % sizeof(T) == 0, "Size %zu isn't a multiple of %zu", m_size, sizeof(T));

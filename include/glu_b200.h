@@ -194,7 +194,8 @@ GLU_API int glu_radix_partition_u32kv(const uint32_t* d_keys, const uint32_t* d_
 
 /* The same pass partitioning by DESTINATION instead of by digit: the i-th pair whose digit maps to destination
  * g = d_dest_of_digit[digit] (a device array of 256 bytes, every g < 16) goes to d_key_dst[g][i] / d_val_dst[g][i].
- * d_key_dst / d_val_dst are device arrays of 256 pointers of which only the first max(g)+1 are read.  A tile then
+ * d_key_dst / d_val_dst are device arrays of at least 16 pointers: the first 16 entries are read, only the first
+ * max(g)+1 are dereferenced.  d_dest_of_digit need not be monotone (padding of the last tile never depends on it).  A tile then
  * leaves the SM as a few long runs (tile / #destinations pairs each) instead of 256 short ones, which is what
  * remote stores over NVLink need to run near link speed: the fused partition + all-to-all of the multi-GPU sort. */
 GLU_API int glu_radix_partition_by_dest_u32kv(const uint32_t* d_keys, const uint32_t* d_vals, size_t count,
@@ -272,7 +273,7 @@ GLU_API int glu_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, glu_str
 GLU_API int glu_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, glu_stream_t stream);
 GLU_API int glu_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, glu_stream_t stream);
 GLU_API int glu_memset_u32(void* d_dst, uint32_t value, size_t count, glu_stream_t stream);
-GLU_API int glu_stream_create(glu_stream_t* stream);
+GLU_API int glu_stream_create(glu_stream_t* stream); /* a blocking stream: ordered with the legacy default stream */
 GLU_API int glu_stream_destroy(glu_stream_t stream);
 GLU_API int glu_stream_synchronize(glu_stream_t stream);
 GLU_API int glu_event_create(glu_event_t* event);

@@ -94,6 +94,61 @@ def test_radix_partition_by_dest_matches_stable_partition(glu, cuda_device, orac
     np.testing.assert_array_equal(to_host(ov, np.uint32), vals[order])
 
 
+@pytest.mark.parametrize("n", [33, 7681, 200_003])
+def test_radix_partition_by_dest_non_monotone_table_and_16_pointers(glu, cuda_device, oracle, n):
+    """The destination table need not be monotone (the padding slots of the partial last tile must not depend on it),
+    and only the first 16 entries of the pointer tables are read (include/glu_b200.h)."""
+    import torch
+
+    keys = oracle.mt19937_u32(9, n)
+    vals = np.arange(n, dtype=np.uint32)
+    ndest = 5
+    lut = ((np.arange(256) * 7 + 3) % ndest).astype(np.uint8)  # scrambled: lut[255] is not the largest destination
+    assert lut[255] != ndest - 1
+    to = lut[(keys >> 24) & 0xFF]
+    counts = np.bincount(to, minlength=ndest).astype(np.int64)
+    offs = np.cumsum(counts) - counts
+    dk, dv = to_device(keys, cuda_device), to_device(vals, cuda_device)
+    ok = torch.zeros(n, dtype=torch.int32, device=cuda_device)
+    ov = torch.zeros(n, dtype=torch.int32, device=cuda_device)
+    ktab = torch.from_numpy(np.concatenate([ok.data_ptr() + 4 * offs, np.zeros(16 - ndest, np.int64)])).to(cuda_device)
+    vtab = torch.from_numpy(np.concatenate([ov.data_ptr() + 4 * offs, np.zeros(16 - ndest, np.int64)])).to(cuda_device)
+    dlut = torch.from_numpy(lut.copy()).to(cuda_device)
+    tmp = torch.empty(int(glu.lib.glu_radix_partition_u32kv_tmp_bytes(n)), dtype=torch.uint8, device=cuda_device)
+    glu.check(glu.lib.glu_radix_partition_by_dest_u32kv(dk.data_ptr(), dv.data_ptr(), n, 24, 8, dlut.data_ptr(),
+                                                        ktab.data_ptr(), vtab.data_ptr(), tmp.data_ptr(), tmp.numel(),
+                                                        _stream(cuda_device)), "partition_by_dest")
+    torch.cuda.synchronize()
+    order = np.argsort(to, kind="stable")
+    np.testing.assert_array_equal(to_host(ok, np.uint32), keys[order])
+    np.testing.assert_array_equal(to_host(ov, np.uint32), vals[order])
+
+
+def test_radix_partition_short_pointer_table(glu, cuda_device, oracle):
+    """glu_radix_partition_u32kv with bits < 8 reads only 1 << bits pointers (include/glu_b200.h)."""
+    import torch
+
+    n, shift, bits = 100_003, 29, 3
+    keys = oracle.mt19937_u32(10, n)
+    vals = np.arange(n, dtype=np.uint32)
+    digit = (keys >> shift) & ((1 << bits) - 1)
+    counts = np.bincount(digit, minlength=1 << bits).astype(np.int64)
+    offs = np.cumsum(counts) - counts
+    dk, dv = to_device(keys, cuda_device), to_device(vals, cuda_device)
+    ok = torch.zeros(n, dtype=torch.int32, device=cuda_device)
+    ov = torch.zeros(n, dtype=torch.int32, device=cuda_device)
+    ktab = torch.from_numpy(ok.data_ptr() + 4 * offs).to(cuda_device)  # exactly 8 pointers
+    vtab = torch.from_numpy(ov.data_ptr() + 4 * offs).to(cuda_device)
+    tmp = torch.empty(int(glu.lib.glu_radix_partition_u32kv_tmp_bytes(n)), dtype=torch.uint8, device=cuda_device)
+    glu.check(glu.lib.glu_radix_partition_u32kv(dk.data_ptr(), dv.data_ptr(), n, shift, bits, ktab.data_ptr(),
+                                                vtab.data_ptr(), tmp.data_ptr(), tmp.numel(), _stream(cuda_device)),
+              "partition")
+    torch.cuda.synchronize()
+    order = np.argsort(digit, kind="stable")
+    np.testing.assert_array_equal(to_host(ok, np.uint32), keys[order])
+    np.testing.assert_array_equal(to_host(ov, np.uint32), vals[order])
+
+
 def test_reduce_into_leaves_the_data_alone(glu, cuda_device, oracle):
     import torch
 
@@ -202,6 +257,41 @@ for exchange in os.environ["GLU_EXCHANGES"].split(","):
             assert np.array_equal(gk, ek), f"{exchange}/{kind}: keys differ"
             assert np.array_equal(gv, ev), f"{exchange}/{kind}: values differ (stability across ranks)"
         dist.barrier()
+    sorter_fixed.close()
+    sorter_auto.close()
+
+# ---- the two-lane pipeline (DistributedSortPipeline): consecutive independent jobs, the exchange of job k+1 runs under
+# the local sort of job k; every job's result must equal std::stable_sort of the concatenated inputs
+pipe = glu.DistributedSortPipeline(400_000, capacity_factor=2.5)
+jobs, pending = [], []
+
+def check_job(j, ticket):
+    sk, sv, m = pipe.result(ticket)
+    keys, vals = jobs[j][0], jobs[j][1]
+    res = gather((keys, vals, sk.cpu().numpy().view(np.uint32), sv.cpu().numpy().view(np.uint32)))
+    if rank == 0:
+        allk = np.concatenate([r[0] for r in res]); allv = np.concatenate([r[1] for r in res])
+        gk = np.concatenate([r[2] for r in res]); gv = np.concatenate([r[3] for r in res])
+        ek, ev = oracle.stable_sort_pairs(allk, allv)
+        assert np.array_equal(gk, ek), f"pipeline job {j}: keys differ"
+        assert np.array_equal(gv, ev), f"pipeline job {j}: values differ"
+
+for j in range(5):
+    n = 250_003 + 977 * rank + 1000 * j
+    keys = oracle.mt19937_u32(60 + 10 * j + rank, n)
+    if j == 3:
+        keys = keys & np.uint32(0xFF0000FF)  # heavy duplicates inside every bucket
+    sizes = gather(n)
+    base = sum(sizes[:rank])
+    vals = np.arange(base, base + n, dtype=np.uint32)
+    dk, dv = up(keys), up(vals)
+    jobs.append((keys, vals, dk, dv))
+    pending.append((j, pipe.submit(dk, dv, n)))
+    if len(pending) == 2:
+        check_job(*pending.pop(0))
+while pending:
+    check_job(*pending.pop(0))
+pipe.close()
 
 # ---- reduce / scan sharded by contiguous ranges
 n = 1_000_003 + 31 * rank

@@ -133,6 +133,37 @@ def test_reduce_integer_vectors(glu, cuda_device, oracle, dt_name, np_dtype, nco
     assert [int(x) for x in got] == [int(x) for x in want]
 
 
+def test_reduce_float_full_size_2_28(glu, cuda_device):
+    """BASELINE configs[4]: Reduce(Float, Sum / Min / Max) over 2^28 uniform floats in [-1, 1).  Min / Max bit-exact
+    against the device's own exact min / max (torch = plumbing; min / max are order-independent), Sum within
+    1e-5 * sum|x| of a float64 accumulation of the same data — the tolerance convention of
+    test/reduce_tests.cpp:72 (absolute 0.1 on sums of ~1e2) scaled to the size."""
+    import torch
+
+    n = 1 << 28
+    g = torch.Generator(device=cuda_device).manual_seed(17)
+    data = torch.rand(n, dtype=torch.float32, device=cuda_device, generator=g) * 2.0 - 1.0
+    want_sum = float(data.sum(dtype=torch.float64).item())
+    abs_sum = float(data.abs().sum(dtype=torch.float64).item())
+    want_min, want_max = data.min(), data.max()
+    for op, want in ((glu.ReduceOperator_Min, want_min), (glu.ReduceOperator_Max, want_max)):
+        work = data.clone()
+        glu.Reduce(glu.DataType_Float, op)(work, n)
+        torch.cuda.synchronize()
+        assert work[0].view(torch.int32).item() == want.view(torch.int32).item(), (int(op), work[0].item(), want.item())
+    work = data.clone()
+    glu.Reduce(glu.DataType_Float, glu.ReduceOperator_Sum)(work, n)
+    torch.cuda.synchronize()
+    got = float(work[0].item())
+    tol = 1e-5 * abs_sum
+    assert abs(got - want_sum) <= tol, (got, want_sum, tol)
+    # run-to-run determinism at size (fixed combination order)
+    again = data.clone()
+    glu.Reduce(glu.DataType_Float, glu.ReduceOperator_Sum)(again, n)
+    torch.cuda.synchronize()
+    assert again[0].view(torch.int32).item() == work[0].view(torch.int32).item()
+
+
 def test_reduce_float_sum_is_deterministic(glu, cuda_device):
     rng = np.random.default_rng(3)
     data = rng.uniform(-1.0, 1.0, size=1 << 22).astype(np.float32)

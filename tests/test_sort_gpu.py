@@ -203,6 +203,59 @@ def test_sort_full_size_2_28(glu, cuda_device, oracle):
     np.testing.assert_array_equal(to_host(dv, np.uint32), ev)
 
 
+@pytest.mark.parametrize("kind", ["zipf", "entropy16_low", "entropy16_high", "all_equal"])
+def test_sort_skewed_full_size_2_28(glu, cuda_device, oracle, kind):
+    """BASELINE configs[4] at the stated size: Zipf(1.1) over 2^20 distinct keys, 16-bit-entropy keys (low half and
+    shifted into the top digit), all-equal keys; 2^28 pairs, values = input index.  Same on-device property checks as
+    test_sort_full_size_2_28 (sorted, stable, it is the permutation it claims, values are a permutation) plus exact
+    oracle parity of a separately sorted 2^24-pair slice of the same data."""
+    import torch
+
+    n = 1 << 28
+    g = torch.Generator(device=cuda_device).manual_seed(11)
+    if kind == "zipf":
+        ranks = torch.arange(1, (1 << 20) + 1, dtype=torch.float64, device=cuda_device)
+        cdf = torch.cumsum(ranks.pow(-1.1), 0)
+        cdf /= cdf[-1].clone()
+        keys = torch.empty(n, dtype=torch.int32, device=cuda_device)
+        for i in range(0, n, 1 << 26):  # inverse-CDF sampling, chunked (float64 temporaries)
+            u = torch.rand(1 << 26, dtype=torch.float64, device=cuda_device, generator=g)
+            keys[i:i + (1 << 26)] = torch.searchsorted(cdf, u).to(torch.int32)
+        del ranks, cdf, u
+    elif kind == "entropy16_low":
+        keys = torch.randint(0, 1 << 16, (n,), dtype=torch.int32, device=cuda_device, generator=g)
+    elif kind == "entropy16_high":
+        keys = torch.randint(0, 1 << 16, (n,), dtype=torch.int32, device=cuda_device, generator=g) << 16
+    else:
+        keys = torch.full((n,), -559038737, dtype=torch.int32, device=cuda_device)  # 0xDEADBEEF
+    vals = torch.arange(n, dtype=torch.int32, device=cuda_device)
+    dk, dv = keys.clone(), vals.clone()
+    glu.RadixSort()(dk, dv, n)
+    torch.cuda.synchronize()
+    ok = True
+    chunk = 1 << 26
+    for i in range(0, n, chunk):
+        j = min(n, i + chunk + 1)
+        k64 = dk[i:j].to(torch.int64) & 0xFFFFFFFF
+        v64 = dv[i:j].to(torch.int64)
+        ok &= bool((k64[1:] >= k64[:-1]).all())
+        ok &= bool(((k64[1:] > k64[:-1]) | (v64[1:] > v64[:-1])).all())  # stability
+        ok &= bool(torch.equal(keys[dv[i:j].to(torch.int64)], dk[i:j]))
+        del k64, v64
+    assert ok, kind
+    assert int(dv.sum(dtype=torch.int64).item()) == n * (n - 1) // 2
+    del dk, dv
+    m = 1 << 24
+    lo = n // 3  # a slice from the middle of the data
+    hk = to_host(keys[lo:lo + m], np.uint32).copy()
+    hv = np.arange(m, dtype=np.uint32)
+    dk, dv = keys[lo:lo + m].clone(), vals[:m].clone()
+    glu.RadixSort()(dk, dv, m)
+    ek, ev = oracle.lsd_sort_pairs(hk, hv)
+    np.testing.assert_array_equal(to_host(dk, np.uint32), ek)
+    np.testing.assert_array_equal(to_host(dv, np.uint32), ev)
+
+
 def test_sort_host_entry_point(glu, cuda_device, oracle):
     keys = oracle.mt19937_u32(12, 300_000)
     vals = np.arange(keys.size, dtype=np.uint32)
