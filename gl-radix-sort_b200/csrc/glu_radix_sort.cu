@@ -681,7 +681,32 @@ namespace glu_b200
             __syncthreads(); // tile-sorted keys and values, gbase
 
             // ---- out: consecutive threads write consecutive addresses inside each digit run
-            if (full)
+            if constexpr (DEST)
+            {
+                // A tile leaves as <= 16 long runs, most of them to peer GPUs over NVLink.  Every warp-wide store is
+                // made to cover ONE 128-byte line of its destination (the window of 32 slots is shifted by the run's
+                // misalignment; only the first and last line of a run are partial): a line that straddles two warps'
+                // windows would cross the link as two byte-masked packets instead of one full one.
+                for (uint32_t d = 0; d <= PAD_DEST; d++)
+                {
+                    const uint32_t begin = s.tile_start[d];
+                    uint32_t end = s.tile_start[d + 1];
+                    end = end < valid ? end : valid; // padding slots rank last and are never written
+                    if (begin >= end)
+                        continue;
+                    uint32_t* const kdst = s.dst.key[d];
+                    uint32_t* const vdst = s.dst.val[d];
+                    const uint32_t shift32 = (uint32_t(reinterpret_cast<uintptr_t>(kdst) >> 2) + begin) & 31u;
+                    // slot p goes to kdst[p]; windows start at begin - shift32 (mod 2^32: the lanes before `begin` idle)
+                    for (uint32_t p = begin - shift32 + warp * 32u + lane; int32_t(p - end) < 0; p += uint32_t(WARPS) * 32u)
+                        if (int32_t(p - begin) >= 0)
+                        {
+                            kdst[p] = s.keys[p];
+                            vdst[p] = s.vals[p];
+                        }
+                }
+            }
+            else if (full)
             {
 #pragma unroll
                 for (int k = 0; k < IPT; k++)
@@ -896,6 +921,11 @@ namespace glu_b200
                 resident[dev].store(per_sm, std::memory_order_release);
             }
             const unsigned chain = chain_rows >= 100 ? 4 : 8;
+            // GLU_SORT_RING_CTAS_PER_SM < occupancy leaves part of every SM to kernels of other streams (the multi-GPU
+            // pipeline runs the next job's NVLink-bound exchange pass beside this sort)
+            static const int share_env = env_int("GLU_SORT_RING_CTAS_PER_SM", 0);
+            if (share_env > 0 && share_env < per_sm)
+                per_sm = share_env;
             const unsigned capacity = unsigned(current_sm_count()) * unsigned(per_sm);
             // two tiles per ticket draw at start-up: no point in more CTAs than pairs of tiles
             unsigned workers = capacity > chain ? capacity - chain : 1;
