@@ -368,6 +368,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         }
         if (!has_next)
             break;
+        // this thread's generic-proxy accesses to the staging buffers (tile-sorted scatters, read-back) are ordered
+        // before the bulk copies that thread 0 issues into the same buffers after the barrier
+        fence_proxy_async_smem();
         __syncthreads(); // the tile has left shared memory
 
         // ---- 6. refill: values of the next tile, keys of the tile after next

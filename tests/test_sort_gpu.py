@@ -166,6 +166,62 @@ def test_sort_without_tma_path_matches(glu, cuda_device, oracle):
         assert r.returncode == 0 and "ok" in r.stdout, (env_extra, r.stdout, r.stderr)
 
 
+@pytest.mark.parametrize("env_extra", [{"GLU_SORT_CONFIG": "9"}, {"GLU_SORT_CONFIG": "10"}, {"GLU_SORT_CONFIG": "15"},
+                                       {"GLU_SORT_CONFIG": "12", "GLU_SORT_TMA": "0"}, {"GLU_SORT_CONFIG": "8"},
+                                       {"GLU_SORT_CONFIG": "13", "GLU_SORT_CHAIN_ROWS": "104"},
+                                       {"GLU_SORT_CONFIG": "10", "GLU_SORT_RING_CTAS_PER_SM": "1"}],
+                         ids=lambda e: "-".join(f"{k[9:]}{v}" for k, v in e.items()))
+def test_sort_both_kernel_forms(cuda_device, env_extra):
+    """Every size class through BOTH forms of the digit pass, whatever the default selection is: the persistent ring
+    kernel (GLU_SORT_CONFIG 9..18: tickets, two-deep key ring, early counts; 14..18 with the returning-atomic ranking
+    loop) and the one-tile-per-CTA kernel (8).  One tile, a few tiles (more CTAs than tiles), many tiles, ragged
+    ends, 16-byte-misaligned inputs (no bulk copies), heavy duplicates, num_steps, device-resident counts."""
+    import os
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+    code = r"""
+import numpy as np, torch, __graft_entry__ as e, oracle
+glu = e.load_package()
+dev = torch.device('cuda', 0)
+def up(a): return torch.from_numpy(a.view(np.int32).copy()).to(dev)
+def check(k, v, num_steps=0, off=0):
+    n = k.size - off
+    dk, dv = up(k), up(v)
+    glu.RadixSort()(dk[off:], dv[off:], n, num_steps); torch.cuda.synchronize()
+    ek, ev = oracle.stable_sort_pairs(k[off:], v[off:], num_steps)
+    assert np.array_equal(dk[off:].cpu().numpy().view(np.uint32), ek), (n, num_steps, off, 'keys')
+    assert np.array_equal(dv[off:].cpu().numpy().view(np.uint32), ev), (n, num_steps, off, 'values')
+for n in (2, 33, 5119, 5120, 5121, 7680, 15361, 41298, 100_003, 1_000_003, 3_000_001):
+    k = oracle.mt19937_u32(n, n); v = np.arange(n, dtype=np.uint32)
+    check(k, v)
+n = 700_001
+k = oracle.mt19937_u32(7, n); v = np.arange(n, dtype=np.uint32)
+for off in (1, 2, 3):
+    check(k, v, 0, off)
+for steps in (1, 3, 5, 8):
+    check(k, v, steps)
+check(oracle.random_u32(1, n, 0, 10), v)                       # keys in [0, 10)
+check(np.full(n, 0xDEADBEEF, dtype=np.uint32), v)              # one digit bin in every pass
+check(oracle.mt19937_u32(3, n) & np.uint32(0xFFFF), v)         # 16-bit entropy
+check(np.sort(k)[::-1].copy(), v)
+# device-resident count (glu_radix_sort_u32kv_dyn): the scratch is sized for max_count, the kernels read the count
+cap = 900_000
+for m in (1, 2, 5121, 333_333, cap):
+    kk = np.zeros(cap, np.uint32); kk[:m] = k[:m]
+    dk, dv = up(kk), up(np.arange(cap, dtype=np.uint32))
+    cnt = torch.tensor([m], dtype=torch.int32, device=dev)
+    glu.RadixSort().sort_device_count(dk, dv, cnt, cap); torch.cuda.synchronize()
+    ek, ev = oracle.stable_sort_pairs(k[:m], np.arange(m, dtype=np.uint32))
+    assert np.array_equal(dk[:m].cpu().numpy().view(np.uint32), ek) and np.array_equal(dv[:m].cpu().numpy().view(np.uint32), ev), m
+print('ok')
+"""
+    env = dict(os.environ, **env_extra)
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, (env_extra, r.stdout[-2000:], r.stderr[-4000:])
+
+
 def test_sort_full_size_2_28(glu, cuda_device, oracle):
     # BASELINE config 3: 2^28 uniform 32-bit keys, vals = index.  Size-independent properties on the device
     # (torch = plumbing): sorted, stable (equal keys => increasing source index), it IS the permutation it
