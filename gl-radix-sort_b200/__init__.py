@@ -66,6 +66,12 @@ ABI = {
     "glu_radix_partition_by_dest_u32kv_dyn": (_int, [_vp, _vp, _vp, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _vp, _vp,
                                                      _sz, _vp]),
     "glu_radix_exchange_plan": (_int, [_vp, _int, _int, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "glu_radix_partition_u32kv_dyn": (_int, [_vp, _vp, _vp, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _vp, _sz, _vp]),
+    "glu_radix_exchange_plan_buckets": (_int, [_vp, _int, _int, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "glu_radix_sort_segment_tile": (_sz, []),
+    "glu_radix_sort_u32kv_segmented_tmp_bytes": (_sz, [_sz]),
+    "glu_radix_sort_u32kv_segmented": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _sz,
+                                              _vp, ctypes.POINTER(_int)]),
     "glu_ipc_get_handle": (_int, [_vp, ctypes.c_char_p]),
     "glu_ipc_open_handle": (_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "glu_ipc_close_handle": (_int, [_vp]),
@@ -346,6 +352,32 @@ class RadixSort:
         st = _current_stream(dev) if stream is None else stream
         check(_lib.glu_radix_sort_wide(kptr, key_bytes, vptr, value_bytes, count, 1 if descending else 0, tmp, tmp_bytes,
                                        st), "RadixSort.sort_wide")
+
+    def sort_segmented(self, keys_a, vals_a, keys_b, vals_b, seg_count_buffer, num_segments: int, max_tiles: int,
+                       begin_bit: int = 0, end_bit: int = 32, stream: int | None = None) -> bool:
+        """glu_radix_sort_u32kv_segmented: `num_segments` independent stable sorts by key bits [begin_bit, end_bit) in one
+        set of launches.  Input in arrays A, segment s at element first_tile[s] * segment_tile() (first_tile = exclusive
+        scan of ceil(count / tile)); output compact.  Returns True when the result is in arrays B, False for A."""
+        ptrs = []
+        dev = None
+        for buf in (keys_a, vals_a, keys_b, vals_b, seg_count_buffer):
+            ptr, d = _ptr_and_device(buf)
+            if not ptr:
+                raise GluError(1, "Invalid buffer")
+            dev = dev if dev is not None else d
+            ptrs.append(ptr)
+        dev = _device_of(dev)
+        need = int(_lib.glu_radix_sort_u32kv_segmented_tmp_bytes(max_tiles))
+        if need == 0:
+            raise GluError(6, "RadixSort.sort_segmented")
+        tmp, tmp_bytes = self._scratch.ensure(need, dev)
+        self._device = dev
+        st = _current_stream(dev) if stream is None else stream
+        in_b = ctypes.c_int(0)
+        check(_lib.glu_radix_sort_u32kv_segmented(ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], num_segments, max_tiles,
+                                                  begin_bit, end_bit, tmp, tmp_bytes, st, ctypes.byref(in_b)),
+              "RadixSort.sort_segmented")
+        return bool(in_b.value)
 
     def sort_device_count(self, key_buffer, val_buffer, count_buffer, max_count: int, num_steps: int = 0,
                           stream: int | None = None) -> None:

@@ -38,17 +38,24 @@ template<int THREADS, int IPT, bool HAS_VALS = true> struct RingSmem
     alignas(8) uint64_t bar_keys[2];                  // mbarriers completed by the bulk copies
     alignas(8) uint64_t bar_vals;
     uint32_t tile_of[2];                              // tile whose keys are (or will be) in keys[b]
+    uint2 info_of[2];                                 // SEG: {valid | segment << 24, first tile of the segment} of that tile
 };
 
 // RATOM: the ranking loop takes the running slot offset with ONE returning shared atomic per digit group (its
 // lowest lane) and a shuffle, instead of every peer reading and re-writing the counter between two warp barriers.
-template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, int RATOM = 0, int FLAVOR = 0>
+//
+// SEG (glu_radix_sort_seg.cuh): many independent segments in one launch.  Tile t is always elements [t * TILE, (t + 1) *
+// TILE) of the input (segments start at tile boundaries), tile_info[t] = {valid | segment << 24, first tile of the
+// segment}; slots past `valid` are padding.  digit_offset is [segment][256] and includes the segment's output base; the
+// chain CTAs keep one running prefix over all tiles and a tile subtracts the prefix row in front of its segment.
+// *d_n is then the number of TILES (device-resident).
+template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, int RATOM = 0, int FLAVOR = 0, bool SEG = false>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     onesweep_ring_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                          uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n, uint32_t shift,
                          uint32_t mask, const uint32_t* __restrict__ digit_offset, uint32_t* lookback, uint32_t* prefix,
                          uint32_t* ticket, uint32_t num_tiles, int allow_tma, int chain_rows, int options,
-                         const uint32_t* __restrict__ d_n = nullptr)
+                         const uint32_t* __restrict__ d_n = nullptr, const uint2* __restrict__ tile_info = nullptr)
 {
     static_assert(THREADS >= k_radix && THREADS % 32 == 0, "one thread per digit");
     static_assert(IPT % 2 == 0, "ranks are packed two per register");
@@ -65,7 +72,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t chain_ctas = chain_rows >= 100 ? 4u : 8u;
-    if (d_n)
+    if constexpr (SEG)
+    {
+        num_tiles = __ldg(d_n);
+        n = num_tiles * uint32_t(TILE);
+    }
+    else if (d_n)
     {
         // *_dyn entry points: the count is device-resident (<= the n the scratch was sized for)
         n = __ldg(d_n);
@@ -91,7 +103,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     }
 
     auto digit_of = [&](uint32_t k) -> uint32_t { return ((k ^ FLIP) >> shift) & mask; };
-    auto tma_ok = [&](uint32_t t) -> bool { return allow_tma && uint64_t(t + 1) * uint32_t(TILE) <= uint64_t(n); };
+    // SEG: every tile is a whole bulk copy (padding slots are masked when the keys go to registers)
+    auto tma_ok = [&](uint32_t t) -> bool {
+        return allow_tma && (SEG || uint64_t(t + 1) * uint32_t(TILE) <= uint64_t(n));
+    };
 
     uint32_t ahead = 0xffffffffu; // thread 0: the ticket drawn for the tile after next
     uint64_t policy = 0;
@@ -105,6 +120,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         const uint32_t t0 = atomicAdd(ticket, 2u); // this CTA's first two tiles
         s.tile_of[0] = t0;
         s.tile_of[1] = t0 + 1;
+        if constexpr (SEG)
+        {
+            s.info_of[0] = t0 < num_tiles ? tile_info[t0] : make_uint2(0, 0);
+            s.info_of[1] = t0 + 1 < num_tiles ? tile_info[t0 + 1] : make_uint2(0, 0);
+        }
         if (t0 < num_tiles && tma_ok(t0))
         {
             mbarrier_arrive_expect_tx(&s.bar_keys[0], TILE * 4);
@@ -136,7 +156,18 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     uint32_t kparity = 0, vparity = 0; // bit b: phase the next wait on bar_keys[b] / bar_vals looks for
 
     // keys of tile t (ring slot b) -> registers, and into the warp's digit counters
-    auto load_and_count = [&](uint32_t b, uint32_t t) {
+    // number of real pairs of tile t (info: its tile_info word, SEG only)
+    auto valid_of = [&](uint32_t t, uint32_t info_x) -> uint32_t {
+        if constexpr (SEG)
+            return info_x & 0xffffffu;
+        else
+        {
+            const uint32_t base = t * uint32_t(TILE);
+            return n - base < uint32_t(TILE) ? n - base : uint32_t(TILE);
+        }
+    };
+    auto load_and_count = [&](uint32_t b, uint32_t t, uint32_t info_x) {
+        const uint32_t valid = valid_of(t, info_x);
         if (tma_ok(t))
         {
             mbarrier_wait(&s.bar_keys[b], (kparity >> b) & 1u);
@@ -144,13 +175,21 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 #pragma unroll
             for (int i = 0; i < IPT; i++)
                 key[i] = s.keys[b][my_off + i * 32];
+            if constexpr (SEG)
+            {
+                if (valid != uint32_t(TILE)) // the last tile of a segment: what lies behind it is not data
+                {
+#pragma unroll
+                    for (int i = 0; i < IPT; i++)
+                        key[i] = my_off + i * 32 < valid ? key[i] : PAD_KEY;
+                }
+            }
         }
         else
         {
             // the last, partial tile and 16-byte-misaligned inputs: straight from global memory; slots past the
             // end hold the largest key — they rank after every real key of the tile and are never written back
             const uint32_t base = t * uint32_t(TILE);
-            const uint32_t valid = n - base < uint32_t(TILE) ? n - base : uint32_t(TILE);
 #pragma unroll
             for (int i = 0; i < IPT; i++)
                 key[i] = my_off + i * 32 < valid ? keys_in[base + my_off + i * 32] : PAD_KEY;
@@ -182,34 +221,43 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     };
 
     // digit threads: the tile's digit counts summed over the warps, PUBLISHED for the chain CTAs at once
-    auto publish = [&](uint32_t t) -> uint32_t {
+    auto publish = [&](uint32_t t, uint32_t info_x) -> uint32_t {
         uint32_t tot = 0;
 #pragma unroll
         for (int w = 0; w < WARPS; w++)
             tot += s.warp_hist[w][tid];
-        const uint32_t base = t * uint32_t(TILE);
-        const uint32_t valid_t = n - base < uint32_t(TILE) ? n - base : uint32_t(TILE);
+        const uint32_t valid_t = valid_of(t, info_x);
         // padding slots all carry the digit of the padding key
         const uint32_t count_valid = tot - (tid == digit_of(PAD_KEY) ? uint32_t(TILE) - valid_t : 0u);
         st_relaxed_u32(&lookback[size_t(t) * k_radix + tid], k_lb_local | count_valid);
         return tot;
     };
 
-    load_and_count(0, cur);
+    uint2 cur_info = make_uint2(0, 0); // SEG: tile_info of the current tile
+    if constexpr (SEG)
+        cur_info = s.info_of[0];
+    load_and_count(0, cur, cur_info.x);
     __syncthreads();
     uint32_t total = 0; // digit threads: digit count of the current tile (padding included)
     if (tid < k_radix)
-        total = publish(cur);
+        total = publish(cur, cur_info.x);
 
     for (uint32_t it = 0;; it++)
     {
         const uint32_t b = it & 1u;
         const uint32_t tile = cur;
         const uint32_t tile_base = tile * uint32_t(TILE);
-        const uint32_t valid = n - tile_base < uint32_t(TILE) ? n - tile_base : uint32_t(TILE);
+        const uint32_t valid = valid_of(tile, cur_info.x);
         const bool full = valid == uint32_t(TILE);
         const bool use_tma = tma_ok(tile);
         uint32_t* skeys = s.keys[b];
+        // thread 0: tile_info of the ticket drawn an iteration ago, requested now, stored with the refill (step 6)
+        uint2 ahead_info = make_uint2(0, 0);
+        if constexpr (SEG)
+        {
+            if (tid == 0 && ahead < num_tiles)
+                ahead_info = tile_info[ahead];
+        }
 
         // ---- 1. per digit: scan of the tile's digit counts; slot offsets of each warp
         uint32_t inc = 0;
@@ -305,15 +353,26 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             if (tid < k_radix)
             {
                 uint32_t exclusive = 0;
-                if (tile > 0 && !(options & k_opt_no_lookback)) // k_opt_no_lookback: timing experiments only
+                const uint32_t first = SEG ? cur_info.y : 0u; // first tile of the sequence this tile belongs to
+                if (tile > first && !(options & k_opt_no_lookback)) // k_opt_no_lookback: timing experiments only
                 {
                     const uint32_t* p = prefix + size_t(tile - 1) * k_radix + tid;
                     uint32_t x = ld_relaxed_u32(p);
                     while ((x & k_lb_inclusive) == 0)
                         x = ld_relaxed_u32(p);
                     exclusive = x & ~k_lb_inclusive;
+                    if (SEG && first > 0)
+                    {
+                        // the running prefix does not restart at a segment: take off what precedes the segment
+                        const uint32_t* q = prefix + size_t(first - 1) * k_radix + tid;
+                        uint32_t y = ld_relaxed_u32(q);
+                        while ((y & k_lb_inclusive) == 0)
+                            y = ld_relaxed_u32(q);
+                        exclusive -= y & ~k_lb_inclusive;
+                    }
                 }
-                s.gbase[tid] = digit_offset[tid] + exclusive - s.tile_start[tid];
+                const uint32_t seg_row = SEG ? (cur_info.x >> 24) * uint32_t(k_radix) : 0u;
+                s.gbase[tid] = digit_offset[seg_row + tid] + exclusive - s.tile_start[tid];
             }
             if constexpr (!KEYS_ONLY)
             {
@@ -330,11 +389,14 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         //         published right away: its successors' look-back never waits for this CTA to get there
         const uint32_t nxt = s.tile_of[b ^ 1u];
         const bool has_next = nxt < num_tiles;
+        uint2 nxt_info = make_uint2(0, 0);
+        if constexpr (SEG)
+            nxt_info = s.info_of[b ^ 1u];
         if (has_next)
-            load_and_count(b ^ 1u, nxt);
+            load_and_count(b ^ 1u, nxt, nxt_info.x);
         __syncthreads(); // tile-sorted keys and values, gbase; the next tile's counts
         if (has_next && tid < k_radix)
-            total = publish(nxt);
+            total = publish(nxt, nxt_info.x);
 
         // ---- 5. out: consecutive threads write consecutive addresses inside each digit run
         if (full)
@@ -386,6 +448,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 }
             }
             s.tile_of[b] = ahead;
+            if constexpr (SEG)
+                s.info_of[b] = ahead_info;
             if (ahead < num_tiles)
             {
                 if (tma_ok(ahead))
@@ -399,5 +463,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             }
         }
         cur = nxt;
+        cur_info = nxt_info;
     }
 }

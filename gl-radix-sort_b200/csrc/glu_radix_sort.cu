@@ -894,13 +894,13 @@ namespace glu_b200
 
 
         // onesweep_ring_kernel: a persistent grid — the chain CTAs plus as many tile CTAs as are resident at once
-        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, int RATOM, int FLAVOR = 0>
+        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, int RATOM, int FLAVOR = 0, bool SEG = false>
         int launch_ring(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint32_t n, uint32_t shift,
                         uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback, uint32_t* ticket, unsigned tiles,
-                        cudaStream_t s, const uint32_t* d_n = nullptr)
+                        cudaStream_t s, const uint32_t* d_n = nullptr, const uint2* tile_info = nullptr)
         {
             uint32_t* prefix = lookback + size_t(tiles) * k_radix;
-            auto kernel = onesweep_ring_kernel<THREADS, IPT, MIN_BLOCKS, MODE, RATOM, FLAVOR>;
+            auto kernel = onesweep_ring_kernel<THREADS, IPT, MIN_BLOCKS, MODE, RATOM, FLAVOR, SEG>;
             const int allow_tma =
                 ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
             constexpr size_t smem = sizeof(RingSmem<THREADS, IPT, (FLAVOR & k_flavor_keys_only) == 0>);
@@ -933,7 +933,7 @@ namespace glu_b200
                 workers = (tiles + 1) / 2;
             ScopedKernelProfile prof(GLU_KERNEL_SORT_ONESWEEP, s);
             kernel<<<chain + workers, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix,
-                                                          ticket, tiles, allow_tma, chain_rows, options, d_n);
+                                                          ticket, tiles, allow_tma, chain_rows, options, d_n, tile_info);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }
@@ -1222,9 +1222,36 @@ extern "C" size_t glu_radix_partition_u32kv_tmp_bytes(size_t count)
     return k_tmp_align + align_up(2 * tiles * k_radix * sizeof(uint32_t), k_tmp_align);
 }
 
+namespace
+{
+    int partition_impl(const uint32_t* d_keys, const uint32_t* d_vals, size_t count, const uint32_t* d_n, unsigned shift,
+                       unsigned bits, uint32_t* const* d_key_dst, uint32_t* const* d_val_dst, void* d_tmp,
+                       size_t tmp_bytes, glu_stream_t stream);
+}
+
 extern "C" int glu_radix_partition_u32kv(const uint32_t* d_keys, const uint32_t* d_vals, size_t count, unsigned shift,
                                          unsigned bits, uint32_t* const* d_key_dst, uint32_t* const* d_val_dst,
                                          void* d_tmp, size_t tmp_bytes, glu_stream_t stream)
+{
+    return partition_impl(d_keys, d_vals, count, nullptr, shift, bits, d_key_dst, d_val_dst, d_tmp, tmp_bytes, stream);
+}
+
+extern "C" int glu_radix_partition_u32kv_dyn(const uint32_t* d_keys, const uint32_t* d_vals, const uint32_t* d_count,
+                                             size_t max_count, unsigned shift, unsigned bits, uint32_t* const* d_key_dst,
+                                             uint32_t* const* d_val_dst, void* d_tmp, size_t tmp_bytes, glu_stream_t stream)
+{
+    if (!d_count)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    if (reinterpret_cast<uintptr_t>(d_count) % sizeof(uint32_t) != 0)
+        return GLU_ERROR_MISALIGNED;
+    return partition_impl(d_keys, d_vals, max_count, d_count, shift, bits, d_key_dst, d_val_dst, d_tmp, tmp_bytes, stream);
+}
+
+namespace
+{
+int partition_impl(const uint32_t* d_keys, const uint32_t* d_vals, size_t count, const uint32_t* d_n, unsigned shift,
+                   unsigned bits, uint32_t* const* d_key_dst, uint32_t* const* d_val_dst, void* d_tmp, size_t tmp_bytes,
+                   glu_stream_t stream)
 {
     if (!d_keys || !d_vals || !d_key_dst || !d_val_dst || bits == 0 || bits > 8 || shift > 31)
         return GLU_ERROR_INVALID_ARGUMENT;
@@ -1251,8 +1278,9 @@ extern "C" int glu_radix_partition_u32kv(const uint32_t* d_keys, const uint32_t*
     uint32_t* lookback = reinterpret_cast<uint32_t*>(tmp + k_tmp_align);
     return launch_sweep<k_part_threads, k_part_ipt, k_part_blocks, Rank_Ballot, true>(
         d_keys, d_vals, nullptr, nullptr, uint32_t(count), shift, (1u << bits) - 1u, nullptr, lookback, ticket, tiles, s,
-        nullptr, d_key_dst, d_val_dst);
+        d_n, d_key_dst, d_val_dst);
 }
+} // namespace
 
 namespace
 {
@@ -1435,6 +1463,136 @@ extern "C" int glu_radix_exchange_plan(const uint32_t* d_hist_all, int world, in
     exchange_plan_kernel<<<1, k_radix, 0, s>>>(d_hist_all, world, rank, uint32_t(send_count), uint64_t(capacity),
                                                d_peer_keys, d_peer_vals, reinterpret_cast<uint64_t*>(d_key_dst),
                                                reinterpret_cast<uint64_t*>(d_val_dst), d_dest_of_digit, d_counts, d_info);
+    GLU_LAUNCH_CHECK();
+    return GLU_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------ segmented sort (many sorts, one launch set)
+#include "glu_radix_sort_seg.cuh"
+
+// ------------------------------------------------------------------------------ bucket-major exchange plan (MSD split + segmented local sort)
+
+namespace glu_b200
+{
+namespace
+{
+    // One CTA of 256 threads, thread b = bucket b.  Same bucket -> rank assignment as exchange_plan_kernel; the receive
+    // layout is BUCKET-major: rank g's buckets in increasing order, each starting at a tile boundary of the segmented
+    // sort (glu_radix_sort_segment_tile()), inside a bucket the sources in rank order (stable).
+    __global__ void __launch_bounds__(k_radix, 1)
+        exchange_plan_buckets_kernel(const uint32_t* __restrict__ hist_all, int world, int rank, uint32_t send_count,
+                                     uint32_t capacity_tiles, uint32_t tile, const uint64_t* __restrict__ peer_keys,
+                                     const uint64_t* __restrict__ peer_vals, uint64_t* key_dst, uint64_t* val_dst,
+                                     uint32_t* seg_count, uint32_t* counts, uint64_t* info)
+    {
+        __shared__ unsigned long long s_warp[k_radix / 32];
+        __shared__ uint32_t s_warp_tiles[k_radix / 32];
+        __shared__ uint32_t s_first_tiles[k_max_plan_world]; // tiles in front of the first bucket of each destination
+        __shared__ uint32_t s_recv_tiles[k_max_plan_world];
+        __shared__ unsigned long long s_recv[k_max_plan_world];
+        __shared__ int s_overflow;
+        const unsigned b = threadIdx.x, lane = b & 31, warp = b >> 5;
+        if (b < k_max_plan_world)
+        {
+            s_first_tiles[b] = 0xffffffffu;
+            s_recv_tiles[b] = 0;
+            s_recv[b] = 0;
+        }
+        if (b == 0)
+            s_overflow = 0;
+        unsigned long long bucket = 0, before_me = 0; // pairs of this bucket: all sources / sources < rank
+#pragma unroll
+        for (int src = 0; src < k_max_plan_world; src++)
+        {
+            const uint32_t c = src < world ? hist_all[src * k_radix + b] : 0u;
+            bucket += c;
+            if (src < rank)
+                before_me += c;
+        }
+        const uint32_t tiles = uint32_t((bucket + tile - 1) / tile);
+        unsigned long long inc = bucket;
+        uint32_t inc_t = tiles;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const unsigned long long t = __shfl_up_sync(k_full_mask, inc, o);
+            const uint32_t tt = __shfl_up_sync(k_full_mask, inc_t, o);
+            if (lane >= unsigned(o))
+            {
+                inc += t;
+                inc_t += tt;
+            }
+        }
+        if (lane == 31)
+        {
+            s_warp[warp] = inc;
+            s_warp_tiles[warp] = inc_t;
+        }
+        __syncthreads();
+        unsigned long long before = inc - bucket, total = 0;
+        uint32_t tiles_before = inc_t - tiles;
+        for (unsigned w = 0; w < k_radix / 32; w++)
+        {
+            if (w < warp)
+            {
+                before += s_warp[w];
+                tiles_before += s_warp_tiles[w];
+            }
+            total += s_warp[w];
+        }
+        unsigned dest = 0;
+        if (total)
+        {
+            const unsigned long long d = (2 * before + bucket) * (unsigned long long)world / (2 * total);
+            dest = d < (unsigned long long)(world - 1) ? unsigned(d) : unsigned(world - 1);
+        }
+        atomicMin(&s_first_tiles[dest], tiles_before);
+        atomicAdd(&s_recv_tiles[dest], tiles);
+        atomicAdd(&s_recv[dest], bucket);
+        __syncthreads();
+        if (b < unsigned(world) && s_recv_tiles[b] > capacity_tiles)
+            atomicOr(&s_overflow, 1);
+        __syncthreads();
+        const bool overflow = s_overflow != 0;
+        const unsigned long long offset = (unsigned long long)(tiles_before - s_first_tiles[dest]) * tile + before_me;
+        key_dst[b] = overflow ? 0ull : peer_keys[dest] + 4ull * offset;
+        val_dst[b] = overflow ? 0ull : peer_vals[dest] + 4ull * offset;
+        seg_count[b] = (!overflow && dest == unsigned(rank)) ? uint32_t(bucket) : 0u;
+        if (b < unsigned(world))
+            info[b] = s_recv[b];
+        if (b == 0)
+        {
+            counts[0] = overflow ? 0u : send_count;
+            counts[1] = overflow ? 0u : uint32_t(s_recv[rank]);
+            info[world] = s_recv[rank];
+            info[world + 1] = overflow ? 1ull : 0ull;
+        }
+    }
+} // namespace
+} // namespace glu_b200
+
+extern "C" int glu_radix_exchange_plan_buckets(const uint32_t* d_hist_all, int world, int rank, size_t send_count,
+                                               size_t capacity_tiles, const uint64_t* d_peer_keys,
+                                               const uint64_t* d_peer_vals, uint32_t** d_key_dst, uint32_t** d_val_dst,
+                                               uint32_t* d_seg_count, uint32_t* d_counts, uint64_t* d_info,
+                                               glu_stream_t stream)
+{
+    if (!d_hist_all || !d_peer_keys || !d_peer_vals || !d_key_dst || !d_val_dst || !d_seg_count || !d_counts || !d_info ||
+        world < 1 || world > k_max_plan_world || rank < 0 || rank >= world)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    if (send_count > k_max_count || capacity_tiles * glu_radix_sort_segment_tile() > k_max_count)
+        return GLU_ERROR_COUNT_TOO_LARGE;
+    if ((reinterpret_cast<uintptr_t>(d_hist_all) | reinterpret_cast<uintptr_t>(d_counts) |
+         reinterpret_cast<uintptr_t>(d_seg_count)) % sizeof(uint32_t) != 0 ||
+        (reinterpret_cast<uintptr_t>(d_peer_keys) | reinterpret_cast<uintptr_t>(d_peer_vals) |
+         reinterpret_cast<uintptr_t>(d_key_dst) | reinterpret_cast<uintptr_t>(d_val_dst) |
+         reinterpret_cast<uintptr_t>(d_info)) % sizeof(uint64_t) != 0)
+        return GLU_ERROR_MISALIGNED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    exchange_plan_buckets_kernel<<<1, k_radix, 0, s>>>(
+        d_hist_all, world, rank, uint32_t(send_count), uint32_t(capacity_tiles), uint32_t(glu_radix_sort_segment_tile()),
+        d_peer_keys, d_peer_vals, reinterpret_cast<uint64_t*>(d_key_dst), reinterpret_cast<uint64_t*>(d_val_dst), d_seg_count,
+        d_counts, d_info);
     GLU_LAUNCH_CHECK();
     return GLU_SUCCESS;
 }

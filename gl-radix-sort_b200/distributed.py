@@ -219,7 +219,9 @@ class DistributedRadixSort:
     slice of the global result, valid until the next call.  Rank r's keys are <= rank r+1's."""
 
     def __init__(self, max_count: int, group=None, capacity_factor: float = 1.25, exchange: str = "auto",
-                 split_shift: int | str = 32 - RADIX_BITS, plan: str = "auto"):
+                 split_shift: int | str = 32 - RADIX_BITS, plan: str = "auto", local: str = "auto"):
+        import os
+
         import torch
 
         glu, dist = _glu(), _dist()
@@ -229,12 +231,26 @@ class DistributedRadixSort:
         self.max_count = int(max_count)
         self.capacity = int(max_count * capacity_factor) + 1024
         self.split_shift = split_shift
-        if self.capacity >= (1 << 31):
+        # local="segmented": the exchange is BUCKET-major (one run per top-digit bucket and source, every bucket at a tile
+        # boundary of the receiver) and the local sort is glu_radix_sort_u32kv_segmented over the key bits below the split
+        # digit — 3 passes for 32-bit keys, north_star's "local onesweep on the remaining 24 bits".  local="full": the
+        # exchange is destination-major (long NVLink runs) and the received range is sorted on all 32 bits (4 passes).
+        if local == "auto":  # GLU_DIST_LOCAL chooses for callers that do not (bench.py's sweeps, the pipeline's lanes)
+            local = os.environ.get("GLU_DIST_LOCAL", "auto")
+        if local not in ("auto", "full", "segmented"):
+            raise ValueError(local)
+        self._tile = int(glu.lib.glu_radix_sort_segment_tile())
+        self.capacity_tiles = -(-self.capacity // self._tile) + RADIX  # every bucket may end in a partial tile
+        seg_capacity = self.capacity_tiles * self._tile
+        want_seg = local in ("auto", "segmented") and exchange in ("auto", "p2p") and plan in ("auto", "device") \
+            and self.world <= 16
+        if max(self.capacity, seg_capacity if want_seg else 0) >= (1 << 31):
             raise glu.GluError(6, "DistributedRadixSort: per-rank capacity must stay below 2^31 pairs")
-        self._recv_keys = _DeviceArray(self.capacity, self.device)
-        self._recv_vals = _DeviceArray(self.capacity, self.device)
+        alloc = seg_capacity if want_seg else self.capacity
+        self._recv_keys = _DeviceArray(alloc, self.device)
+        self._recv_vals = _DeviceArray(alloc, self.device)
         self._sorter = glu.RadixSort()
-        self._sorter.prepare_internal_buffers(self.capacity, self.device)
+        self._alt_keys = self._alt_vals = None
         self._part_tmp = torch.empty(int(glu.lib.glu_radix_partition_u32kv_tmp_bytes(self.max_count)), dtype=torch.uint8,
                                      device=self.device)
         self._hist = torch.zeros(RADIX, dtype=torch.int32, device=self.device)
@@ -248,6 +264,18 @@ class DistributedRadixSort:
         self._peer_keys = self._peer_vals = None
         self._stage_keys = self._stage_vals = None
         self.exchange = self._setup_exchange(exchange)
+        self.local = "segmented" if (want_seg and self.exchange == "p2p") else "full"
+        if local == "segmented" and self.local != "segmented":
+            raise glu.GluError(1, "DistributedRadixSort: local='segmented' needs the p2p exchange, the device plan and "
+                                  "at most 16 ranks")
+        if self.local == "segmented":
+            self._alt_keys = torch.empty(seg_capacity, dtype=torch.int32, device=self.device)
+            self._alt_vals = torch.empty(seg_capacity, dtype=torch.int32, device=self.device)
+            self._seg_count = torch.zeros(RADIX, dtype=torch.int32, device=self.device)
+            self._sorter._scratch.ensure(int(glu.lib.glu_radix_sort_u32kv_segmented_tmp_bytes(self.capacity_tiles)),
+                                         self.device)
+        else:
+            self._sorter.prepare_internal_buffers(self.capacity, self.device)
         # plan="device": the exchange plan is computed by glu_radix_exchange_plan and the partition / local sort read
         # their counts from device memory — the step has no host round trip between the histogram and the sort (the
         # host only waits, after everything is enqueued, for the few bytes that tell it how much it received).
@@ -436,6 +464,15 @@ class DistributedRadixSort:
     def _call_device_plan(self, kptr: int, vptr: int, count: int, shift: int, st: int, mark):
         """The step without a host round trip: histogram -> all-gather -> plan kernel -> partition (+ NVLink all-to-all)
         -> device barrier -> local sort, all enqueued back to back; counts travel through device memory."""
+        self._enqueue_exchange(kptr, vptr, count, shift, st, mark)
+        mark("partition+exchange")
+        rk, rv = self._enqueue_local_sort(shift, st)
+        mark("local sort")
+        return self._finish(rk, rv)
+
+    def _enqueue_exchange(self, kptr: int, vptr: int, count: int, shift: int, st: int, mark=lambda name: None):
+        """histogram -> all-gather -> device plan -> partition pass whose stores are the all-to-all -> device barrier
+        (enqueued on the CURRENT torch stream, whose raw handle is `st`)."""
         glu, dist = _glu(), _dist()
         world, rank = self.world, self.rank
         glu.check(glu.lib.glu_radix_histogram_u32(kptr, count, shift, RADIX_BITS, self._hist.data_ptr(), st),
@@ -444,30 +481,59 @@ class DistributedRadixSort:
         dist.all_gather_into_tensor(self._hist_all, self._hist, group=self.group)
         tptr = self._tables.data_ptr()
         pptr = self._peers_dev.data_ptr()
-        glu.check(glu.lib.glu_radix_exchange_plan(self._hist_all.data_ptr(), world, rank, count, self.capacity, pptr,
-                                                  pptr + 8 * world, tptr, tptr + 8 * RADIX, tptr + 16 * RADIX,
-                                                  self._counts_dev.data_ptr(), self._info_dev.data_ptr(), st),
-                  "glu_radix_exchange_plan")
+        cptr = self._counts_dev.data_ptr()
+        if self.local == "segmented":
+            glu.check(glu.lib.glu_radix_exchange_plan_buckets(self._hist_all.data_ptr(), world, rank, count,
+                                                              self.capacity_tiles, pptr, pptr + 8 * world, tptr,
+                                                              tptr + 8 * RADIX, self._seg_count.data_ptr(), cptr,
+                                                              self._info_dev.data_ptr(), st),
+                      "glu_radix_exchange_plan_buckets")
+        else:
+            glu.check(glu.lib.glu_radix_exchange_plan(self._hist_all.data_ptr(), world, rank, count, self.capacity, pptr,
+                                                      pptr + 8 * world, tptr, tptr + 8 * RADIX, tptr + 16 * RADIX, cptr,
+                                                      self._info_dev.data_ptr(), st),
+                      "glu_radix_exchange_plan")
         self._info_host.copy_(self._info_dev, non_blocking=True)
         self._hist_host.copy_(self._hist_all, non_blocking=True)
         self._plan_event.record()
         mark("histogram+allgather+plan")
-        cptr = self._counts_dev.data_ptr()
-        glu.check(glu.lib.glu_radix_partition_by_dest_u32kv_dyn(kptr, vptr, cptr, count, shift, RADIX_BITS,
-                                                                tptr + 16 * RADIX, tptr, tptr + 8 * RADIX,
-                                                                self._part_tmp.data_ptr(), self._part_tmp.numel(), st),
-                  "glu_radix_partition_by_dest_u32kv_dyn")
+        if self.local == "segmented":
+            # one run per (bucket, source): the receiver gets its buckets contiguous, ready for the segmented sort
+            glu.check(glu.lib.glu_radix_partition_u32kv_dyn(kptr, vptr, cptr, count, shift, RADIX_BITS, tptr,
+                                                            tptr + 8 * RADIX, self._part_tmp.data_ptr(),
+                                                            self._part_tmp.numel(), st),
+                      "glu_radix_partition_u32kv_dyn")
+        else:
+            glu.check(glu.lib.glu_radix_partition_by_dest_u32kv_dyn(kptr, vptr, cptr, count, shift, RADIX_BITS,
+                                                                    tptr + 16 * RADIX, tptr, tptr + 8 * RADIX,
+                                                                    self._part_tmp.data_ptr(), self._part_tmp.numel(), st),
+                      "glu_radix_partition_by_dest_u32kv_dyn")
         # device-side barrier: when this tiny all-reduce completes, every rank's partition kernel has completed
         dist.all_reduce(self._token, group=self.group)
-        mark("partition+exchange")
+
+    def _enqueue_local_sort(self, shift: int, st: int):
+        """The local sort of what this rank received, on stream `st`; returns the arrays that will hold the result."""
         rk, rv = self._recv_keys.tensor, self._recv_vals.tensor
-        self._sorter.sort_device_count(rk, rv, cptr + 4, self.capacity)
-        mark("local sort")
+        if self.local == "segmented":
+            # key bits [0, shift) are what is left to sort inside a bucket.  shift == 0 (adaptive split digit at the
+            # bottom of the key): the keys of a bucket are all equal — one pass over the digit itself is a stable no-op
+            # that still brings the tile-aligned buckets into the compact output layout
+            end_bit = shift if shift > 0 else RADIX_BITS
+            in_b = self._sorter.sort_segmented(rk, rv, self._alt_keys, self._alt_vals, self._seg_count, RADIX,
+                                               self.capacity_tiles, 0, end_bit, stream=st)
+            return (self._alt_keys, self._alt_vals) if in_b else (rk, rv)
+        self._sorter.sort_device_count(rk, rv, self._counts_dev.data_ptr() + 4, self.capacity, stream=st)
+        return rk, rv
+
+    def _finish(self, rk, rv):
+        """Host side of a step, after everything is enqueued: how much did this rank receive, did anybody overflow."""
+        glu = _glu()
+        world = self.world
         # only now does the host look at the plan: the GPU is busy with the partition and the sort meanwhile
         self._plan_event.synchronize()
         info = self._info_host.numpy()
         self.last_plan = None
-        self._last_hist = self._hist_host.numpy().view(np.uint32).reshape(world, RADIX)
+        self._last_hist = self._hist_host.numpy().view(np.uint32).reshape(world, RADIX).copy()
         if int(info[world + 1]) != 0:
             raise glu.GluError(6, f"DistributedRadixSort: a rank would receive {int(info[:world].max())} pairs, "
                                   f"capacity is {self.capacity} (raise capacity_factor or use split_shift='auto')")
@@ -499,6 +565,7 @@ class DistributedRadixSort:
         self._recv_vals.free()
         self._sorter = None
         self._part_tmp = None
+        self._alt_keys = self._alt_vals = None
 
     def __del__(self):
         try:
@@ -542,11 +609,17 @@ class DistributedSortPipeline:
         self.lanes = [DistributedRadixSort(max_count, group=group, capacity_factor=capacity_factor, exchange="p2p",
                                            split_shift=int(split_shift), plan="device") for _ in range(2)]
         self.device = self.lanes[0].device
-        self.stream_x = torch.cuda.Stream(device=self.device)
-        self.stream_s = torch.cuda.Stream(device=self.device)
+        # GLU_PIPE_PRIORITY=x / s gives the exchange / the sorting stream the higher CUDA stream priority (its CTAs are
+        # dispatched first whenever both streams have work pending); default: equal priorities
+        import os
+
+        prio = os.environ.get("GLU_PIPE_PRIORITY", "")
+        self.stream_x = torch.cuda.Stream(device=self.device, priority=-1 if prio == "x" else 0)
+        self.stream_s = torch.cuda.Stream(device=self.device, priority=-1 if prio == "s" else 0)
         self._exchanged = [torch.cuda.Event(), torch.cuda.Event()]
         self._sorted = [torch.cuda.Event(), torch.cuda.Event()]
         self._submitted = 0
+        self._results = [None, None]
         self._glu = glu
 
     def submit(self, key_buffer, val_buffer, count: int) -> int:
@@ -562,33 +635,15 @@ class DistributedSortPipeline:
         if count < 1 or count > lane.max_count:
             raise glu.GluError(1, f"count must be in [1, {lane.max_count}]")
         shift = int(lane.split_shift)
-        world, rank = lane.world, lane.rank
         self.stream_x.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream_x):
             if k >= 2:
                 self.stream_x.wait_event(self._sorted[k % 2])
-            st = self.stream_x.cuda_stream
-            glu.check(glu.lib.glu_radix_histogram_u32(kptr, count, shift, RADIX_BITS, lane._hist.data_ptr(), st),
-                      "glu_radix_histogram_u32")
-            dist.all_gather_into_tensor(lane._hist_all, lane._hist, group=lane.group)
-            tptr, pptr = lane._tables.data_ptr(), lane._peers_dev.data_ptr()
-            glu.check(glu.lib.glu_radix_exchange_plan(lane._hist_all.data_ptr(), world, rank, count, lane.capacity, pptr,
-                                                      pptr + 8 * world, tptr, tptr + 8 * RADIX, tptr + 16 * RADIX,
-                                                      lane._counts_dev.data_ptr(), lane._info_dev.data_ptr(), st),
-                      "glu_radix_exchange_plan")
-            lane._info_host.copy_(lane._info_dev, non_blocking=True)
-            lane._plan_event.record(self.stream_x)
-            cptr = lane._counts_dev.data_ptr()
-            glu.check(glu.lib.glu_radix_partition_by_dest_u32kv_dyn(kptr, vptr, cptr, count, shift, RADIX_BITS,
-                                                                    tptr + 16 * RADIX, tptr, tptr + 8 * RADIX,
-                                                                    lane._part_tmp.data_ptr(), lane._part_tmp.numel(), st),
-                      "glu_radix_partition_by_dest_u32kv_dyn")
-            dist.all_reduce(lane._token, group=lane.group)  # every rank's peer stores of this job have landed
+            lane._enqueue_exchange(kptr, vptr, count, shift, self.stream_x.cuda_stream)
             self._exchanged[k % 2].record(self.stream_x)
         with torch.cuda.stream(self.stream_s):
             self.stream_s.wait_event(self._exchanged[k % 2])
-            lane._sorter.sort_device_count(lane._recv_keys.tensor, lane._recv_vals.tensor, cptr + 4, lane.capacity,
-                                           stream=self.stream_s.cuda_stream)
+            self._results[k % 2] = lane._enqueue_local_sort(shift, self.stream_s.cuda_stream)
             self._sorted[k % 2].record(self.stream_s)
         self._submitted = k + 1
         return k
@@ -609,7 +664,8 @@ class DistributedSortPipeline:
             raise glu.GluError(6, f"DistributedSortPipeline: a rank would receive {int(info[:lane.world].max())} pairs, "
                                   f"capacity is {lane.capacity}")
         m = int(info[lane.world])
-        return lane._recv_keys.tensor[:m], lane._recv_vals.tensor[:m], m
+        rk, rv = self._results[ticket % 2]
+        return rk[:m], rv[:m], m
 
     def flush(self) -> None:
         """Make the caller's current stream wait for everything submitted so far (e.g. before recording a timing event)."""

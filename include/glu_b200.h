@@ -210,11 +210,33 @@ GLU_API int glu_radix_partition_by_dest_u32kv(const uint32_t* d_keys, const uint
  * elements [*d_count, max_count) of d_keys / d_vals are undefined. */
 GLU_API int glu_radix_sort_u32kv_dyn(uint32_t* d_keys, uint32_t* d_vals, const uint32_t* d_count, size_t max_count,
                                      size_t num_steps, void* d_tmp, size_t tmp_bytes, glu_stream_t stream);
+GLU_API int glu_radix_partition_u32kv_dyn(const uint32_t* d_keys, const uint32_t* d_vals, const uint32_t* d_count,
+                                          size_t max_count, unsigned shift, unsigned bits, uint32_t* const* d_key_dst,
+                                          uint32_t* const* d_val_dst, void* d_tmp, size_t tmp_bytes, glu_stream_t stream);
 GLU_API int glu_radix_partition_by_dest_u32kv_dyn(const uint32_t* d_keys, const uint32_t* d_vals,
                                                   const uint32_t* d_count, size_t max_count, unsigned shift,
                                                   unsigned bits, const uint8_t* d_dest_of_digit,
                                                   uint32_t* const* d_key_dst, uint32_t* const* d_val_dst, void* d_tmp,
                                                   size_t tmp_bytes, glu_stream_t stream);
+
+/* SEGMENTED stable sort: `num_segments` (<= 256) independent (key, value) sequences sorted by key bits
+ * [begin_bit, end_bit) in one histogram launch + ceil(bits / 8) digit passes — what the multi-GPU sort runs on the
+ * top-digit buckets a rank received ("the local onesweep on the remaining 24 bits", BASELINE.json north_star): 4 + 16 B
+ * per pair and pass instead of a full 32-bit sort of the received range.
+ *   Input (arrays A): segment s holds d_seg_count[s] pairs (device-resident counts) starting at element
+ *   first_tile[s] * glu_radix_sort_segment_tile(), first_tile = exclusive scan of ceil(count / tile): segments start at
+ *   tile boundaries, the gap behind a segment's last pair is padding (never read as data, never written).
+ *   Output: compact — segment s at the sum of the counts before it — in arrays B when the number of passes
+ *   (ceil((end_bit - begin_bit) / 8)) is odd, in arrays A when it is even; *result_in_b says which (host value, may be
+ *   NULL).  The other pair of arrays is scratch.  All four arrays hold max_tiles * tile elements and are 16-byte
+ *   aligned.  If the segments need more than max_tiles tiles nothing is sorted (the caller's plan checks capacity).
+ * Keys with equal bits keep their order inside the segment (stable); segments never mix. */
+GLU_API size_t glu_radix_sort_segment_tile(void);
+GLU_API size_t glu_radix_sort_u32kv_segmented_tmp_bytes(size_t max_tiles);
+GLU_API int glu_radix_sort_u32kv_segmented(uint32_t* d_keys_a, uint32_t* d_vals_a, uint32_t* d_keys_b, uint32_t* d_vals_b,
+                                           const uint32_t* d_seg_count, size_t num_segments, size_t max_tiles,
+                                           unsigned begin_bit, unsigned end_bit, void* d_tmp, size_t tmp_bytes,
+                                           glu_stream_t stream, int* result_in_b);
 
 /* The exchange plan of the multi-GPU sort, computed on the device from the all-gathered split-digit histograms
  * d_hist_all[world][256] (world <= 16): bucket -> destination rank by balanced prefix (contiguous bucket ranges),
@@ -230,6 +252,20 @@ GLU_API int glu_radix_exchange_plan(const uint32_t* d_hist_all, int world, int r
                                     const uint64_t* d_peer_keys, const uint64_t* d_peer_vals, uint32_t** d_key_dst,
                                     uint32_t** d_val_dst, uint8_t* d_dest_of_digit, uint32_t* d_counts,
                                     uint64_t* d_info, glu_stream_t stream);
+
+/* The BUCKET-major exchange plan (MSD split followed by the segmented local sort): same bucket -> rank assignment, but
+ * rank g receives its buckets one after the other in increasing order, each starting at a tile boundary of
+ * glu_radix_sort_u32kv_segmented (glu_radix_sort_segment_tile() pairs), inside a bucket the sources in rank order —
+ *   d_key_dst / d_val_dst[256]   entry b: where THIS rank's run of bucket b goes (for glu_radix_partition_u32kv_dyn),
+ *   d_seg_count[256]             pairs of bucket b if this rank receives it, else 0: the segment table of the local sort,
+ *   d_counts / d_info            as glu_radix_exchange_plan (d_counts[1], d_info[g] = pairs received, without padding).
+ * capacity_tiles: tiles a rank's receive arrays hold; if any rank needs more the overflow flag is set, nothing is sent
+ * and nothing is sorted. */
+GLU_API int glu_radix_exchange_plan_buckets(const uint32_t* d_hist_all, int world, int rank, size_t send_count,
+                                            size_t capacity_tiles, const uint64_t* d_peer_keys,
+                                            const uint64_t* d_peer_vals, uint32_t** d_key_dst, uint32_t** d_val_dst,
+                                            uint32_t* d_seg_count, uint32_t* d_counts, uint64_t* d_info,
+                                            glu_stream_t stream);
 
 /* CUDA IPC plumbing for one-process-per-GPU peer access: export a glu_malloc'ed allocation, map a peer's. */
 #define GLU_IPC_HANDLE_BYTES 64

@@ -227,10 +227,14 @@ def gather(obj):
     return out
 
 # ---- sort: uniform 32-bit, the reference's 31-bit keys (adaptive split), heavy duplicates, 16-bit entropy
+# exchange "p2p" runs twice: destination-major exchange + full local sort, and bucket-major exchange + segmented local
+# sort on the key bits below the split digit (north_star's MSD split + 24-bit local sort)
 for exchange in os.environ["GLU_EXCHANGES"].split(","):
-    sorter_fixed = glu.DistributedRadixSort(400_000, exchange=exchange, capacity_factor=2.5)
-    sorter_auto = glu.DistributedRadixSort(400_000, exchange=exchange, capacity_factor=2.5, split_shift="auto")
+  for local in (("full", "segmented") if exchange == "p2p" else ("full",)):
+    sorter_fixed = glu.DistributedRadixSort(400_000, exchange=exchange, capacity_factor=2.5, local=local)
+    sorter_auto = glu.DistributedRadixSort(400_000, exchange=exchange, capacity_factor=2.5, split_shift="auto", local=local)
     assert sorter_fixed.exchange == exchange, (sorter_fixed.exchange, exchange)
+    assert sorter_fixed.local == local, (sorter_fixed.local, local)
     for kind, sorter in (("uniform", sorter_fixed), ("uniform", sorter_auto), ("ref31", sorter_auto), ("dups", sorter_auto),
                          ("ent16", sorter_auto), ("uniform_again", sorter_fixed)):
         n = 300_007 + 1013 * rank
@@ -254,44 +258,48 @@ for exchange in os.environ["GLU_EXCHANGES"].split(","):
             allk = np.concatenate([r[0] for r in res]); allv = np.concatenate([r[1] for r in res])
             gk = np.concatenate([r[2] for r in res]); gv = np.concatenate([r[3] for r in res])
             ek, ev = oracle.stable_sort_pairs(allk, allv)
-            assert np.array_equal(gk, ek), f"{exchange}/{kind}: keys differ"
-            assert np.array_equal(gv, ev), f"{exchange}/{kind}: values differ (stability across ranks)"
+            assert np.array_equal(gk, ek), f"{exchange}/{local}/{kind}: keys differ"
+            assert np.array_equal(gv, ev), f"{exchange}/{local}/{kind}: values differ (stability across ranks)"
         dist.barrier()
     sorter_fixed.close()
     sorter_auto.close()
 
 # ---- the two-lane pipeline (DistributedSortPipeline): consecutive independent jobs, the exchange of job k+1 runs under
 # the local sort of job k; every job's result must equal std::stable_sort of the concatenated inputs
-pipe = glu.DistributedSortPipeline(400_000, capacity_factor=2.5)
-jobs, pending = [], []
+for pipe_local in ("segmented", "full"):
+  os.environ["GLU_DIST_LOCAL"] = pipe_local
+  pipe = glu.DistributedSortPipeline(400_000, capacity_factor=2.5)
+  assert pipe.lanes[0].local == pipe_local
+  jobs, pending = [], []
 
-def check_job(j, ticket):
-    sk, sv, m = pipe.result(ticket)
-    keys, vals = jobs[j][0], jobs[j][1]
-    res = gather((keys, vals, sk.cpu().numpy().view(np.uint32), sv.cpu().numpy().view(np.uint32)))
-    if rank == 0:
-        allk = np.concatenate([r[0] for r in res]); allv = np.concatenate([r[1] for r in res])
-        gk = np.concatenate([r[2] for r in res]); gv = np.concatenate([r[3] for r in res])
-        ek, ev = oracle.stable_sort_pairs(allk, allv)
-        assert np.array_equal(gk, ek), f"pipeline job {j}: keys differ"
-        assert np.array_equal(gv, ev), f"pipeline job {j}: values differ"
+  def check_job(j, ticket):
+      sk, sv, m = pipe.result(ticket)
+      keys, vals = jobs[j][0], jobs[j][1]
+      res = gather((keys, vals, sk.cpu().numpy().view(np.uint32), sv.cpu().numpy().view(np.uint32)))
+      if rank == 0:
+          allk = np.concatenate([r[0] for r in res]); allv = np.concatenate([r[1] for r in res])
+          gk = np.concatenate([r[2] for r in res]); gv = np.concatenate([r[3] for r in res])
+          ek, ev = oracle.stable_sort_pairs(allk, allv)
+          assert np.array_equal(gk, ek), f"pipeline job {j}: keys differ"
+          assert np.array_equal(gv, ev), f"pipeline job {j}: values differ"
 
-for j in range(5):
-    n = 250_003 + 977 * rank + 1000 * j
-    keys = oracle.mt19937_u32(60 + 10 * j + rank, n)
-    if j == 3:
-        keys = keys & np.uint32(0xFF0000FF)  # heavy duplicates inside every bucket
-    sizes = gather(n)
-    base = sum(sizes[:rank])
-    vals = np.arange(base, base + n, dtype=np.uint32)
-    dk, dv = up(keys), up(vals)
-    jobs.append((keys, vals, dk, dv))
-    pending.append((j, pipe.submit(dk, dv, n)))
-    if len(pending) == 2:
-        check_job(*pending.pop(0))
-while pending:
-    check_job(*pending.pop(0))
-pipe.close()
+  for j in range(5):
+      n = 250_003 + 977 * rank + 1000 * j
+      keys = oracle.mt19937_u32(60 + 10 * j + rank, n)
+      if j == 3:
+          keys = keys & np.uint32(0xFF0000FF)  # heavy duplicates inside every bucket
+      sizes = gather(n)
+      base = sum(sizes[:rank])
+      vals = np.arange(base, base + n, dtype=np.uint32)
+      dk, dv = up(keys), up(vals)
+      jobs.append((keys, vals, dk, dv))
+      pending.append((j, pipe.submit(dk, dv, n)))
+      if len(pending) == 2:
+          check_job(*pending.pop(0))
+  while pending:
+      check_job(*pending.pop(0))
+  pipe.close()
+del os.environ["GLU_DIST_LOCAL"]
 
 # ---- reduce / scan sharded by contiguous ranges
 n = 1_000_003 + 31 * rank

@@ -1,0 +1,87 @@
+"""GPU parity tests of glu_radix_sort_u32kv_segmented — many independent stable sorts by a key-bit range in one set of
+launches (the "local onesweep on the remaining 24 bits" of the multi-GPU sort, BASELINE.json north_star).  The oracle
+is std::stable_sort of every segment on its own, comparing the key bits that take part (oracle.stable_sort_ex)."""
+import numpy as np
+import pytest
+
+from conftest import to_device, to_host
+
+pytestmark = pytest.mark.gpu
+
+
+def run_case(glu, dev, oracle, counts, begin_bit, end_bit, seed=1, key_transform=None):
+    import torch
+
+    tile = int(glu.lib.glu_radix_sort_segment_tile())
+    counts = np.asarray(counts, dtype=np.int64)
+    tiles = (counts + tile - 1) // tile
+    first = np.cumsum(tiles) - tiles
+    max_tiles = int(tiles.sum()) + 3  # some head room: the scratch may be larger than what the segments need
+    total = int(counts.sum())
+    keys = oracle.mt19937_u32(seed, max(total, 1))[:total]
+    if key_transform is not None:
+        keys = key_transform(keys)
+    vals = (np.arange(total, dtype=np.uint32) * np.uint32(2654435761)) ^ np.uint32(seed)  # arbitrary payload
+    a_keys = np.full(max_tiles * tile, 0x0BADF00D, dtype=np.uint32)  # what lies in the padding must never matter
+    a_vals = np.full(max_tiles * tile, 0xDEADDEAD, dtype=np.uint32)
+    want_k, want_v = np.empty(total, np.uint32), np.empty(total, np.uint32)
+    pos = 0
+    for s, c in enumerate(counts):
+        c = int(c)
+        seg_k, seg_v = keys[pos:pos + c], vals[pos:pos + c]
+        a_keys[first[s] * tile:first[s] * tile + c] = seg_k
+        a_vals[first[s] * tile:first[s] * tile + c] = seg_v
+        if c:
+            ek, ev = oracle.stable_sort_ex(seg_k, seg_v, begin_bit, end_bit)
+            want_k[pos:pos + c], want_v[pos:pos + c] = ek, ev
+        pos += c
+    dka, dva = to_device(a_keys, dev), to_device(a_vals, dev)
+    dkb = torch.full((max_tiles * tile,), 0x5A5A5A5A, dtype=torch.int32, device=dev)
+    dvb = torch.full((max_tiles * tile,), 0x5A5A5A5A, dtype=torch.int32, device=dev)
+    dcount = to_device(counts.astype(np.uint32), dev)
+    in_b = glu.RadixSort().sort_segmented(dka, dva, dkb, dvb, dcount, counts.size, max_tiles, begin_bit, end_bit)
+    torch.cuda.synchronize()
+    assert in_b == (((end_bit - begin_bit + 7) // 8) % 2 == 1)
+    gk = to_host(dkb if in_b else dka, np.uint32)[:total]
+    gv = to_host(dvb if in_b else dva, np.uint32)[:total]
+    np.testing.assert_array_equal(gk, want_k)
+    np.testing.assert_array_equal(gv, want_v)
+
+
+@pytest.mark.parametrize("bits", [(0, 24), (0, 8), (0, 16), (8, 32), (0, 32), (3, 21)])
+@pytest.mark.parametrize("shape", ["one_small", "empties", "exact_tile", "ragged", "many", "one_big"])
+def test_segmented_sort_matches_per_segment_stable_sort(glu, cuda_device, oracle, bits, shape):
+    tile = int(glu.lib.glu_radix_sort_segment_tile())
+    rng = np.random.default_rng(7)
+    counts = {
+        "one_small": [5],
+        "empties": [0, 7, 0, 0, 1, 0],
+        "exact_tile": [tile, tile, 2 * tile],
+        "ragged": [tile + 1, 1, 0, 3 * tile - 1, 12345, 2, tile - 1],
+        "many": list(rng.integers(0, 3 * tile, size=256)),
+        "one_big": [3, 50 * tile + 17, 0, 9],
+    }[shape]
+    run_case(glu, cuda_device, oracle, counts, bits[0], bits[1], seed=3)
+
+
+def test_segmented_sort_heavy_duplicates_and_skew(glu, cuda_device, oracle):
+    tile = int(glu.lib.glu_radix_sort_segment_tile())
+    counts = [4 * tile + 5, 100_001, 3]
+    run_case(glu, cuda_device, oracle, counts, 0, 24, seed=5, key_transform=lambda k: k % np.uint32(7))
+    run_case(glu, cuda_device, oracle, counts, 0, 24, seed=6, key_transform=lambda k: np.full_like(k, 0x00ABCDEF))
+    run_case(glu, cuda_device, oracle, counts, 0, 24, seed=7, key_transform=lambda k: k & np.uint32(0xFF0000FF))
+
+
+def test_segmented_sort_argument_checks(glu, cuda_device):
+    import torch
+
+    tile = int(glu.lib.glu_radix_sort_segment_tile())
+    buf = torch.zeros(4 * tile, dtype=torch.int32, device=cuda_device)
+    cnt = torch.zeros(4, dtype=torch.int32, device=cuda_device)
+    rs = glu.RadixSort()
+    with pytest.raises(glu.GluError):
+        rs.sort_segmented(buf, buf, buf, buf, cnt, 257, 4)           # too many segments
+    with pytest.raises(glu.GluError):
+        rs.sort_segmented(buf, buf, buf, buf, cnt, 4, 4, 8, 8)        # no key bit takes part
+    with pytest.raises(glu.GluError):
+        rs.sort_segmented(buf[1:], buf, buf, buf, cnt, 4, 3)          # misaligned array (bulk copies need 16 bytes)
