@@ -109,6 +109,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
     };
 
     uint32_t ahead = 0xffffffffu; // thread 0: the ticket drawn for the tile after next
+    // options bits 8..: tiles a CTA may draw before it stops drawing and retires (0 = until the tickets run out).  A
+    // bounded life lets the block scheduler interleave other streams' kernels (the multi-GPU pipeline) at a granularity
+    // of a few tiles; the grid then holds more CTAs than are resident at once, which tickets make safe.
+    uint32_t budget = uint32_t(options) >> 8;
+    budget = budget ? budget : 0xffffffffu;
     uint64_t policy = 0;
     if (tid == 0)
     {
@@ -142,7 +147,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             if constexpr (!KEYS_ONLY)
                 tma_prefetch_l2_1d(vals_in + size_t(t0 + 1) * TILE, TILE * 4);
         }
-        ahead = atomicAdd(ticket, 1u);
+        ahead = budget > 2 ? atomicAdd(ticket, 1u) : 0xffffffffu;
+        budget = budget > 3 ? budget - 3 : 0;
     }
     __syncthreads();
 
@@ -459,7 +465,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                     if constexpr (!KEYS_ONLY)
                         tma_prefetch_l2_1d(vals_in + size_t(ahead) * TILE, TILE * 4);
                 }
-                ahead = atomicAdd(ticket, 1u);
+                ahead = budget ? atomicAdd(ticket, 1u) : 0xffffffffu;
+                budget -= budget ? 1u : 0u;
             }
         }
         cur = nxt;

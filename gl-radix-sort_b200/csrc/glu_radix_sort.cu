@@ -320,6 +320,22 @@ namespace glu_b200
 #pragma unroll
                 for (int j = 0; j < ROWS; j++)
                     q[j] = r0 + BATCH + j < num_tiles ? ld_relaxed_u32(col + size_t(r0 + BATCH + j) * k_radix) : k_lb_local;
+                // what can be done before the predecessor's total arrives: inclusive sums over the leading rows that
+                // are already there (normally all of them — the chain trails the tiles)
+                uint32_t ready = 0; // number of leading rows whose counts are known
+                uint32_t sum[ROWS];
+                {
+                    uint32_t run0 = 0;
+                    bool all = true;
+#pragma unroll
+                    for (int j = 0; j < ROWS; j++)
+                    {
+                        all = all && (p[j] & k_lb_local) != 0;
+                        run0 += p[j] & k_lb_value_mask;
+                        sum[j] = run0;
+                        ready += all ? 1u : 0u;
+                    }
+                }
                 // running total of all rows before mine (it depends on earlier rows only)
                 uint32_t in = 0;
                 if (w > 0 || batch > 0)
@@ -332,7 +348,22 @@ namespace glu_b200
                     __threadfence_block();
                     in = *const_cast<volatile uint32_t*>(&carry[pb & 1][g][pw][lane]);
                 }
-                // my rows in order: prefix row r0 + j is written as soon as count rows <= r0 + j are known
+                if (__all_sync(k_full_mask, ready == uint32_t(ROWS)))
+                {
+                    // the short critical section: hand the running total on, THEN write the prefix rows
+                    *const_cast<volatile uint32_t*>(&carry[batch & 1][g][w][lane]) = in + sum[ROWS - 1];
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0)
+                        seq[g * WPG + w] = batch + 1;
+#pragma unroll
+                    for (int j = 0; j < ROWS; j++)
+                        if (r0 + j < num_tiles)
+                            st_relaxed_u32(prefix + size_t(r0 + j) * k_radix + d, k_lb_inclusive | (in + sum[j]));
+                    continue;
+                }
+                // some row is late: my rows in order — prefix row r0 + j is written as soon as count rows <= r0 + j
+                // are known (a tile of the ring kernel may be waiting for it before it publishes a later row)
                 uint32_t run = in;
 #pragma unroll
                 for (int j = 0; j < ROWS; j++)
@@ -905,7 +936,9 @@ namespace glu_b200
                 ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
             constexpr size_t smem = sizeof(RingSmem<THREADS, IPT, (FLAVOR & k_flavor_keys_only) == 0>);
             const int chain_rows = chain_rows_env();
-            static const int options = env_int("GLU_SORT_OPTIONS", 0) & 0xff;
+            // GLU_SORT_RING_TILES_PER_CTA: a CTA retires after that many tiles (0 = persistent until the tickets run out)
+            static const int life = env_int("GLU_SORT_RING_TILES_PER_CTA", 0);
+            static const int options = (env_int("GLU_SORT_OPTIONS", 0) & 0xff) | ((life > 0 ? (life < 3 ? 3 : life) : 0) << 8);
             static std::atomic<int> resident[64]; // CTAs per SM the hardware really grants, per device (0 = not asked yet)
             int dev = 0;
             GLU_CUDA_TRY(cudaGetDevice(&dev));
@@ -929,6 +962,8 @@ namespace glu_b200
             const unsigned capacity = unsigned(current_sm_count()) * unsigned(per_sm);
             // two tiles per ticket draw at start-up: no point in more CTAs than pairs of tiles
             unsigned workers = capacity > chain ? capacity - chain : 1;
+            if (life > 0) // bounded CTA life: enough CTAs to draw every ticket, whatever is resident at once
+                workers = (tiles + unsigned(life < 3 ? 3 : life) - 1) / unsigned(life < 3 ? 3 : life) + workers;
             if (workers > (tiles + 1) / 2)
                 workers = (tiles + 1) / 2;
             ScopedKernelProfile prof(GLU_KERNEL_SORT_ONESWEEP, s);

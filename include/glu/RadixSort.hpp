@@ -89,6 +89,29 @@ namespace glu
             GLU_CHECK_STATUS(glu_radix_sort_wide(key_buffer, key_bytes, val_buffer, value_bytes, count, descending ? 1 : 0,
                                                  m_tmp.handle(), m_tmp.size(), m_stream));
         }
+
+        /// Many independent stable sorts by key bits [begin_bit, end_bit) in one set of launches
+        /// (glu_radix_sort_u32kv_segmented; the local step of the multi-GPU sort).  Input in the A arrays, segment s —
+        /// seg_count_buffer[s] pairs, a device array — starting at element first_tile[s] * segment_tile() with
+        /// first_tile = exclusive scan of ceil(count / tile); output compact.  Returns true when the result is in the
+        /// B arrays (odd number of 8-bit passes), false when it is in the A arrays.
+        static size_t segment_tile() { return glu_radix_sort_segment_tile(); }
+        bool sort_segmented(DevicePtr keys_a, DevicePtr vals_a, DevicePtr keys_b, DevicePtr vals_b,
+                            DevicePtr seg_count_buffer, size_t num_segments, size_t max_tiles, unsigned begin_bit = 0,
+                            unsigned end_bit = 32)
+        {
+            GLU_CHECK_ARGUMENT(keys_a && vals_a && keys_b && vals_b && seg_count_buffer, "Invalid buffer");
+            const size_t need = glu_radix_sort_u32kv_segmented_tmp_bytes(max_tiles);
+            GLU_CHECK_ARGUMENT(need != 0, "RadixSort: %zu tiles are too many", max_tiles);
+            if (m_tmp.size() < need)
+                m_tmp.resize(need, false);
+            int in_b = 0;
+            GLU_CHECK_STATUS(glu_radix_sort_u32kv_segmented(
+                static_cast<uint32_t*>(keys_a), static_cast<uint32_t*>(vals_a), static_cast<uint32_t*>(keys_b),
+                static_cast<uint32_t*>(vals_b), static_cast<const uint32_t*>(seg_count_buffer), num_segments, max_tiles,
+                begin_bit, end_bit, m_tmp.handle(), m_tmp.size(), m_stream, &in_b));
+            return in_b != 0;
+        }
     };
 } // namespace glu
 

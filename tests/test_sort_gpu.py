@@ -207,7 +207,7 @@ check(np.full(n, 0xDEADBEEF, dtype=np.uint32), v)              # one digit bin i
 check(oracle.mt19937_u32(3, n) & np.uint32(0xFFFF), v)         # 16-bit entropy
 check(np.sort(k)[::-1].copy(), v)
 # device-resident count (glu_radix_sort_u32kv_dyn): the scratch is sized for max_count, the kernels read the count
-cap = 900_000
+cap = 600_000
 for m in (1, 2, 5121, 333_333, cap):
     kk = np.zeros(cap, np.uint32); kk[:m] = k[:m]
     dk, dv = up(kk), up(np.arange(cap, dtype=np.uint32))
