@@ -320,70 +320,70 @@ namespace glu_b200
 #pragma unroll
                 for (int j = 0; j < ROWS; j++)
                     q[j] = r0 + BATCH + j < num_tiles ? ld_relaxed_u32(col + size_t(r0 + BATCH + j) * k_radix) : k_lb_local;
-                // what can be done before the predecessor's total arrives: inclusive sums over the leading rows that
-                // are already there (normally all of them — the chain trails the tiles)
-                uint32_t ready = 0; // number of leading rows whose counts are known
+                // Wait for BOTH the predecessor's running total (`in`, through shared memory) and my rows (global
+                // memory; late rows are asked for again TOGETHER: one L2 round trip per round however many are late) —
+                // at the same time, not one after the other.  While waiting, a row whose predecessors are all known is
+                // published at once: prefix row t depends on count rows <= t ONLY (a tile of the ring kernel waits for
+                // prefix row t - 1 before it publishes the counts of its next tile, which may be one of my later rows).
+                uint32_t in = 0, run = 0;
+                unsigned published = 0; // rows [0, published) of my slice are written
+                bool have_in = (w == 0 && batch == 0);
+                const unsigned pw = w > 0 ? w - 1 : WPG - 1;
+                const uint32_t pb = w > 0 ? batch : batch - 1;
+                while (true)
+                {
+                    if (!have_in && seq[g * WPG + pw] >= pb + 1) // warp-uniform
+                    {
+                        __threadfence_block();
+                        in = *const_cast<volatile uint32_t*>(&carry[pb & 1][g][pw][lane]);
+                        have_in = true;
+                    }
+                    uint32_t all = k_lb_local;
+#pragma unroll
+                    for (int j = 0; j < ROWS; j++)
+                        all &= p[j];
+                    const bool rows_ready = (all & k_lb_local) != 0;
+                    if (have_in && __all_sync(k_full_mask, rows_ready))
+                        break;
+                    if (have_in)
+                    {
+#pragma unroll
+                        for (int j = 0; j < ROWS; j++)
+                            if (unsigned(j) == published && (p[j] & k_lb_local) != 0)
+                            {
+                                run += p[j] & k_lb_value_mask;
+                                if (r0 + j < num_tiles)
+                                    st_relaxed_u32(prefix + size_t(r0 + j) * k_radix + d, k_lb_inclusive | (in + run));
+                                published = unsigned(j) + 1;
+                            }
+                    }
+                    if (!rows_ready)
+                    {
+#pragma unroll
+                        for (int j = 0; j < ROWS; j++)
+                            if ((p[j] & k_lb_local) == 0)
+                                p[j] = ld_relaxed_u32(col + size_t(r0 + j) * k_radix);
+                    }
+                }
+                // everything is known: the short critical section — hand the running total on, THEN write what is left
                 uint32_t sum[ROWS];
-                {
-                    uint32_t run0 = 0;
-                    bool all = true;
-#pragma unroll
-                    for (int j = 0; j < ROWS; j++)
-                    {
-                        all = all && (p[j] & k_lb_local) != 0;
-                        run0 += p[j] & k_lb_value_mask;
-                        sum[j] = run0;
-                        ready += all ? 1u : 0u;
-                    }
-                }
-                // running total of all rows before mine (it depends on earlier rows only)
-                uint32_t in = 0;
-                if (w > 0 || batch > 0)
-                {
-                    const unsigned pw = w > 0 ? w - 1 : WPG - 1;
-                    const uint32_t pb = w > 0 ? batch : batch - 1;
-                    while (seq[g * WPG + pw] < pb + 1)
-                    {
-                    }
-                    __threadfence_block();
-                    in = *const_cast<volatile uint32_t*>(&carry[pb & 1][g][pw][lane]);
-                }
-                if (__all_sync(k_full_mask, ready == uint32_t(ROWS)))
-                {
-                    // the short critical section: hand the running total on, THEN write the prefix rows
-                    *const_cast<volatile uint32_t*>(&carry[batch & 1][g][w][lane]) = in + sum[ROWS - 1];
-                    __threadfence_block();
-                    __syncwarp();
-                    if (lane == 0)
-                        seq[g * WPG + w] = batch + 1;
-#pragma unroll
-                    for (int j = 0; j < ROWS; j++)
-                        if (r0 + j < num_tiles)
-                            st_relaxed_u32(prefix + size_t(r0 + j) * k_radix + d, k_lb_inclusive | (in + sum[j]));
-                    continue;
-                }
-                // some row is late: my rows in order — prefix row r0 + j is written as soon as count rows <= r0 + j
-                // are known (a tile of the ring kernel may be waiting for it before it publishes a later row)
-                uint32_t run = in;
+                uint32_t total = run;
 #pragma unroll
                 for (int j = 0; j < ROWS; j++)
                 {
-                    while ((p[j] & k_lb_local) == 0)
-                    {
-#pragma unroll
-                        for (int jj = j; jj < ROWS; jj++) // late rows are asked for again TOGETHER
-                            if ((p[jj] & k_lb_local) == 0)
-                                p[jj] = ld_relaxed_u32(col + size_t(r0 + jj) * k_radix);
-                    }
-                    run += p[j] & k_lb_value_mask;
-                    if (r0 + j < num_tiles)
-                        st_relaxed_u32(prefix + size_t(r0 + j) * k_radix + d, k_lb_inclusive | run);
+                    if (unsigned(j) >= published)
+                        total += p[j] & k_lb_value_mask;
+                    sum[j] = total;
                 }
-                *const_cast<volatile uint32_t*>(&carry[batch & 1][g][w][lane]) = run;
+                *const_cast<volatile uint32_t*>(&carry[batch & 1][g][w][lane]) = in + total;
                 __threadfence_block();
                 __syncwarp();
                 if (lane == 0)
                     seq[g * WPG + w] = batch + 1;
+#pragma unroll
+                for (int j = 0; j < ROWS; j++)
+                    if (unsigned(j) >= published && r0 + j < num_tiles)
+                        st_relaxed_u32(prefix + size_t(r0 + j) * k_radix + d, k_lb_inclusive | (in + sum[j]));
             }
         }
 
