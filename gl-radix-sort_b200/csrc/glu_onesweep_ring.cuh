@@ -10,11 +10,11 @@
 //       1. digit threads: scan of the tile's digit counts -> per-warp slot offsets
 //       2. ranking warps: ballot match, keys straight to their tile-sorted slot (in place); each warp clears its
 //          own counter row when it is done with it
-//       3. values (bulk copy issued one iteration ago) -> registers; digit threads read ONE prefix row -> gbase;
+//       3. EARLY COUNTS of tile k + 1: its keys (bulk copy issued one iteration ago into the other ring slot) go to
+//          registers and into the warp's counters, and its count row is PUBLISHED — an iteration before tile k + 1 is
+//          processed and BEFORE tile k's look-back: a tile's counts never wait for anything but its own bulk copy
+//       4. values (bulk copy issued one iteration ago) -> registers; digit threads read ONE prefix row -> gbase;
 //          values -> tile-sorted slot (in place)
-//       4. EARLY COUNTS of tile k + 1: its keys (bulk copy issued one iteration ago into the other ring slot) go to
-//          registers and into the warp's counters, and its count row is PUBLISHED — long before tile k + 1 is
-//          processed, and after tile k's look-back (chain_cta: prefix row t depends on count rows <= t only)
 //       5. tile k leaves: consecutive threads, consecutive addresses inside every digit run
 //       6. one thread refills: values of tile k + 1, keys of tile k + 2 (ticket drawn an iteration earlier), L2
 //          prefetch of the values of tile k + 2
@@ -93,11 +93,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
         uint32_t* totals = reinterpret_cast<uint32_t*>(&s.warp_hist[0][0]);
         switch (chain_rows)
         {
-        case 2: chain_cta<WARPS, 2, 1>(totals, blockIdx.x, lookback, prefix, num_tiles); break;
-        case 4: chain_cta<WARPS, 4, 1>(totals, blockIdx.x, lookback, prefix, num_tiles); break;
-        case 104: chain_cta<WARPS, 4, 2>(totals, blockIdx.x, lookback, prefix, num_tiles); break;
-        case 108: chain_cta<WARPS, 8, 2>(totals, blockIdx.x, lookback, prefix, num_tiles); break;
-        default: chain_cta<WARPS, 8, 1>(totals, blockIdx.x, lookback, prefix, num_tiles); break;
+        case 2: chain_cta<WARPS, 2, 1, true>(totals, blockIdx.x, lookback, prefix, num_tiles); break;
+        case 4: chain_cta<WARPS, 4, 1, true>(totals, blockIdx.x, lookback, prefix, num_tiles); break;
+        case 104: chain_cta<WARPS, 4, 2, true>(totals, blockIdx.x, lookback, prefix, num_tiles); break;
+        case 108: chain_cta<WARPS, 8, 2, true>(totals, blockIdx.x, lookback, prefix, num_tiles); break;
+        default: chain_cta<WARPS, 8, 1, true>(totals, blockIdx.x, lookback, prefix, num_tiles); break;
         }
         return;
     }
@@ -336,7 +336,20 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             reinterpret_cast<uint4*>(wh)[lane + 32] = make_uint4(0, 0, 0, 0);
         }
 
-        // ---- 3. values -> registers; this digit's count in all earlier tiles (one row, written by the chain CTA)
+        // ---- 3. early counts of the next tile (its keys stay in registers until iteration it + 1 ranks them).  They are
+        //         published BEFORE this tile's look-back: a tile's counts never wait for anything but its own bulk copy,
+        //         so the chain CTAs always find them there.
+        const uint32_t nxt = s.tile_of[b ^ 1u];
+        const bool has_next = nxt < num_tiles;
+        uint2 nxt_info = make_uint2(0, 0);
+        if constexpr (SEG)
+            nxt_info = s.info_of[b ^ 1u];
+        __syncwarp(); // the cleared counters
+        if (has_next)
+            load_and_count(b ^ 1u, nxt, nxt_info.x);
+
+        // ---- 4. values -> registers; next tile's counts published; this digit's count in all earlier tiles (one row,
+        //         written by the chain CTA); values -> tile-sorted slot
         {
             uint32_t val[KEYS_ONLY ? 2 : IPT];
             if constexpr (!KEYS_ONLY)
@@ -356,8 +369,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                         val[i] = my_off + i * 32 < valid ? vals_in[tile_base + my_off + i * 32] : 0u;
                 }
             }
+            __syncthreads(); // all values are in registers; the next tile's counts are final; keys are tile-sorted
             if (tid < k_radix)
             {
+                if (has_next)
+                    total = publish(nxt, nxt_info.x);
                 uint32_t exclusive = 0;
                 const uint32_t first = SEG ? cur_info.y : 0u; // first tile of the sequence this tile belongs to
                 if (tile > first && !(options & k_opt_no_lookback)) // k_opt_no_lookback: timing experiments only
@@ -382,7 +398,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
             }
             if constexpr (!KEYS_ONLY)
             {
-                __syncthreads(); // all values are in registers
 #pragma unroll
                 for (int i = 0; i < IPT; i += 2)
                 {
@@ -391,18 +406,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
                 }
             }
         }
-        // ---- 4. early counts of the next tile (its keys stay in registers until iteration it + 1 ranks them),
-        //         published right away: its successors' look-back never waits for this CTA to get there
-        const uint32_t nxt = s.tile_of[b ^ 1u];
-        const bool has_next = nxt < num_tiles;
-        uint2 nxt_info = make_uint2(0, 0);
-        if constexpr (SEG)
-            nxt_info = s.info_of[b ^ 1u];
-        if (has_next)
-            load_and_count(b ^ 1u, nxt, nxt_info.x);
-        __syncthreads(); // tile-sorted keys and values, gbase; the next tile's counts
-        if (has_next && tid < k_radix)
-            total = publish(nxt, nxt_info.x);
+        __syncthreads(); // tile-sorted keys and values, gbase
 
         // ---- 5. out: consecutive threads write consecutive addresses inside each digit run
         if (full)

@@ -286,10 +286,11 @@ namespace glu_b200
         // consecutive rows of the batch, requests them all at once (late rows are asked for again TOGETHER: one L2
         // round trip per polling round however many are late), takes the running total of everything before its
         // rows from its predecessor warp through shared memory (a ring: warp 0 continues from the last warp of the
-        // previous batch), walks its rows in order — prefix row t is written the moment count rows <= t are known,
-        // so prefix[t] NEVER depends on a later tile (the ring kernel publishes tile t + 1's counts only after tile
-        // t's look-back) — and hands its own running total on.  The next batch's requests are in flight meanwhile.
-        template<int WARPS, int ROWS, int GROUPS>
+        // previous batch) and hands its own running total on.  ORDERED (the ring kernel, whose CTAs hold tickets of
+        // tiles they have not counted yet): prefix row t is written the moment count rows <= t are known, so it NEVER
+        // depends on a later tile; otherwise a warp simply waits for all rows of its slice.  The next batch's requests
+        // are in flight meanwhile.
+        template<int WARPS, int ROWS, int GROUPS, bool ORDERED = false>
         __device__ __noinline__ void chain_cta(uint32_t* smem, uint32_t chain_id, const uint32_t* lookback,
                                                uint32_t* prefix, uint32_t num_tiles)
         {
@@ -309,6 +310,64 @@ namespace glu_b200
 #pragma unroll
             for (int j = 0; j < ROWS; j++)
                 q[j] = w * ROWS + j < num_tiles ? ld_relaxed_u32(col + size_t(w * ROWS + j) * k_radix) : k_lb_local;
+            if constexpr (!ORDERED)
+            {
+                // one tile per CTA (onesweep_kernel): every tile publishes its counts before it waits for anything, so a
+                // warp may wait for ALL rows of its slice first — the shortest hand-off path
+                uint32_t batch = 0;
+                for (uint32_t t0 = 0; t0 < num_tiles; t0 += BATCH, batch++)
+                {
+                    const uint32_t r0 = t0 + w * ROWS;
+#pragma unroll
+                    for (int j = 0; j < ROWS; j++)
+                        p[j] = q[j];
+                    while (true)
+                    {
+                        uint32_t all = k_lb_local;
+#pragma unroll
+                        for (int j = 0; j < ROWS; j++)
+                            all &= p[j];
+                        if (all & k_lb_local)
+                            break;
+#pragma unroll
+                        for (int j = 0; j < ROWS; j++)
+                            if ((p[j] & k_lb_local) == 0)
+                                p[j] = ld_relaxed_u32(col + size_t(r0 + j) * k_radix);
+                    }
+#pragma unroll
+                    for (int j = 0; j < ROWS; j++)
+                        q[j] = r0 + BATCH + j < num_tiles ? ld_relaxed_u32(col + size_t(r0 + BATCH + j) * k_radix) : k_lb_local;
+                    uint32_t run = 0;
+#pragma unroll
+                    for (int j = 0; j < ROWS; j++)
+                    {
+                        run += p[j] & k_lb_value_mask;
+                        p[j] = run;
+                    }
+                    // running total of all rows before mine
+                    uint32_t in = 0;
+                    if (w > 0 || batch > 0)
+                    {
+                        const unsigned pw = w > 0 ? w - 1 : WPG - 1;
+                        const uint32_t pb = w > 0 ? batch : batch - 1;
+                        while (seq[g * WPG + pw] < pb + 1)
+                        {
+                        }
+                        __threadfence_block();
+                        in = *const_cast<volatile uint32_t*>(&carry[pb & 1][g][pw][lane]);
+                    }
+                    *const_cast<volatile uint32_t*>(&carry[batch & 1][g][w][lane]) = in + run;
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0)
+                        seq[g * WPG + w] = batch + 1;
+#pragma unroll
+                    for (int j = 0; j < ROWS; j++)
+                        if (r0 + j < num_tiles)
+                            st_relaxed_u32(prefix + size_t(r0 + j) * k_radix + d, k_lb_inclusive | (in + p[j]));
+                }
+                return;
+            }
             uint32_t batch = 0;
             for (uint32_t t0 = 0; t0 < num_tiles; t0 += BATCH, batch++)
             {
@@ -1628,6 +1687,187 @@ extern "C" int glu_radix_exchange_plan_buckets(const uint32_t* d_hist_all, int w
         d_hist_all, world, rank, uint32_t(send_count), uint32_t(capacity_tiles), uint32_t(glu_radix_sort_segment_tile()),
         d_peer_keys, d_peer_vals, reinterpret_cast<uint64_t*>(d_key_dst), reinterpret_cast<uint64_t*>(d_val_dst), d_seg_count,
         d_counts, d_info);
+    GLU_LAUNCH_CHECK();
+    return GLU_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------ staged exchange: local MSD pass + long-run peer copy
+
+namespace glu_b200
+{
+namespace
+{
+    // One CTA of 256 threads, thread b = bucket b: where this rank's pairs of bucket b go in its own bucket-major
+    // staging arrays (exclusive scan of its 256 counts) — the pointer table of the local MSD pass.
+    __global__ void __launch_bounds__(k_radix, 1)
+        exchange_stage_tables_kernel(const uint32_t* __restrict__ my_hist, uint64_t stage_keys, uint64_t stage_vals,
+                                     uint64_t* stage_key_dst, uint64_t* stage_val_dst, uint32_t* stage_off)
+    {
+        __shared__ uint32_t s_warp[k_radix / 32];
+        const unsigned b = threadIdx.x, lane = b & 31, warp = b >> 5;
+        const uint32_t c = my_hist[b];
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(k_full_mask, inc, o);
+            if (lane >= unsigned(o))
+                inc += t;
+        }
+        if (lane == 31)
+            s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t off = inc - c;
+        for (unsigned w = 0; w < warp; w++)
+            off += s_warp[w];
+        stage_off[b] = off;
+        stage_key_dst[b] = stage_keys + 4ull * off;
+        stage_val_dst[b] = stage_vals + 4ull * off;
+    }
+
+    // The all-to-all itself: this rank's run of bucket b — count[b] pairs at stage_off[b] of the staging arrays — goes to
+    // key_dst[b] / val_dst[b] (peer memory over NVLink for remote buckets).  Runs are long (count / 256 pairs), so every
+    // warp-wide store is one full, aligned 128-byte line of its destination: the row grid of a bucket starts at the
+    // line its destination starts in (only the first and last line of a run are partial).  Few CTAs saturate the links;
+    // the rest of the GPU keeps sorting (the two-lane pipeline runs this under the previous job's local sort).
+    constexpr int k_copy_threads = 256, k_copy_unroll = 4;
+    __global__ void __launch_bounds__(k_copy_threads)
+        exchange_copy_kernel(const uint32_t* __restrict__ stage_keys, const uint32_t* __restrict__ stage_vals,
+                             const uint32_t* __restrict__ stage_off, const uint32_t* __restrict__ count,
+                             uint32_t* const* __restrict__ key_dst, uint32_t* const* __restrict__ val_dst)
+    {
+        __shared__ uint32_t s_off[k_radix], s_cnt[k_radix], s_shift[k_radix], s_rows[k_radix + 1], s_warp[k_radix / 32];
+        __shared__ uint32_t* s_kd[k_radix];
+        __shared__ uint32_t* s_vd[k_radix];
+        const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        {
+            uint32_t* kd = key_dst[tid];
+            uint32_t c = kd ? count[tid] : 0u; // a null destination: the plan found an overflow, nothing moves
+            const uint32_t shift32 = uint32_t(reinterpret_cast<uintptr_t>(kd) >> 2) & 31u;
+            const uint32_t rows = c ? (shift32 + c + 31u) / 32u : 0u;
+            s_off[tid] = stage_off[tid];
+            s_cnt[tid] = c;
+            s_shift[tid] = shift32;
+            s_kd[tid] = kd;
+            s_vd[tid] = val_dst[tid];
+            uint32_t inc = rows;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t t = __shfl_up_sync(k_full_mask, inc, o);
+                if (lane >= unsigned(o))
+                    inc += t;
+            }
+            if (lane == 31)
+                s_warp[warp] = inc;
+            __syncthreads();
+            uint32_t before = inc - rows;
+            for (unsigned w = 0; w < warp; w++)
+                before += s_warp[w];
+            s_rows[tid] = before;
+            if (tid == k_radix - 1)
+                s_rows[k_radix] = before + rows;
+            __syncthreads();
+        }
+        const uint32_t total_rows = s_rows[k_radix];
+        const uint32_t warps = gridDim.x * (k_copy_threads / 32);
+        const uint32_t per = (total_rows + warps - 1) / warps; // a contiguous range of rows per warp
+        const uint32_t gw = blockIdx.x * (k_copy_threads / 32) + warp;
+        uint32_t r = gw * per;
+        const uint32_t r_end = r + per < total_rows ? r + per : total_rows;
+        if (r >= r_end)
+            return;
+        // bucket of row r: the last b with s_rows[b] <= r among the non-empty ones
+        uint32_t b;
+        {
+            uint32_t lo = 0, hi = k_radix;
+            while (hi - lo > 1)
+            {
+                const uint32_t mid = (lo + hi) / 2;
+                if (s_rows[mid] <= r)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            b = lo;
+        }
+        while (r < r_end)
+        {
+            uint32_t kk[k_copy_unroll], vv[k_copy_unroll];
+            uint32_t* kp[k_copy_unroll];
+            uint32_t* vp[k_copy_unroll];
+#pragma unroll
+            for (int u = 0; u < k_copy_unroll; u++)
+            {
+                kp[u] = nullptr;
+                vp[u] = nullptr;
+                if (r < r_end)
+                {
+                    while (r >= s_rows[b + 1]) // rows are consecutive: the bucket only moves forward
+                        b++;
+                    const int32_t e = int32_t((r - s_rows[b]) * 32u + lane) - int32_t(s_shift[b]);
+                    if (e >= 0 && uint32_t(e) < s_cnt[b])
+                    {
+                        kk[u] = ld_stream_u32(stage_keys + s_off[b] + e);
+                        vv[u] = ld_stream_u32(stage_vals + s_off[b] + e);
+                        kp[u] = s_kd[b] + e;
+                        vp[u] = s_vd[b] + e;
+                    }
+                    r++;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < k_copy_unroll; u++)
+                if (kp[u])
+                {
+                    *kp[u] = kk[u];
+                    *vp[u] = vv[u];
+                }
+        }
+    }
+} // namespace
+} // namespace glu_b200
+
+extern "C" int glu_radix_exchange_stage_tables(const uint32_t* d_my_hist, uint32_t* d_stage_keys, uint32_t* d_stage_vals,
+                                               uint32_t** d_stage_key_dst, uint32_t** d_stage_val_dst,
+                                               uint32_t* d_stage_off, glu_stream_t stream)
+{
+    if (!d_my_hist || !d_stage_keys || !d_stage_vals || !d_stage_key_dst || !d_stage_val_dst || !d_stage_off)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(d_my_hist) | reinterpret_cast<uintptr_t>(d_stage_off) |
+         reinterpret_cast<uintptr_t>(d_stage_keys) | reinterpret_cast<uintptr_t>(d_stage_vals)) % sizeof(uint32_t) != 0 ||
+        (reinterpret_cast<uintptr_t>(d_stage_key_dst) | reinterpret_cast<uintptr_t>(d_stage_val_dst)) % sizeof(uint64_t) != 0)
+        return GLU_ERROR_MISALIGNED;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    exchange_stage_tables_kernel<<<1, k_radix, 0, s>>>(d_my_hist, reinterpret_cast<uint64_t>(d_stage_keys),
+                                                       reinterpret_cast<uint64_t>(d_stage_vals),
+                                                       reinterpret_cast<uint64_t*>(d_stage_key_dst),
+                                                       reinterpret_cast<uint64_t*>(d_stage_val_dst), d_stage_off);
+    GLU_LAUNCH_CHECK();
+    return GLU_SUCCESS;
+}
+
+extern "C" int glu_radix_exchange_copy_u32kv(const uint32_t* d_stage_keys, const uint32_t* d_stage_vals,
+                                             const uint32_t* d_stage_off, const uint32_t* d_count,
+                                             uint32_t* const* d_key_dst, uint32_t* const* d_val_dst, int num_ctas,
+                                             glu_stream_t stream)
+{
+    if (!d_stage_keys || !d_stage_vals || !d_stage_off || !d_count || !d_key_dst || !d_val_dst)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    if ((reinterpret_cast<uintptr_t>(d_stage_keys) | reinterpret_cast<uintptr_t>(d_stage_vals) |
+         reinterpret_cast<uintptr_t>(d_stage_off) | reinterpret_cast<uintptr_t>(d_count)) % sizeof(uint32_t) != 0 ||
+        (reinterpret_cast<uintptr_t>(d_key_dst) | reinterpret_cast<uintptr_t>(d_val_dst)) % sizeof(void*) != 0)
+        return GLU_ERROR_MISALIGNED;
+    const int sms = current_sm_count();
+    if (sms <= 0)
+        return GLU_ERROR_CUDA;
+    // default: one CTA per SM (GLU_EXCHANGE_COPY_CTAS for sweeps) — NVLink-bound, it needs no more
+    static const int env_ctas = env_int("GLU_EXCHANGE_COPY_CTAS", 0);
+    const int ctas = num_ctas > 0 ? num_ctas : (env_ctas > 0 ? env_ctas : sms);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ScopedKernelProfile prof(GLU_KERNEL_SORT_PARTITION, s);
+    exchange_copy_kernel<<<unsigned(ctas), k_copy_threads, 0, s>>>(d_stage_keys, d_stage_vals, d_stage_off, d_count, d_key_dst,
+                                                                   d_val_dst);
     GLU_LAUNCH_CHECK();
     return GLU_SUCCESS;
 }

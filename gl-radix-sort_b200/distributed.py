@@ -272,6 +272,18 @@ class DistributedRadixSort:
             self._alt_keys = torch.empty(seg_capacity, dtype=torch.int32, device=self.device)
             self._alt_vals = torch.empty(seg_capacity, dtype=torch.int32, device=self.device)
             self._seg_count = torch.zeros(RADIX, dtype=torch.int32, device=self.device)
+            # How the bucket-major exchange crosses NVLink.  "staged": a local MSD pass into this rank's own bucket-major
+            # staging arrays (full HBM speed), then a copy kernel that moves each bucket's long run with full-line
+            # stores on a few CTAs.  "direct": the MSD pass stores straight into the peers' memory (no staging, 16 B of
+            # HBM traffic less per pair, but ~30-pair runs: byte-masked NVLink packets).
+            self.exchange_style = os.environ.get("GLU_DIST_EXCHANGE_STYLE", "staged")
+            if self.exchange_style not in ("staged", "direct"):
+                raise ValueError(self.exchange_style)
+            if self.exchange_style == "staged":
+                self._stage_k = torch.empty(self.max_count, dtype=torch.int32, device=self.device)
+                self._stage_v = torch.empty(self.max_count, dtype=torch.int32, device=self.device)
+                # [256 key pointers][256 value pointers] of the local MSD pass, then [256] staging offsets (as 128 int64)
+                self._stage_tables = torch.zeros(2 * RADIX + RADIX // 2, dtype=torch.int64, device=self.device)
             self._sorter._scratch.ensure(int(glu.lib.glu_radix_sort_u32kv_segmented_tmp_bytes(self.capacity_tiles)),
                                          self.device)
         else:
@@ -497,8 +509,23 @@ class DistributedRadixSort:
         self._hist_host.copy_(self._hist_all, non_blocking=True)
         self._plan_event.record()
         mark("histogram+allgather+plan")
-        if self.local == "segmented":
-            # one run per (bucket, source): the receiver gets its buckets contiguous, ready for the segmented sort
+        if self.local == "segmented" and self.exchange_style == "staged":
+            # one run per (bucket, source) at the receiver, its buckets contiguous, ready for the segmented sort:
+            # local MSD pass into the staging arrays, then the long-run copy over NVLink
+            sptr = self._stage_tables.data_ptr()
+            my_hist = self._hist_all.data_ptr() + 4 * RADIX * rank
+            glu.check(glu.lib.glu_radix_exchange_stage_tables(my_hist, self._stage_k.data_ptr(), self._stage_v.data_ptr(),
+                                                              sptr, sptr + 8 * RADIX, sptr + 16 * RADIX, st),
+                      "glu_radix_exchange_stage_tables")
+            glu.check(glu.lib.glu_radix_partition_u32kv_dyn(kptr, vptr, cptr, count, shift, RADIX_BITS, sptr,
+                                                            sptr + 8 * RADIX, self._part_tmp.data_ptr(),
+                                                            self._part_tmp.numel(), st),
+                      "glu_radix_partition_u32kv_dyn (local MSD pass)")
+            glu.check(glu.lib.glu_radix_exchange_copy_u32kv(self._stage_k.data_ptr(), self._stage_v.data_ptr(),
+                                                            sptr + 16 * RADIX, my_hist, tptr, tptr + 8 * RADIX, 0, st),
+                      "glu_radix_exchange_copy_u32kv")
+        elif self.local == "segmented":
+            # the MSD pass stores straight into the peers' memory
             glu.check(glu.lib.glu_radix_partition_u32kv_dyn(kptr, vptr, cptr, count, shift, RADIX_BITS, tptr,
                                                             tptr + 8 * RADIX, self._part_tmp.data_ptr(),
                                                             self._part_tmp.numel(), st),
@@ -566,6 +593,7 @@ class DistributedRadixSort:
         self._sorter = None
         self._part_tmp = None
         self._alt_keys = self._alt_vals = None
+        self._stage_k = self._stage_v = None
 
     def __del__(self):
         try:

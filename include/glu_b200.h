@@ -267,6 +267,20 @@ GLU_API int glu_radix_exchange_plan_buckets(const uint32_t* d_hist_all, int worl
                                             uint32_t* d_seg_count, uint32_t* d_counts, uint64_t* d_info,
                                             glu_stream_t stream);
 
+/* The STAGED form of the bucket-major exchange: (1) a local MSD pass (glu_radix_partition_u32kv_dyn with the table
+ * written by glu_radix_exchange_stage_tables) brings this rank's pairs into bucket-major order in its own staging arrays
+ * at full HBM speed; (2) glu_radix_exchange_copy_u32kv moves every bucket's run — count[b] pairs at d_stage_off[b] — to
+ * d_key_dst[b] / d_val_dst[b] (the tables of glu_radix_exchange_plan_buckets; peer memory over NVLink).  The runs are
+ * long, so every warp-wide store is one full aligned 128-byte line, and a grid of one CTA per SM (num_ctas <= 0) keeps
+ * the links busy while the rest of the GPU sorts.  d_my_hist / d_count: this rank's 256 split-digit counts (its row of
+ * the all-gathered histograms).  Buckets whose destination pointer is NULL (overflow) are skipped. */
+GLU_API int glu_radix_exchange_stage_tables(const uint32_t* d_my_hist, uint32_t* d_stage_keys, uint32_t* d_stage_vals,
+                                            uint32_t** d_stage_key_dst, uint32_t** d_stage_val_dst, uint32_t* d_stage_off,
+                                            glu_stream_t stream);
+GLU_API int glu_radix_exchange_copy_u32kv(const uint32_t* d_stage_keys, const uint32_t* d_stage_vals,
+                                          const uint32_t* d_stage_off, const uint32_t* d_count, uint32_t* const* d_key_dst,
+                                          uint32_t* const* d_val_dst, int num_ctas, glu_stream_t stream);
+
 /* CUDA IPC plumbing for one-process-per-GPU peer access: export a glu_malloc'ed allocation, map a peer's. */
 #define GLU_IPC_HANDLE_BYTES 64
 GLU_API int glu_ipc_get_handle(void* d_ptr, unsigned char handle[GLU_IPC_HANDLE_BYTES]);
