@@ -33,7 +33,7 @@ namespace glu_b200
         constexpr uint32_t k_lb_local = 1u << 30;     // counts row: tile-local digit count published (bits 0..29)
         constexpr uint32_t k_lb_inclusive = 1u << 31; // prefix row: inclusive count over tiles 0..t (bits 0..30)
         constexpr uint32_t k_lb_value_mask = (1u << 30) - 1u;
-        constexpr int k_opt_no_lookback = 1, k_opt_ticket = 2; // GLU_SORT_OPTIONS bits
+        constexpr int k_opt_no_lookback = 1, k_opt_ticket = 2, k_opt_copy4 = 4, k_opt_copy16 = 8; // GLU_SORT_OPTIONS bits
         // onesweep_kernel FLAVOR bits (glu_radix_sort_u32_ex): no value array; digits complemented (descending order)
         constexpr int k_flavor_keys_only = 1, k_flavor_descending = 2;
         // 31-bit running digit counts in the prefix rows (bit 31 is the flag), 32-bit element indices
@@ -474,7 +474,12 @@ namespace glu_b200
         // FLAVOR (glu_radix_sort_u32_ex): k_flavor_keys_only — there is no value array (vals_in / vals_out are not
         // touched); k_flavor_descending — the pass partitions by the complemented digit, which sorts descending and
         // keeps equal keys in input order.  FLAVOR 0 compiles to exactly the code it was before the flavours existed.
-        template<int RANK_THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false, int FLAVOR = 0>
+        //
+        // SEG (glu_radix_sort_seg.cuh): many independent segments in one launch — tile t is elements [t * TILE, (t + 1) *
+        // TILE) of a tile-aligned layout, tile_info[t] = {valid | segment << 24, first tile of the segment}, digit_offset
+        // is [segment][256] incl. the output base, *d_n the number of tiles; see onesweep_ring_kernel.
+        template<int RANK_THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false, int FLAVOR = 0,
+                 bool SEG = false>
         __global__ void __launch_bounds__(RANK_THREADS, MIN_BLOCKS)
             onesweep_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                             uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
@@ -482,9 +487,10 @@ namespace glu_b200
                             uint32_t* lookback, uint32_t* prefix, uint32_t* ticket, uint32_t num_tiles, int allow_tma,
                             int chain_rows, int options, const uint32_t* __restrict__ d_n = nullptr,
                             uint32_t* const* key_dst = nullptr, uint32_t* const* val_dst = nullptr,
-                            const uint8_t* __restrict__ dest_lut = nullptr)
+                            const uint8_t* __restrict__ dest_lut = nullptr, const uint2* __restrict__ tile_info = nullptr)
         {
             static_assert(!DEST || PEER, "DEST is a flavour of PEER");
+            static_assert(!SEG || (!PEER && FLAVOR == 0), "SEG is a flavour of the plain key/value pass");
             static_assert(RANK_THREADS >= k_radix && RANK_THREADS % 32 == 0, "one ranking thread per digit");
             static_assert(IPT % 2 == 0, "ranks are packed two per register");
             static_assert(FLAVOR == 0 || !PEER, "the flavours belong to the single-GPU sort");
@@ -502,7 +508,12 @@ namespace glu_b200
 
             const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
             const uint32_t chain_ctas = chain_rows >= 100 ? 4u : 8u; // 64 or 32 digits per chain CTA
-            if (d_n)
+            if constexpr (SEG)
+            {
+                num_tiles = __ldg(d_n);
+                n = num_tiles * uint32_t(TILE);
+            }
+            else if (d_n)
             {
                 // *_dyn entry points: the count is device-resident (<= the n the grid and the scratch were sized
                 // for); CTAs past the last tile leave at once
@@ -579,9 +590,13 @@ namespace glu_b200
             if (tile >= num_tiles)
                 return;
             const uint32_t tile_base = tile * uint32_t(TILE);
-            const uint32_t valid = n - tile_base < uint32_t(TILE) ? n - tile_base : uint32_t(TILE);
+            uint2 info = make_uint2(0, 0);
+            if constexpr (SEG)
+                info = tile_info[tile];
+            const uint32_t valid =
+                SEG ? (info.x & 0xffffffu) : (n - tile_base < uint32_t(TILE) ? n - tile_base : uint32_t(TILE));
             const bool full = valid == uint32_t(TILE);
-            const bool use_tma = full && allow_tma;
+            const bool use_tma = (SEG || full) && allow_tma; // SEG: every tile is a whole bulk copy, padding is masked below
             const uint32_t my_off = warp * WARP_ELEMS + lane; // + i * 32   (warp-striped)
 
             // ---- stage the tile
@@ -610,6 +625,40 @@ namespace glu_b200
             };
             const uint32_t pad_digit = DEST ? PAD_DEST : digit_of(PAD_KEY);
 
+            // GLU_SORT_OPTIONS bits 2 / 3 (timing experiments only, wrong results): the tile is written straight back —
+            // what a pass costs when nothing but its memory traffic is left (bit 2: 4-byte stores like the real
+            // write-out, bit 3: 16-byte stores); the look-back protocol still runs so that the chain CTAs terminate
+            if constexpr (!PEER && FLAVOR == 0 && !SEG)
+            {
+                if (options & (k_opt_copy4 | k_opt_copy16))
+                {
+                    if (use_tma)
+                    {
+                        mbarrier_wait(&s.bar_keys, 0);
+                        mbarrier_wait(&s.bar_vals, 0);
+                    }
+                    if (tid < k_radix)
+                        st_relaxed_u32(&lookback[size_t(tile) * k_radix + tid], k_lb_local | (tid == 0 ? valid : 0u));
+                    if ((options & k_opt_copy16) && full)
+                    {
+                        for (uint32_t p = tid; p < uint32_t(TILE / 4); p += THREADS)
+                        {
+                            reinterpret_cast<uint4*>(keys_out + tile_base)[p] = reinterpret_cast<const uint4*>(s.keys)[p];
+                            reinterpret_cast<uint4*>(vals_out + tile_base)[p] = reinterpret_cast<const uint4*>(s.vals)[p];
+                        }
+                    }
+                    else
+                    {
+                        for (uint32_t p = tid; p < valid; p += THREADS)
+                        {
+                            keys_out[tile_base + p] = s.keys[p];
+                            vals_out[tile_base + p] = s.vals[p];
+                        }
+                    }
+                    return;
+                }
+            }
+
             // ---- early counts: the warp's digit histogram
             uint32_t key[IPT];
             uint32_t* wh = s.warp_hist[warp];
@@ -619,6 +668,15 @@ namespace glu_b200
 #pragma unroll
                 for (int i = 0; i < IPT; i++)
                     key[i] = s.keys[my_off + i * 32];
+                if constexpr (SEG)
+                {
+                    if (!full) // the last tile of a segment: what lies behind it is not data
+                    {
+#pragma unroll
+                        for (int i = 0; i < IPT; i++)
+                            key[i] = my_off + i * 32 < valid ? key[i] : PAD_KEY;
+                    }
+                }
                 if constexpr (DEST)
                 {
                     // a handful of destinations: plain atomics would pile up on the same few words, so the lanes
@@ -737,13 +795,23 @@ namespace glu_b200
                 if (tid < k_radix)
                 {
                     uint32_t exclusive = 0;
-                    if (tile > 0 && !(options & k_opt_no_lookback)) // k_opt_no_lookback: timing experiments only
+                    const uint32_t first = SEG ? info.y : 0u; // first tile of the sequence this tile belongs to
+                    if (tile > first && !(options & k_opt_no_lookback)) // k_opt_no_lookback: timing experiments only
                     {
                         const uint32_t* p = prefix + size_t(tile - 1) * k_radix + tid;
                         uint32_t x = ld_relaxed_u32(p);
                         while ((x & k_lb_inclusive) == 0)
                             x = ld_relaxed_u32(p);
                         exclusive = x & ~k_lb_inclusive;
+                        if (SEG && first > 0)
+                        {
+                            // the running prefix does not restart at a segment: take off what precedes the segment
+                            const uint32_t* q = prefix + size_t(first - 1) * k_radix + tid;
+                            uint32_t y = ld_relaxed_u32(q);
+                            while ((y & k_lb_inclusive) == 0)
+                                y = ld_relaxed_u32(q);
+                            exclusive -= y & ~k_lb_inclusive;
+                        }
                     }
                     if constexpr (PEER)
                     {
@@ -755,7 +823,8 @@ namespace glu_b200
                         s.dst.val[tid] = in_table ? val_dst[tid] + off : nullptr;
                     }
                     else
-                        s.gbase[tid] = digit_offset[tid] + exclusive - s.tile_start[tid];
+                        s.gbase[tid] = digit_offset[(SEG ? (info.x >> 24) * uint32_t(k_radix) : 0u) + tid] + exclusive -
+                                       s.tile_start[tid];
                 }
                 if constexpr (!KEYS_ONLY)
                 {
@@ -941,16 +1010,17 @@ namespace glu_b200
             return l;
         }
 
-        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false, int FLAVOR = 0>
+        template<int THREADS, int IPT, int MIN_BLOCKS, int MODE, bool PEER = false, bool DEST = false, int FLAVOR = 0,
+                 bool SEG = false>
         int launch_sweep(const uint32_t* ki, const uint32_t* vi, uint32_t* ko, uint32_t* vo, uint32_t n, uint32_t shift,
                          uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback, uint32_t* ticket,
                          unsigned tiles, cudaStream_t s, const uint32_t* d_n = nullptr,
                          uint32_t* const* key_dst = nullptr, uint32_t* const* val_dst = nullptr,
-                         const uint8_t* dest_lut = nullptr)
+                         const uint8_t* dest_lut = nullptr, const uint2* tile_info = nullptr)
         {
             // per pass: `tiles` count rows followed by `tiles` prefix rows; grid = tiles + the chain CTAs
             uint32_t* prefix = lookback + size_t(tiles) * k_radix;
-            auto kernel = onesweep_kernel<THREADS, IPT, MIN_BLOCKS, MODE, PEER, DEST, FLAVOR>;
+            auto kernel = onesweep_kernel<THREADS, IPT, MIN_BLOCKS, MODE, PEER, DEST, FLAVOR, SEG>;
             // TMA bulk copies need 16-byte aligned sources (tiles are multiples of 4 elements); vi is null without values
             const int allow_tma =
                 ((reinterpret_cast<uintptr_t>(ki) | reinterpret_cast<uintptr_t>(vi)) & 15) == 0 && use_tma_env();
@@ -977,7 +1047,8 @@ namespace glu_b200
             const unsigned grid = tiles + (chain_rows >= 100 ? 4 : 8);
             ScopedKernelProfile prof(PEER ? GLU_KERNEL_SORT_PARTITION : GLU_KERNEL_SORT_ONESWEEP, s);
             kernel<<<grid, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
-                                                    tiles, allow_tma, chain_rows, options, d_n, key_dst, val_dst, dest_lut);
+                                                    tiles, allow_tma, chain_rows, options, d_n, key_dst, val_dst, dest_lut,
+                                                    tile_info);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }

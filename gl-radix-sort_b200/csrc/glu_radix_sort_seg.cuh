@@ -24,8 +24,12 @@ namespace glu_b200
 {
 namespace
 {
-    constexpr int k_seg_threads = 480, k_seg_ipt = 16, k_seg_blocks = 2; // the ring shape of the segmented passes
+    // tile shapes of the segmented passes: the ring kernel's and the one-tile-per-CTA kernel's — the same 7680 pairs, so
+    // the tile-aligned layout does not depend on which kernel runs (GLU_SEG_KERNEL: 1 = ring, 0 = one tile per CTA)
+    constexpr int k_seg_threads = 480, k_seg_ipt = 16, k_seg_blocks = 2;
+    constexpr int k_seg1_threads = 320, k_seg1_ipt = 24, k_seg1_blocks = 3;
     constexpr int k_seg_tile = k_seg_threads * k_seg_ipt;
+    static_assert(k_seg_tile == k_seg1_threads * k_seg1_ipt, "one layout for both kernels");
     constexpr int k_max_segments = 256;
 
     struct SegLayout
@@ -301,10 +305,17 @@ extern "C" int glu_radix_sort_u32kv_segmented(uint32_t* d_keys_a, uint32_t* d_va
     for (int p = 0; p < plan.num_passes; p++)
     {
         uint32_t* lb = lookback + 2 * size_t(p) * max_tiles * k_radix;
-        const int rc = launch_ring<k_seg_threads, k_seg_ipt, k_seg_blocks, Rank_Ballot, 0, 0, true>(
-            kbuf[p & 1], vbuf[p & 1], kbuf[(p + 1) & 1], vbuf[(p + 1) & 1], uint32_t(max_tiles * size_t(k_seg_tile)),
-            plan.shift[p], plan.mask[p], hist + size_t(p) * k_max_segments * k_radix, lb, tickets + p, unsigned(max_tiles), s,
-            num_tiles, info);
+        static const int use_ring = env_int("GLU_SEG_KERNEL", 0);
+        const uint32_t n_padded = uint32_t(max_tiles * size_t(k_seg_tile));
+        const uint32_t* offsets = hist + size_t(p) * k_max_segments * k_radix;
+        const int rc =
+            use_ring ? launch_ring<k_seg_threads, k_seg_ipt, k_seg_blocks, Rank_Ballot, 0, 0, true>(
+                           kbuf[p & 1], vbuf[p & 1], kbuf[(p + 1) & 1], vbuf[(p + 1) & 1], n_padded, plan.shift[p],
+                           plan.mask[p], offsets, lb, tickets + p, unsigned(max_tiles), s, num_tiles, info)
+                     : launch_sweep<k_seg1_threads, k_seg1_ipt, k_seg1_blocks, Rank_Ballot, false, false, 0, true>(
+                           kbuf[p & 1], vbuf[p & 1], kbuf[(p + 1) & 1], vbuf[(p + 1) & 1], n_padded, plan.shift[p],
+                           plan.mask[p], offsets, lb, tickets + p, unsigned(max_tiles), s, num_tiles, nullptr, nullptr,
+                           nullptr, info);
         if (rc != GLU_SUCCESS)
             return rc;
     }

@@ -230,7 +230,9 @@ def gather(obj):
 # exchange "p2p" runs twice: destination-major exchange + full local sort, and bucket-major exchange + segmented local
 # sort on the key bits below the split digit (north_star's MSD split + 24-bit local sort)
 for exchange in os.environ["GLU_EXCHANGES"].split(","):
-  for local in (("full", "segmented") if exchange == "p2p" else ("full",)):
+  for local, style in ((("full", "staged"), ("segmented", "staged"), ("segmented", "direct")) if exchange == "p2p"
+                       else (("full", "staged"),)):
+    os.environ["GLU_DIST_EXCHANGE_STYLE"] = style  # how the bucket-major exchange crosses NVLink (segmented only)
     sorter_fixed = glu.DistributedRadixSort(400_000, exchange=exchange, capacity_factor=2.5, local=local)
     sorter_auto = glu.DistributedRadixSort(400_000, exchange=exchange, capacity_factor=2.5, split_shift="auto", local=local)
     assert sorter_fixed.exchange == exchange, (sorter_fixed.exchange, exchange)
@@ -258,11 +260,12 @@ for exchange in os.environ["GLU_EXCHANGES"].split(","):
             allk = np.concatenate([r[0] for r in res]); allv = np.concatenate([r[1] for r in res])
             gk = np.concatenate([r[2] for r in res]); gv = np.concatenate([r[3] for r in res])
             ek, ev = oracle.stable_sort_pairs(allk, allv)
-            assert np.array_equal(gk, ek), f"{exchange}/{local}/{kind}: keys differ"
-            assert np.array_equal(gv, ev), f"{exchange}/{local}/{kind}: values differ (stability across ranks)"
+            assert np.array_equal(gk, ek), f"{exchange}/{local}/{style}/{kind}: keys differ"
+            assert np.array_equal(gv, ev), f"{exchange}/{local}/{style}/{kind}: values differ (stability across ranks)"
         dist.barrier()
     sorter_fixed.close()
     sorter_auto.close()
+os.environ.pop("GLU_DIST_EXCHANGE_STYLE", None)
 
 # ---- the two-lane pipeline (DistributedSortPipeline): consecutive independent jobs, the exchange of job k+1 runs under
 # the local sort of job k; every job's result must equal std::stable_sort of the concatenated inputs

@@ -85,3 +85,21 @@ def test_segmented_sort_argument_checks(glu, cuda_device):
         rs.sort_segmented(buf, buf, buf, buf, cnt, 4, 4, 8, 8)        # no key bit takes part
     with pytest.raises(glu.GluError):
         rs.sort_segmented(buf[1:], buf, buf, buf, cnt, 4, 3)          # misaligned array (bulk copies need 16 bytes)
+
+
+def test_segmented_sort_other_kernel_form(cuda_device):
+    """The same cases through the other form of the digit pass (GLU_SEG_KERNEL, read once per process: 0 = one tile per
+    CTA, 1 = persistent ring kernel): both must agree with the oracle whatever the default is."""
+    import os
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+    if os.environ.get("GLU_SEG_TEST_CHILD"):
+        pytest.skip("already the child run")
+    other = "0" if os.environ.get("GLU_SEG_KERNEL", "0") == "1" else "1"
+    env = dict(os.environ, GLU_SEG_KERNEL=other, GLU_SEG_TEST_CHILD="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_sort_segmented_gpu.py"), "-m", "gpu",
+                        "-x", "-q", "-k", "matches_per_segment or heavy_duplicates"], cwd=ROOT, env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -26,12 +26,14 @@ if has phases; then
   cat $OUT/phases.log
 fi
 if has sweep; then
-  for v in "GLU_BENCH_MODE=serial GLU_DIST_LOCAL=full" "GLU_BENCH_MODE=serial GLU_DIST_LOCAL=segmented" \
-           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=full" "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented" \
-           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_SORT_RING_TILES_PER_CTA=8" \
-           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_SORT_RING_CTAS_PER_SM=1" \
-           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_PIPE_PRIORITY=x" \
-           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=full GLU_SORT_CONFIG=8"; do
+  for v in "GLU_BENCH_MODE=serial GLU_DIST_LOCAL=full" \
+           "GLU_BENCH_MODE=serial GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=direct" \
+           "GLU_BENCH_MODE=serial GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=staged" \
+           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=full" \
+           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=direct" \
+           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=staged" \
+           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=staged GLU_EXCHANGE_COPY_CTAS=74" \
+           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=staged GLU_PIPE_PRIORITY=x"; do
     echo "== $v" >> $OUT/sweep.log
     ( env $v timeout 200 $RUN --master-port 29712 bench.py --gpus $N --steps $STEPS --warmup 3 --no-side-metrics 2>&1 \
         | grep -E "^\{|Error|error|assert|Traceback" | tail -3 \
