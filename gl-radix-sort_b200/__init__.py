@@ -68,7 +68,7 @@ ABI = {
     "glu_radix_exchange_plan": (_int, [_vp, _int, _int, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "glu_radix_partition_u32kv_dyn": (_int, [_vp, _vp, _vp, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _vp, _vp, _sz, _vp]),
     "glu_radix_exchange_plan_buckets": (_int, [_vp, _int, _int, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "glu_radix_exchange_stage_tables": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "glu_radix_exchange_stage_tables": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "glu_radix_exchange_copy_u32kv": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "glu_radix_sort_segment_tile": (_sz, []),
     "glu_radix_sort_u32kv_segmented_tmp_bytes": (_sz, [_sz]),

@@ -1770,9 +1770,13 @@ namespace
 {
     // One CTA of 256 threads, thread b = bucket b: where this rank's pairs of bucket b go in its own bucket-major
     // staging arrays (exclusive scan of its 256 counts) — the pointer table of the local MSD pass.
+    // Buckets this rank keeps (seg_count[b] != 0) skip the staging arrays: the MSD pass writes them straight to their
+    // place in the rank's own receive arrays (final_key_dst[b]) and the copy kernel gets a count of 0 for them.
     __global__ void __launch_bounds__(k_radix, 1)
         exchange_stage_tables_kernel(const uint32_t* __restrict__ my_hist, uint64_t stage_keys, uint64_t stage_vals,
-                                     uint64_t* stage_key_dst, uint64_t* stage_val_dst, uint32_t* stage_off)
+                                     const uint32_t* __restrict__ seg_count, const uint64_t* __restrict__ final_key_dst,
+                                     const uint64_t* __restrict__ final_val_dst, uint64_t* stage_key_dst,
+                                     uint64_t* stage_val_dst, uint32_t* stage_off, uint32_t* copy_count)
     {
         __shared__ uint32_t s_warp[k_radix / 32];
         const unsigned b = threadIdx.x, lane = b & 31, warp = b >> 5;
@@ -1791,9 +1795,11 @@ namespace
         uint32_t off = inc - c;
         for (unsigned w = 0; w < warp; w++)
             off += s_warp[w];
+        const bool mine = seg_count && seg_count[b] != 0 && final_key_dst[b] != 0;
         stage_off[b] = off;
-        stage_key_dst[b] = stage_keys + 4ull * off;
-        stage_val_dst[b] = stage_vals + 4ull * off;
+        stage_key_dst[b] = mine ? final_key_dst[b] : stage_keys + 4ull * off;
+        stage_val_dst[b] = mine ? final_val_dst[b] : stage_vals + 4ull * off;
+        copy_count[b] = mine ? 0u : c;
     }
 
     // The all-to-all itself: this rank's run of bucket b — count[b] pairs at stage_off[b] of the staging arrays — goes to
@@ -1900,20 +1906,26 @@ namespace
 } // namespace glu_b200
 
 extern "C" int glu_radix_exchange_stage_tables(const uint32_t* d_my_hist, uint32_t* d_stage_keys, uint32_t* d_stage_vals,
-                                               uint32_t** d_stage_key_dst, uint32_t** d_stage_val_dst,
-                                               uint32_t* d_stage_off, glu_stream_t stream)
+                                               const uint32_t* d_seg_count, uint32_t* const* d_key_dst,
+                                               uint32_t* const* d_val_dst, uint32_t** d_stage_key_dst,
+                                               uint32_t** d_stage_val_dst, uint32_t* d_stage_off, uint32_t* d_copy_count,
+                                               glu_stream_t stream)
 {
-    if (!d_my_hist || !d_stage_keys || !d_stage_vals || !d_stage_key_dst || !d_stage_val_dst || !d_stage_off)
+    if (!d_my_hist || !d_stage_keys || !d_stage_vals || !d_stage_key_dst || !d_stage_val_dst || !d_stage_off ||
+        !d_copy_count || (d_seg_count && (!d_key_dst || !d_val_dst)))
         return GLU_ERROR_INVALID_ARGUMENT;
     if ((reinterpret_cast<uintptr_t>(d_my_hist) | reinterpret_cast<uintptr_t>(d_stage_off) |
-         reinterpret_cast<uintptr_t>(d_stage_keys) | reinterpret_cast<uintptr_t>(d_stage_vals)) % sizeof(uint32_t) != 0 ||
-        (reinterpret_cast<uintptr_t>(d_stage_key_dst) | reinterpret_cast<uintptr_t>(d_stage_val_dst)) % sizeof(uint64_t) != 0)
+         reinterpret_cast<uintptr_t>(d_stage_keys) | reinterpret_cast<uintptr_t>(d_stage_vals) |
+         reinterpret_cast<uintptr_t>(d_seg_count) | reinterpret_cast<uintptr_t>(d_copy_count)) % sizeof(uint32_t) != 0 ||
+        (reinterpret_cast<uintptr_t>(d_stage_key_dst) | reinterpret_cast<uintptr_t>(d_stage_val_dst) |
+         reinterpret_cast<uintptr_t>(d_key_dst) | reinterpret_cast<uintptr_t>(d_val_dst)) % sizeof(uint64_t) != 0)
         return GLU_ERROR_MISALIGNED;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    exchange_stage_tables_kernel<<<1, k_radix, 0, s>>>(d_my_hist, reinterpret_cast<uint64_t>(d_stage_keys),
-                                                       reinterpret_cast<uint64_t>(d_stage_vals),
-                                                       reinterpret_cast<uint64_t*>(d_stage_key_dst),
-                                                       reinterpret_cast<uint64_t*>(d_stage_val_dst), d_stage_off);
+    exchange_stage_tables_kernel<<<1, k_radix, 0, s>>>(
+        d_my_hist, reinterpret_cast<uint64_t>(d_stage_keys), reinterpret_cast<uint64_t>(d_stage_vals), d_seg_count,
+        reinterpret_cast<const uint64_t*>(d_key_dst), reinterpret_cast<const uint64_t*>(d_val_dst),
+        reinterpret_cast<uint64_t*>(d_stage_key_dst), reinterpret_cast<uint64_t*>(d_stage_val_dst), d_stage_off,
+        d_copy_count);
     GLU_LAUNCH_CHECK();
     return GLU_SUCCESS;
 }

@@ -282,8 +282,9 @@ class DistributedRadixSort:
             if self.exchange_style == "staged":
                 self._stage_k = torch.empty(self.max_count, dtype=torch.int32, device=self.device)
                 self._stage_v = torch.empty(self.max_count, dtype=torch.int32, device=self.device)
-                # [256 key pointers][256 value pointers] of the local MSD pass, then [256] staging offsets (as 128 int64)
-                self._stage_tables = torch.zeros(2 * RADIX + RADIX // 2, dtype=torch.int64, device=self.device)
+                # [256 key pointers][256 value pointers] of the local MSD pass, then [256] staging offsets and [256] copy
+                # counts (uint32, as 2 x 128 int64)
+                self._stage_tables = torch.zeros(2 * RADIX + RADIX, dtype=torch.int64, device=self.device)
             self._sorter._scratch.ensure(int(glu.lib.glu_radix_sort_u32kv_segmented_tmp_bytes(self.capacity_tiles)),
                                          self.device)
         else:
@@ -515,14 +516,16 @@ class DistributedRadixSort:
             sptr = self._stage_tables.data_ptr()
             my_hist = self._hist_all.data_ptr() + 4 * RADIX * rank
             glu.check(glu.lib.glu_radix_exchange_stage_tables(my_hist, self._stage_k.data_ptr(), self._stage_v.data_ptr(),
-                                                              sptr, sptr + 8 * RADIX, sptr + 16 * RADIX, st),
+                                                              self._seg_count.data_ptr(), tptr, tptr + 8 * RADIX, sptr,
+                                                              sptr + 8 * RADIX, sptr + 16 * RADIX, sptr + 20 * RADIX, st),
                       "glu_radix_exchange_stage_tables")
             glu.check(glu.lib.glu_radix_partition_u32kv_dyn(kptr, vptr, cptr, count, shift, RADIX_BITS, sptr,
                                                             sptr + 8 * RADIX, self._part_tmp.data_ptr(),
                                                             self._part_tmp.numel(), st),
                       "glu_radix_partition_u32kv_dyn (local MSD pass)")
             glu.check(glu.lib.glu_radix_exchange_copy_u32kv(self._stage_k.data_ptr(), self._stage_v.data_ptr(),
-                                                            sptr + 16 * RADIX, my_hist, tptr, tptr + 8 * RADIX, 0, st),
+                                                            sptr + 16 * RADIX, sptr + 20 * RADIX, tptr, tptr + 8 * RADIX, 0,
+                                                            st),
                       "glu_radix_exchange_copy_u32kv")
         elif self.local == "segmented":
             # the MSD pass stores straight into the peers' memory

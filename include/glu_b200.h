@@ -272,10 +272,15 @@ GLU_API int glu_radix_exchange_plan_buckets(const uint32_t* d_hist_all, int worl
  * at full HBM speed; (2) glu_radix_exchange_copy_u32kv moves every bucket's run — count[b] pairs at d_stage_off[b] — to
  * d_key_dst[b] / d_val_dst[b] (the tables of glu_radix_exchange_plan_buckets; peer memory over NVLink).  The runs are
  * long, so every warp-wide store is one full aligned 128-byte line, and a grid of one CTA per SM (num_ctas <= 0) keeps
- * the links busy while the rest of the GPU sorts.  d_my_hist / d_count: this rank's 256 split-digit counts (its row of
- * the all-gathered histograms).  Buckets whose destination pointer is NULL (overflow) are skipped. */
+ * the links busy while the rest of the GPU sorts.  d_my_hist: this rank's 256 split-digit counts (its row of the
+ * all-gathered histograms).  Buckets the rank keeps for itself (d_seg_count[b] != 0, the plan's segment table; may be
+ * NULL) skip the staging arrays: their table entry is the final place d_key_dst[b] / d_val_dst[b] and d_copy_count[b]
+ * is 0; for the others d_copy_count[b] = d_my_hist[b] — the `d_count` of glu_radix_exchange_copy_u32kv.  Buckets whose
+ * destination pointer is NULL (overflow) are skipped. */
 GLU_API int glu_radix_exchange_stage_tables(const uint32_t* d_my_hist, uint32_t* d_stage_keys, uint32_t* d_stage_vals,
-                                            uint32_t** d_stage_key_dst, uint32_t** d_stage_val_dst, uint32_t* d_stage_off,
+                                            const uint32_t* d_seg_count, uint32_t* const* d_key_dst,
+                                            uint32_t* const* d_val_dst, uint32_t** d_stage_key_dst,
+                                            uint32_t** d_stage_val_dst, uint32_t* d_stage_off, uint32_t* d_copy_count,
                                             glu_stream_t stream);
 GLU_API int glu_radix_exchange_copy_u32kv(const uint32_t* d_stage_keys, const uint32_t* d_stage_vals,
                                           const uint32_t* d_stage_off, const uint32_t* d_count, uint32_t* const* d_key_dst,
