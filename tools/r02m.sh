@@ -15,6 +15,10 @@ if has probe; then
   ( timeout 120 $RUN --master-port 29701 tools/nvlink_probe.py 2>&1 | grep -E "^\{|Error|error" | tail -3 ) > $OUT/nvlink.log
   cat $OUT/nvlink.log
 fi
+if has pcie; then
+  ( timeout 120 $RUN --master-port 29702 tools/pcie_probe.py 2>&1 | grep -E "^\{|Error|error" | tail -3 ) > $OUT/pcie.log
+  cat $OUT/pcie.log
+fi
 if has pytest; then
   ( GLU_TEST_WORLD=$N timeout 600 python -m pytest tests/test_multigpu_gpu.py -m gpu -x -q -k "distributed_world" 2>&1 | tail -15 ) > $OUT/pytest_world.log
   cat $OUT/pytest_world.log
