@@ -490,6 +490,18 @@ class InputRing:
         return k, v
 
 
+def describe_exchange(sorter) -> str:
+    """What a DistributedRadixSort does between the plan and the result, in words (for the line's `config`)."""
+    if sorter.exchange != "p2p":
+        return "partition + NCCL all_to_all, local onesweep sort on all 32 bits"
+    if sorter.local != "segmented":
+        return "fused partition + NVLink peer-store all-to-all, local onesweep sort on all 32 bits"
+    how = {"dma": "local MSD pass into tile-aligned staging + one copy-engine transfer per peer over NVLink (host plan)",
+           "staged": "local MSD pass into staging + NVLink peer-store copy kernel",
+           "direct": "MSD pass storing straight into the peers' memory"}[sorter.exchange_style]
+    return f"{how}, segmented local onesweep sort on the 24 key bits below the split digit"
+
+
 def measure_sort(args, glu, torch, dist, dev, world, rank, n, steps, warmup, mode, peak, input_budget_bytes):
     """K timed steps of the sort at `n` pairs per GPU.  Returns (line fields, objects to keep alive / close)."""
     in_place = world == 1  # glu::RadixSort sorts the caller's arrays; the multi-GPU sort leaves its input alone
@@ -515,9 +527,9 @@ def measure_sort(args, glu, torch, dist, dev, world, rank, n, steps, warmup, mod
             def result():
                 return pipe.result(last["ticket"])
 
-            parallelism = (f"msd-split x{world}: top-8-bit histogram all-gather, balanced bucket->GPU prefix, fused "
-                           f"partition + NVLink peer-store all-to-all, local onesweep sort; consecutive steps software-"
-                           f"pipelined on two lanes (the NVLink-bound exchange of step k+1 runs under the local sort of step k)")
+            parallelism = (f"msd-split x{world}: top-8-bit histogram all-gather, balanced bucket->GPU prefix, "
+                           f"{describe_exchange(pipe.lanes[0])}; consecutive steps software-pipelined on "
+                           f"{pipe.num_lanes} lanes (the NVLink-bound exchange of step k+1 runs under the local sort of step k)")
         else:
             dsort = glu.DistributedRadixSort(n, exchange=os.environ.get("GLU_BENCH_EXCHANGE", "auto"))
             closers.append(dsort.close)
@@ -533,8 +545,7 @@ def measure_sort(args, glu, torch, dist, dev, world, rank, n, steps, warmup, mod
                 return last["out"]
 
             parallelism = (f"msd-split x{world}: top-8-bit histogram all-gather, balanced bucket->GPU prefix, "
-                           f"{'fused partition + NVLink peer-store all-to-all' if exchange == 'p2p' else 'partition + NCCL all_to_all'}"
-                           f", local onesweep sort; steps back to back, not overlapped")
+                           f"{describe_exchange(dsort)}; steps back to back, not overlapped")
     else:
         sorter = glu.RadixSort()
         sorter.prepare_internal_buffers(n)  # as the reference's benchmark does (test/radix_sort_tests.cpp:187)
@@ -643,7 +654,7 @@ def measure_sort(args, glu, torch, dist, dev, world, rank, n, steps, warmup, mod
                                "achieved_GB/s": step_bytes * n * steps / (ms_total * 1e-3) / 1e9,
                                "frac": step_bytes * n * steps / (ms_total * 1e-3) / 1e9 / peak}}
     if world > 1 and mode == "pipeline":
-        roofline["note"] = ("two lanes overlap: per-launch times are those of kernels sharing the GPU with the other "
+        roofline["note"] = ("the lanes overlap: per-launch times are those of kernels sharing the GPU with the other "
                             "lane's kernels, so achieved is a lower bound of the kernel alone")
     fields = {"value": value, "ms_per_step": ms_total / steps, "roofline": roofline, "clocks": clocks,
               "gpu_launches": int(gpu_launches), "verified": verified, "parallelism": parallelism,

@@ -74,6 +74,8 @@ ABI = {
     "glu_radix_sort_u32kv_segmented_tmp_bytes": (_sz, [_sz]),
     "glu_radix_sort_u32kv_segmented": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, ctypes.c_uint, ctypes.c_uint, _vp, _sz,
                                               _vp, ctypes.POINTER(_int)]),
+    "glu_radix_sort_u32kv_segmented_runs": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _sz, ctypes.c_uint, ctypes.c_uint, _vp,
+                                                   _sz, _vp, _sz, _vp, ctypes.POINTER(_int)]),
     "glu_ipc_get_handle": (_int, [_vp, ctypes.c_char_p]),
     "glu_ipc_open_handle": (_int, [ctypes.c_char_p, ctypes.POINTER(_vp)]),
     "glu_ipc_close_handle": (_int, [_vp]),
@@ -356,10 +358,13 @@ class RadixSort:
                                        st), "RadixSort.sort_wide")
 
     def sort_segmented(self, keys_a, vals_a, keys_b, vals_b, seg_count_buffer, num_segments: int, max_tiles: int,
-                       begin_bit: int = 0, end_bit: int = 32, stream: int | None = None) -> bool:
+                       begin_bit: int = 0, end_bit: int = 32, stream: int | None = None, runs_buffer=None,
+                       num_runs: int = 0) -> bool:
         """glu_radix_sort_u32kv_segmented: `num_segments` independent stable sorts by key bits [begin_bit, end_bit) in one
         set of launches.  Input in arrays A, segment s at element first_tile[s] * segment_tile() (first_tile = exclusive
-        scan of ceil(count / tile)); output compact.  Returns True when the result is in arrays B, False for A."""
+        scan of ceil(count / tile)); output compact.  Returns True when the result is in arrays B, False for A.
+        With `runs_buffer` (5 x (num_runs + 1) uint32, see glu_radix_sort_u32kv_segmented_runs) the input is a sequence of
+        tile-aligned runs placed anywhere in arrays A."""
         ptrs = []
         dev = None
         for buf in (keys_a, vals_a, keys_b, vals_b, seg_count_buffer):
@@ -376,6 +381,14 @@ class RadixSort:
         self._device = dev
         st = _current_stream(dev) if stream is None else stream
         in_b = ctypes.c_int(0)
+        if runs_buffer is not None:
+            rptr, _ = _ptr_and_device(runs_buffer)
+            if not rptr:
+                raise GluError(1, "Invalid run table")
+            check(_lib.glu_radix_sort_u32kv_segmented_runs(ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], num_segments,
+                                                           max_tiles, begin_bit, end_bit, rptr, num_runs, tmp, tmp_bytes,
+                                                           st, ctypes.byref(in_b)), "RadixSort.sort_segmented (runs)")
+            return bool(in_b.value)
         check(_lib.glu_radix_sort_u32kv_segmented(ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], num_segments, max_tiles,
                                                   begin_bit, end_bit, tmp, tmp_bytes, st, ctypes.byref(in_b)),
               "RadixSort.sort_segmented")

@@ -487,7 +487,8 @@ namespace glu_b200
                             uint32_t* lookback, uint32_t* prefix, uint32_t* ticket, uint32_t num_tiles, int allow_tma,
                             int chain_rows, int options, const uint32_t* __restrict__ d_n = nullptr,
                             uint32_t* const* key_dst = nullptr, uint32_t* const* val_dst = nullptr,
-                            const uint8_t* __restrict__ dest_lut = nullptr, const uint2* __restrict__ tile_info = nullptr)
+                            const uint8_t* __restrict__ dest_lut = nullptr, const uint2* __restrict__ tile_info = nullptr,
+                            const uint32_t* __restrict__ tile_map = nullptr)
         {
             static_assert(!DEST || PEER, "DEST is a flavour of PEER");
             static_assert(!SEG || (!PEER && FLAVOR == 0), "SEG is a flavour of the plain key/value pass");
@@ -534,7 +535,14 @@ namespace glu_b200
                 // clearing its counters)
                 if (allow_tma && t >= chain_ctas && uint64_t(t - chain_ctas + 1) * uint32_t(TILE) <= uint64_t(n))
                 {
-                    const uint32_t tb = (t - chain_ctas) * uint32_t(TILE);
+                    // SEG with a tile map (glu_radix_sort_u32kv_segmented_runs, first pass): tile t is READ from tile
+                    // tile_map[t] of the input arrays
+                    uint32_t tb = (t - chain_ctas) * uint32_t(TILE);
+                    if constexpr (SEG)
+                    {
+                        if (tile_map)
+                            tb = __ldg(tile_map + (t - chain_ctas)) * uint32_t(TILE);
+                    }
                     const uint64_t policy = l2_policy_evict_first();
                     mbarrier_arrive_expect_tx(&s.bar_keys, TILE * 4);
                     tma_load_1d(s.keys, keys_in + tb, TILE * 4, &s.bar_keys, policy);
@@ -545,9 +553,14 @@ namespace glu_b200
                     }
                     // L2 prefetch of the tile that will occupy this CTA slot `options >> 8` tiles from now: its bulk
                     // copies then start from L2 instead of paying the loaded-DRAM latency at CTA start
-                    const uint64_t ahead = uint64_t(t - chain_ctas) + uint32_t(options >> 8);
+                    uint64_t ahead = uint64_t(t - chain_ctas) + uint32_t(options >> 8);
                     if ((options >> 8) != 0 && (ahead + 1) * uint64_t(TILE) <= uint64_t(n))
                     {
+                        if constexpr (SEG)
+                        {
+                            if (tile_map)
+                                ahead = __ldg(tile_map + ahead);
+                        }
                         tma_prefetch_l2_1d(keys_in + ahead * TILE, TILE * 4);
                         if constexpr (!KEYS_ONLY)
                             tma_prefetch_l2_1d(vals_in + ahead * TILE, TILE * 4);
@@ -589,7 +602,12 @@ namespace glu_b200
             const uint32_t tile = s.tile - chain_ctas;
             if (tile >= num_tiles)
                 return;
-            const uint32_t tile_base = tile * uint32_t(TILE);
+            uint32_t tile_base = tile * uint32_t(TILE); // where the tile is read from
+            if constexpr (SEG)
+            {
+                if (tile_map)
+                    tile_base = __ldg(tile_map + tile) * uint32_t(TILE);
+            }
             uint2 info = make_uint2(0, 0);
             if constexpr (SEG)
                 info = tile_info[tile];
@@ -1016,7 +1034,8 @@ namespace glu_b200
                          uint32_t mask, const uint32_t* digit_offset, uint32_t* lookback, uint32_t* ticket,
                          unsigned tiles, cudaStream_t s, const uint32_t* d_n = nullptr,
                          uint32_t* const* key_dst = nullptr, uint32_t* const* val_dst = nullptr,
-                         const uint8_t* dest_lut = nullptr, const uint2* tile_info = nullptr)
+                         const uint8_t* dest_lut = nullptr, const uint2* tile_info = nullptr,
+                         const uint32_t* tile_map = nullptr)
         {
             // per pass: `tiles` count rows followed by `tiles` prefix rows; grid = tiles + the chain CTAs
             uint32_t* prefix = lookback + size_t(tiles) * k_radix;
@@ -1048,7 +1067,7 @@ namespace glu_b200
             ScopedKernelProfile prof(PEER ? GLU_KERNEL_SORT_PARTITION : GLU_KERNEL_SORT_ONESWEEP, s);
             kernel<<<grid, THREADS, smem, s>>>(ki, vi, ko, vo, n, shift, mask, digit_offset, lookback, prefix, ticket,
                                                     tiles, allow_tma, chain_rows, options, d_n, key_dst, val_dst, dest_lut,
-                                                    tile_info);
+                                                    tile_info, tile_map);
             GLU_LAUNCH_CHECK();
             return GLU_SUCCESS;
         }

@@ -37,6 +37,8 @@ namespace
         size_t max_tiles;
         size_t off_seg;   // [4][k_max_segments] u32: first_tile, compact base, (spare), (spare)
         size_t off_info;  // [max_tiles] uint2 {valid | seg << 24, first tile of the segment}
+        size_t off_info0; // [max_tiles] uint2: the same for the FIRST pass of the runs variant (input made of runs)
+        size_t off_map0;  // [max_tiles] u32: tile of the input arrays that tile t of the first pass is read from
         size_t off_hist;  // [k_max_passes][k_max_segments][256] u32
         size_t off_lookback; // per pass: max_tiles count rows + max_tiles prefix rows
         size_t zero_begin, zero_bytes; // tickets + num_tiles + histograms + look-back words: zeroed per sort
@@ -49,7 +51,9 @@ namespace
         l.max_tiles = max_tiles;
         l.off_seg = k_tmp_align; // [0, 256): 4 tickets, num_tiles at word 8
         l.off_info = l.off_seg + 4 * k_max_segments * sizeof(uint32_t);
-        l.off_hist = align_up(l.off_info + max_tiles * sizeof(uint2), k_tmp_align);
+        l.off_info0 = align_up(l.off_info + max_tiles * sizeof(uint2), k_tmp_align);
+        l.off_map0 = align_up(l.off_info0 + max_tiles * sizeof(uint2), k_tmp_align);
+        l.off_hist = align_up(l.off_map0 + max_tiles * sizeof(uint32_t), k_tmp_align);
         l.off_lookback = l.off_hist + size_t(k_max_passes) * k_max_segments * k_radix * sizeof(uint32_t);
         l.total = align_up(l.off_lookback + 2 * size_t(k_max_passes) * max_tiles * k_radix * sizeof(uint32_t), k_tmp_align);
         l.zero_begin = 0;
@@ -123,12 +127,45 @@ namespace
         info[t] = make_uint2(valid | (lo << 24), first);
     }
 
+    // Runs variant (glu_radix_sort_u32kv_segmented_runs): the input of the FIRST pass is a sequence of `num_runs` runs in
+    // segment order (a segment = one or more consecutive runs), run r = count[r] pairs starting at tile phys[r] of the
+    // input arrays — wherever the exchange put it.  runs: 5 rows of (num_runs + 1) words: first tile of the run in the
+    // pass's own tile numbering (exclusive scan of ceil(count / TILE); entry num_runs = the total), phys, count, segment,
+    // first tile (same numbering) of the run's segment.  Writes the first pass's tile descriptors and its tile map.
+    __global__ void __launch_bounds__(256)
+        run_tile_info_kernel(const uint32_t* __restrict__ runs, uint32_t num_runs, uint32_t max_tiles, uint2* info0,
+                             uint32_t* map0, uint32_t* num_tiles0)
+    {
+        const uint32_t stride = num_runs + 1;
+        const uint32_t total = runs[num_runs] <= max_tiles ? runs[num_runs] : 0u; // more than the scratch holds: sort nothing
+        const uint32_t t = blockIdx.x * 256u + threadIdx.x;
+        if (t == 0)
+            *num_tiles0 = total;
+        if (t >= total)
+            return;
+        uint32_t lo = 0, hi = num_runs; // first[lo] <= t < first[hi]
+        while (hi - lo > 1)
+        {
+            const uint32_t mid = (lo + hi) / 2;
+            if (runs[mid] <= t)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        // empty runs share their first tile with the next run: `lo` is the last of them, i.e. the one that owns tile t
+        const uint32_t k = t - runs[lo];
+        const uint32_t left = runs[2 * stride + lo] - k * uint32_t(k_seg_tile);
+        const uint32_t valid = left < uint32_t(k_seg_tile) ? left : uint32_t(k_seg_tile);
+        info0[t] = make_uint2(valid | (runs[3 * stride + lo] << 24), runs[4 * stride + lo]);
+        map0[t] = runs[stride + lo] + k;
+    }
+
     // hist[pass][segment][256] += digit counts of the valid keys of the tiles; a CTA takes a contiguous range of tiles
     // and flushes its shared bins whenever the segment changes.  Same lane-private bin layout as histogram_kernel.
     __global__ void __launch_bounds__(k_hist_threads, 1)
         seg_histogram_kernel(const uint32_t* __restrict__ keys, const uint2* __restrict__ info,
                              const uint32_t* __restrict__ d_num_tiles, int num_passes, uint32_t pre_shift, uint32_t key_mask,
-                             uint32_t* hist)
+                             uint32_t* hist, const uint32_t* __restrict__ tile_map)
     {
         extern __shared__ __align__(16) uint32_t s_hist[]; // [num_passes][k_radix][k_hist_copies]
         const uint32_t num_tiles = *d_num_tiles;
@@ -169,7 +206,7 @@ namespace
                 flush(cur_seg);
                 cur_seg = seg;
             }
-            const uint4* body = reinterpret_cast<const uint4*>(keys + size_t(t) * k_seg_tile);
+            const uint4* body = reinterpret_cast<const uint4*>(keys + size_t(tile_map ? tile_map[t] : t) * k_seg_tile);
             for (uint32_t u = threadIdx.x; u < uint32_t(k_seg_tile / 4); u += k_hist_threads)
             {
                 if (u * 4 >= valid)
@@ -235,10 +272,11 @@ extern "C" size_t glu_radix_sort_u32kv_segmented_tmp_bytes(size_t max_tiles)
     return make_seg_layout(max_tiles).total;
 }
 
-extern "C" int glu_radix_sort_u32kv_segmented(uint32_t* d_keys_a, uint32_t* d_vals_a, uint32_t* d_keys_b, uint32_t* d_vals_b,
-                                              const uint32_t* d_seg_count, size_t num_segments, size_t max_tiles,
-                                              unsigned begin_bit, unsigned end_bit, void* d_tmp, size_t tmp_bytes,
-                                              glu_stream_t stream, int* result_in_b)
+namespace
+{
+int seg_sort_impl(uint32_t* d_keys_a, uint32_t* d_vals_a, uint32_t* d_keys_b, uint32_t* d_vals_b, const uint32_t* d_seg_count,
+                  size_t num_segments, size_t max_tiles, unsigned begin_bit, unsigned end_bit, const uint32_t* d_runs,
+                  size_t num_runs, void* d_tmp, size_t tmp_bytes, glu_stream_t stream, int* result_in_b)
 {
     if (!d_keys_a || !d_vals_a || !d_keys_b || !d_vals_b || !d_seg_count || num_segments == 0 ||
         num_segments > size_t(k_max_segments) || begin_bit >= end_bit || end_bit > 32 || max_tiles == 0)
@@ -264,6 +302,10 @@ extern "C" int glu_radix_sort_u32kv_segmented(uint32_t* d_keys_a, uint32_t* d_va
     uint32_t* num_tiles = tickets + 8;
     uint32_t* seg = reinterpret_cast<uint32_t*>(tmp + l.off_seg);
     uint2* info = reinterpret_cast<uint2*>(tmp + l.off_info);
+    // runs variant: the first pass (and the histogram) read the input through its own tile descriptors and tile map
+    uint32_t* num_tiles0 = d_runs ? tickets + 9 : num_tiles;
+    uint2* info0 = d_runs ? reinterpret_cast<uint2*>(tmp + l.off_info0) : info;
+    uint32_t* map0 = d_runs ? reinterpret_cast<uint32_t*>(tmp + l.off_map0) : nullptr;
     uint32_t* hist = reinterpret_cast<uint32_t*>(tmp + l.off_hist);
     uint32_t* lookback = reinterpret_cast<uint32_t*>(tmp + l.off_lookback);
     const PassPlan plan = make_bit_plan(begin_bit, int(end_bit - begin_bit));
@@ -278,6 +320,12 @@ extern "C" int glu_radix_sort_u32kv_segmented(uint32_t* d_keys_a, uint32_t* d_va
     GLU_LAUNCH_CHECK();
     seg_tile_info_kernel<<<unsigned((max_tiles + 255) / 256), 256, 0, s>>>(d_seg_count, seg, S, num_tiles, info);
     GLU_LAUNCH_CHECK();
+    if (d_runs)
+    {
+        run_tile_info_kernel<<<unsigned((max_tiles + 255) / 256), 256, 0, s>>>(d_runs, uint32_t(num_runs), uint32_t(max_tiles),
+                                                                                info0, map0, num_tiles0);
+        GLU_LAUNCH_CHECK();
+    }
     {
         const size_t smem = size_t(plan.num_passes) * k_radix * k_hist_copies * sizeof(uint32_t);
         static std::atomic<bool> configured[64];
@@ -293,8 +341,8 @@ extern "C" int glu_radix_sort_u32kv_segmented(uint32_t* d_keys_a, uint32_t* d_va
         }
         const unsigned grid = unsigned(max_tiles < size_t(sms) ? max_tiles : size_t(sms));
         ScopedKernelProfile prof(GLU_KERNEL_SORT_HISTOGRAM, s);
-        seg_histogram_kernel<<<grid, k_hist_threads, smem, s>>>(d_keys_a, info, num_tiles, plan.num_passes, plan.begin_bit,
-                                                                plan.key_mask, hist);
+        seg_histogram_kernel<<<grid, k_hist_threads, smem, s>>>(d_keys_a, info0, num_tiles0, plan.num_passes, plan.begin_bit,
+                                                                plan.key_mask, hist, map0);
         GLU_LAUNCH_CHECK();
     }
     seg_offsets_kernel<<<dim3(S, unsigned(plan.num_passes)), k_radix, 0, s>>>(hist, seg, plan.num_passes);
@@ -305,7 +353,9 @@ extern "C" int glu_radix_sort_u32kv_segmented(uint32_t* d_keys_a, uint32_t* d_va
     for (int p = 0; p < plan.num_passes; p++)
     {
         uint32_t* lb = lookback + 2 * size_t(p) * max_tiles * k_radix;
-        static const int use_ring = env_int("GLU_SEG_KERNEL", 0);
+        static const int use_ring_env = env_int("GLU_SEG_KERNEL", 0);
+        const bool first_of_runs = d_runs && p == 0;
+        const bool use_ring = use_ring_env && !d_runs; // the tile map exists in the one-tile-per-CTA kernel only
         const uint32_t n_padded = uint32_t(max_tiles * size_t(k_seg_tile));
         const uint32_t* offsets = hist + size_t(p) * k_max_segments * k_radix;
         const int rc =
@@ -314,12 +364,35 @@ extern "C" int glu_radix_sort_u32kv_segmented(uint32_t* d_keys_a, uint32_t* d_va
                            plan.mask[p], offsets, lb, tickets + p, unsigned(max_tiles), s, num_tiles, info)
                      : launch_sweep<k_seg1_threads, k_seg1_ipt, k_seg1_blocks, Rank_Ballot, false, false, 0, true>(
                            kbuf[p & 1], vbuf[p & 1], kbuf[(p + 1) & 1], vbuf[(p + 1) & 1], n_padded, plan.shift[p],
-                           plan.mask[p], offsets, lb, tickets + p, unsigned(max_tiles), s, num_tiles, nullptr, nullptr,
-                           nullptr, info);
+                           plan.mask[p], offsets, lb, tickets + p, unsigned(max_tiles), s,
+                           first_of_runs ? num_tiles0 : num_tiles, nullptr, nullptr, nullptr, first_of_runs ? info0 : info,
+                           first_of_runs ? map0 : nullptr);
         if (rc != GLU_SUCCESS)
             return rc;
     }
     if (result_in_b)
         *result_in_b = plan.num_passes & 1;
     return GLU_SUCCESS;
+}
+} // namespace
+
+extern "C" int glu_radix_sort_u32kv_segmented(uint32_t* d_keys_a, uint32_t* d_vals_a, uint32_t* d_keys_b, uint32_t* d_vals_b,
+                                              const uint32_t* d_seg_count, size_t num_segments, size_t max_tiles,
+                                              unsigned begin_bit, unsigned end_bit, void* d_tmp, size_t tmp_bytes,
+                                              glu_stream_t stream, int* result_in_b)
+{
+    return seg_sort_impl(d_keys_a, d_vals_a, d_keys_b, d_vals_b, d_seg_count, num_segments, max_tiles, begin_bit, end_bit,
+                         nullptr, 0, d_tmp, tmp_bytes, stream, result_in_b);
+}
+
+extern "C" int glu_radix_sort_u32kv_segmented_runs(uint32_t* d_keys_a, uint32_t* d_vals_a, uint32_t* d_keys_b,
+                                                   uint32_t* d_vals_b, const uint32_t* d_seg_count, size_t num_segments,
+                                                   size_t max_tiles, unsigned begin_bit, unsigned end_bit,
+                                                   const uint32_t* d_runs, size_t num_runs, void* d_tmp, size_t tmp_bytes,
+                                                   glu_stream_t stream, int* result_in_b)
+{
+    if (!d_runs || num_runs == 0 || num_runs > size_t(1) << 16 || reinterpret_cast<uintptr_t>(d_runs) % sizeof(uint32_t) != 0)
+        return GLU_ERROR_INVALID_ARGUMENT;
+    return seg_sort_impl(d_keys_a, d_vals_a, d_keys_b, d_vals_b, d_seg_count, num_segments, max_tiles, begin_bit, end_bit,
+                         d_runs, num_runs, d_tmp, tmp_bytes, stream, result_in_b);
 }

@@ -97,6 +97,67 @@ def plan_exchange(hist_all: np.ndarray) -> ExchangePlan:
     return ExchangePlan(dest, send_counts, recv_totals, recv_offset, send_offset, dst_offset, src_offset)
 
 
+@dataclass
+class DmaExchangePlan:
+    """Layout of the exchange whose all-to-all is ONE copy-engine transfer per peer and array (exchange style "dma").
+
+    Every rank lays its pairs out bucket-major in its staging arrays, every bucket at a tile boundary; the buckets of one
+    destination are contiguous there, so what rank s sends to rank g is one chunk of whole tiles.  Rank g receives the
+    chunks one after the other in source order; the run of bucket b from source s is then at a tile the plan knows, and
+    the local sort reads bucket b as the runs (b, 0), (b, 1), ... (glu_radix_sort_u32kv_segmented_runs)."""
+    tile: int
+    counts: np.ndarray          # [world, RADIX]     the all-gathered histograms
+    dest: np.ndarray            # [RADIX]            destination rank of each bucket (monotone)
+    first_bucket: np.ndarray    # [world + 1]        rank g owns buckets [first_bucket[g], first_bucket[g + 1])
+    stage_tile: np.ndarray      # [world, RADIX + 1] first tile of bucket b in rank s's staging arrays
+    chunk_tiles: np.ndarray     # [world, world]     tiles rank s sends to rank g
+    recv_base_tile: np.ndarray  # [world, world]     [g, s]: first tile of rank s's chunk in rank g's receive arrays
+    recv_totals: np.ndarray     # [world]            pairs every rank receives
+    recv_tiles: np.ndarray      # [world]            tiles every rank's receive arrays hold afterwards
+
+    def phys_tile(self, g: int, b, s):
+        """Tile of rank g's receive arrays where source s's run of bucket b (owned by g) starts."""
+        return self.recv_base_tile[g, s] + self.stage_tile[s, b] - self.stage_tile[s, self.first_bucket[g]]
+
+    def run_table(self, g: int):
+        """(runs [5, R + 1] uint32, seg_count [RADIX] uint32, number of segments) of rank g's local sort: the runs in
+        bucket order, inside a bucket in source order (include/glu_b200.h: glu_radix_sort_u32kv_segmented_runs)."""
+        world = self.counts.shape[0]
+        b0, b1 = int(self.first_bucket[g]), int(self.first_bucket[g + 1])
+        nb = b1 - b0
+        seg_count = np.zeros(RADIX, dtype=np.uint32)
+        if nb == 0:
+            return np.zeros((5, 1), dtype=np.uint32), seg_count, 0
+        cnt = self.counts[:, b0:b1].T.reshape(-1)                       # [bucket, source]
+        tiles = -(-cnt // self.tile)
+        first = np.concatenate([[0], np.cumsum(tiles)])
+        phys = (self.recv_base_tile[g][None, :] + (self.stage_tile[:, b0:b1] - self.stage_tile[:, b0:b0 + 1]).T).reshape(-1)
+        seg = np.repeat(np.arange(nb), world)
+        runs = np.zeros((5, nb * world + 1), dtype=np.uint32)
+        runs[0] = first
+        runs[1, :-1] = phys
+        runs[2, :-1] = cnt
+        runs[3, :-1] = seg
+        runs[4, :-1] = first[seg * world]
+        seg_count[:nb] = self.counts[:, b0:b1].sum(axis=0)
+        return runs, seg_count, nb
+
+
+def plan_dma_exchange(hist_all: np.ndarray, tile: int) -> DmaExchangePlan:
+    counts = np.asarray(hist_all, dtype=np.int64)
+    world, radix = counts.shape
+    dest = assign_buckets(counts.sum(axis=0), world)
+    first_bucket = np.searchsorted(dest, np.arange(world + 1), side="left").astype(np.int64)
+    tiles = -(-counts // tile)
+    stage_tile = np.concatenate([np.zeros((world, 1), dtype=np.int64), np.cumsum(tiles, axis=1)], axis=1)
+    chunk_tiles = stage_tile[:, first_bucket[1:]] - stage_tile[:, first_bucket[:-1]]      # [src, dst]
+    recv_base_tile = (np.cumsum(chunk_tiles, axis=0) - chunk_tiles).T.copy()              # [dst, src]
+    onehot = (dest[:, None] == np.arange(world)[None, :]).astype(np.int64)
+    recv_totals = (counts @ onehot).sum(axis=0)
+    return DmaExchangePlan(int(tile), counts, dest, first_bucket, stage_tile, chunk_tiles, recv_base_tile, recv_totals,
+                           chunk_tiles.sum(axis=0))
+
+
 # ------------------------------------------------------------------------------------------------------ GPU side
 
 def _glu():
@@ -240,7 +301,18 @@ class DistributedRadixSort:
         if local not in ("auto", "full", "segmented"):
             raise ValueError(local)
         self._tile = int(glu.lib.glu_radix_sort_segment_tile())
-        self.capacity_tiles = -(-self.capacity // self._tile) + RADIX  # every bucket may end in a partial tile
+        # How the bucket-major exchange crosses NVLink.  "staged": a local MSD pass into this rank's own bucket-major
+        # staging arrays (full HBM speed), then a copy kernel that moves each bucket's long run with full-line
+        # stores.  "direct": the MSD pass stores straight into the peers' memory (no staging, 16 B of HBM traffic less
+        # per pair, but ~30-pair runs: byte-masked NVLink packets).  "dma": the staging arrays are tile-aligned per
+        # bucket, what a rank sends to a peer is ONE contiguous chunk, moved by the copy engines (cudaMemcpyAsync over
+        # the peer mapping: no SM is spent on the all-to-all); the plan is made on the host from the all-gathered
+        # histograms (DmaExchangePlan) and the local sort reads its buckets as runs.
+        self.exchange_style = os.environ.get("GLU_DIST_EXCHANGE_STYLE", "staged")
+        if self.exchange_style not in ("staged", "direct", "dma"):
+            raise ValueError(self.exchange_style)
+        # every bucket (dma: every run = bucket x source) may end in a partial tile
+        self.capacity_tiles = -(-self.capacity // self._tile) + RADIX * (self.world if self.exchange_style == "dma" else 1)
         seg_capacity = self.capacity_tiles * self._tile
         want_seg = local in ("auto", "segmented") and exchange in ("auto", "p2p") and plan in ("auto", "device") \
             and self.world <= 16
@@ -272,14 +344,23 @@ class DistributedRadixSort:
             self._alt_keys = torch.empty(seg_capacity, dtype=torch.int32, device=self.device)
             self._alt_vals = torch.empty(seg_capacity, dtype=torch.int32, device=self.device)
             self._seg_count = torch.zeros(RADIX, dtype=torch.int32, device=self.device)
-            # How the bucket-major exchange crosses NVLink.  "staged": a local MSD pass into this rank's own bucket-major
-            # staging arrays (full HBM speed), then a copy kernel that moves each bucket's long run with full-line
-            # stores on a few CTAs.  "direct": the MSD pass stores straight into the peers' memory (no staging, 16 B of
-            # HBM traffic less per pair, but ~30-pair runs: byte-masked NVLink packets).
-            self.exchange_style = os.environ.get("GLU_DIST_EXCHANGE_STYLE", "staged")
-            if self.exchange_style not in ("staged", "direct"):
-                raise ValueError(self.exchange_style)
-            if self.exchange_style == "staged":
+            if self.exchange_style == "dma":
+                self._stage_tiles = -(-self.max_count // self._tile) + RADIX
+                self._stage_k = torch.empty(self._stage_tiles * self._tile, dtype=torch.int32, device=self.device)
+                self._stage_v = torch.empty(self._stage_tiles * self._tile, dtype=torch.int32, device=self.device)
+                # host plan -> device: [256 key pointers][256 value pointers] of the local MSD pass, the segment counts
+                # and the run table of the local sort, in one pinned block / one upload
+                self._max_runs = RADIX * self.world
+                words = 2 * (2 * RADIX) + RADIX + 5 * (self._max_runs + 1)   # int64 pointers as 2 words each
+                self._dma_host = torch.zeros(words, dtype=torch.int32).pin_memory()
+                self._dma_dev = torch.zeros(words, dtype=torch.int32, device=self.device)
+                self._hist_pinned = torch.zeros(self.world * RADIX, dtype=torch.int32).pin_memory()
+                self._hist_event = torch.cuda.Event()
+                self._dma_plan = None
+                self._dma_segments = 0
+                self._dma_runs = 0
+                self._m = 0
+            elif self.exchange_style == "staged":
                 self._stage_k = torch.empty(self.max_count, dtype=torch.int32, device=self.device)
                 self._stage_v = torch.empty(self.max_count, dtype=torch.int32, device=self.device)
                 # [256 key pointers][256 value pointers] of the local MSD pass, then [256] staging offsets and [256] copy
@@ -288,6 +369,7 @@ class DistributedRadixSort:
             self._sorter._scratch.ensure(int(glu.lib.glu_radix_sort_u32kv_segmented_tmp_bytes(self.capacity_tiles)),
                                          self.device)
         else:
+            self.exchange_style = "by-destination"
             self._sorter.prepare_internal_buffers(self.capacity, self.device)
         # plan="device": the exchange plan is computed by glu_radix_exchange_plan and the partition / local sort read
         # their counts from device memory — the step has no host round trip between the histogram and the sort (the
@@ -492,6 +574,8 @@ class DistributedRadixSort:
                   "glu_radix_histogram_u32")
         # (this all-gather also orders this call's peer writes after every rank's previous use of its receive buffers)
         dist.all_gather_into_tensor(self._hist_all, self._hist, group=self.group)
+        if self.local == "segmented" and self.exchange_style == "dma":
+            return self._enqueue_exchange_dma(kptr, vptr, count, shift, st, mark)
         tptr = self._tables.data_ptr()
         pptr = self._peers_dev.data_ptr()
         cptr = self._counts_dev.data_ptr()
@@ -541,9 +625,75 @@ class DistributedRadixSort:
         # device-side barrier: when this tiny all-reduce completes, every rank's partition kernel has completed
         dist.all_reduce(self._token, group=self.group)
 
+    def _enqueue_exchange_dma(self, kptr: int, vptr: int, count: int, shift: int, st: int, mark):
+        """Exchange style "dma" (after the histogram all-gather): the host reads the histograms, plans, uploads one
+        small block of tables; a local MSD pass brings the pairs into tile-aligned bucket-major order (the buckets this
+        rank keeps go straight to their place in its own receive arrays); one copy-engine transfer per peer and array
+        moves the chunks; a device-side barrier.  The only host wait of the step is the one for the 8 KB of histograms."""
+        import torch
+
+        glu, dist = _glu(), _dist()
+        world, rank, tile = self.world, self.rank, self._tile
+        self._hist_pinned.copy_(self._hist_all, non_blocking=True)
+        self._hist_event.record()
+        self._hist_event.synchronize()
+        hist_all = self._hist_pinned.numpy().view(np.uint32).reshape(world, RADIX)
+        plan = plan_dma_exchange(hist_all, tile)
+        self._dma_plan = plan
+        self._last_hist = hist_all.copy()
+        self.last_plan = None
+        # every rank sees the same plan, so every rank raises (or none does)
+        if int(plan.recv_tiles.max()) > self.capacity_tiles or int(plan.recv_totals.max()) > self.capacity:
+            raise glu.GluError(6, f"DistributedRadixSort: a rank would receive {int(plan.recv_totals.max())} pairs, "
+                                  f"capacity is {self.capacity} (raise capacity_factor or use split_shift='auto')")
+        runs, seg_count, nb = plan.run_table(rank)
+        self._m = int(plan.recv_totals[rank])
+        self._dma_segments, self._dma_runs = nb, runs.shape[1] - 1
+        host = self._dma_host.numpy()
+        ptrs = host[: 4 * RADIX].view(np.int64)                       # [256 key pointers][256 value pointers]
+        mine = plan.dest == rank
+        b = np.arange(RADIX)
+        own_tile = np.where(mine, plan.phys_tile(rank, np.where(mine, b, plan.first_bucket[rank]), rank), 0)
+        stage_tile = plan.stage_tile[rank, :RADIX]
+        ptrs[:RADIX] = np.where(mine, self._recv_keys.ptr.value + 4 * tile * own_tile,
+                                self._stage_k.data_ptr() + 4 * tile * stage_tile)
+        ptrs[RADIX:] = np.where(mine, self._recv_vals.ptr.value + 4 * tile * own_tile,
+                                self._stage_v.data_ptr() + 4 * tile * stage_tile)
+        host[4 * RADIX: 5 * RADIX] = seg_count.view(np.int32)
+        r0 = 5 * RADIX
+        host[r0: r0 + runs.size] = runs.reshape(-1).view(np.int32)
+        self._dma_dev.copy_(self._dma_host, non_blocking=True)
+        mark("histogram+allgather+plan")
+        dptr = self._dma_dev.data_ptr()
+        glu.check(glu.lib.glu_radix_partition_u32kv(kptr, vptr, count, shift, RADIX_BITS, dptr, dptr + 8 * RADIX,
+                                                    self._part_tmp.data_ptr(), self._part_tmp.numel(), st),
+                  "glu_radix_partition_u32kv (local MSD pass)")
+        for i in range(1, world):
+            g = (rank + i) % world
+            nt = int(plan.chunk_tiles[rank, g])
+            if nt == 0:
+                continue
+            src = 4 * tile * int(plan.stage_tile[rank, plan.first_bucket[g]])
+            dst = 4 * tile * int(plan.recv_base_tile[g, rank])
+            glu.check(glu.lib.glu_memcpy_d2d(int(self._peer_keys[g]) + dst, self._stage_k.data_ptr() + src, 4 * tile * nt, st),
+                      "DistributedRadixSort (peer copy, keys)")
+            glu.check(glu.lib.glu_memcpy_d2d(int(self._peer_vals[g]) + dst, self._stage_v.data_ptr() + src, 4 * tile * nt, st),
+                      "DistributedRadixSort (peer copy, values)")
+        # device-side barrier: when this tiny all-reduce completes, every rank's copies have completed
+        dist.all_reduce(self._token, group=self.group)
+
     def _enqueue_local_sort(self, shift: int, st: int):
         """The local sort of what this rank received, on stream `st`; returns the arrays that will hold the result."""
         rk, rv = self._recv_keys.tensor, self._recv_vals.tensor
+        if self.local == "segmented" and self.exchange_style == "dma":
+            if self._dma_segments == 0:  # this rank owns no bucket (heavily skewed keys): it receives nothing
+                return rk, rv
+            end_bit = shift if shift > 0 else RADIX_BITS
+            dptr = self._dma_dev.data_ptr()
+            in_b = self._sorter.sort_segmented(rk, rv, self._alt_keys, self._alt_vals, dptr + 4 * 4 * RADIX,
+                                               self._dma_segments, self.capacity_tiles, 0, end_bit, stream=st,
+                                               runs_buffer=dptr + 4 * 5 * RADIX, num_runs=self._dma_runs)
+            return (self._alt_keys, self._alt_vals) if in_b else (rk, rv)
         if self.local == "segmented":
             # key bits [0, shift) are what is left to sort inside a bucket.  shift == 0 (adaptive split digit at the
             # bottom of the key): the keys of a bucket are all equal — one pass over the digit itself is a stable no-op
@@ -557,8 +707,15 @@ class DistributedRadixSort:
 
     def _finish(self, rk, rv):
         """Host side of a step, after everything is enqueued: how much did this rank receive, did anybody overflow."""
+        m = self._result_count()
+        return rk[:m], rv[:m], m
+
+    def _result_count(self) -> int:
+        """Pairs this rank received in the step enqueued last; raises if any rank overflowed."""
         glu = _glu()
         world = self.world
+        if self.local == "segmented" and self.exchange_style == "dma":
+            return self._m  # the host made the plan (and raised there on overflow)
         # only now does the host look at the plan: the GPU is busy with the partition and the sort meanwhile
         self._plan_event.synchronize()
         info = self._info_host.numpy()
@@ -567,8 +724,7 @@ class DistributedRadixSort:
         if int(info[world + 1]) != 0:
             raise glu.GluError(6, f"DistributedRadixSort: a rank would receive {int(info[:world].max())} pairs, "
                                   f"capacity is {self.capacity} (raise capacity_factor or use split_shift='auto')")
-        m = int(info[world])
-        return rk[:m], rv[:m], m
+        return int(info[world])
 
     def close(self, collective: bool = True) -> None:
         """Release the receive arrays and the CUDA IPC mappings of the peers' arrays.  Collective by default: a barrier
@@ -701,12 +857,7 @@ class DistributedSortPipeline:
             raise glu.GluError(1, "DistributedSortPipeline.result: the job's lane has been reused (or never submitted)")
         lane = self.lanes[ticket % L]
         torch.cuda.current_stream(self.device).wait_event(self._sorted[ticket % L])
-        lane._plan_event.synchronize()
-        info = lane._info_host.numpy()
-        if int(info[lane.world + 1]) != 0:
-            raise glu.GluError(6, f"DistributedSortPipeline: a rank would receive {int(info[:lane.world].max())} pairs, "
-                                  f"capacity is {lane.capacity}")
-        m = int(info[lane.world])
+        m = lane._result_count()
         rk, rv = self._results[ticket % L]
         return rk[:m], rv[:m], m
 

@@ -238,6 +238,22 @@ GLU_API int glu_radix_sort_u32kv_segmented(uint32_t* d_keys_a, uint32_t* d_vals_
                                            unsigned begin_bit, unsigned end_bit, void* d_tmp, size_t tmp_bytes,
                                            glu_stream_t stream, int* result_in_b);
 
+/* The same sort on an input made of RUNS (the multi-GPU sort whose all-to-all is one DMA copy per peer: a rank receives
+ * one chunk per source, and a bucket is spread over the chunks).  The input of the first pass is `num_runs` runs in
+ * segment order — a segment is one or more consecutive runs, concatenated in run order (this is what keeps the global
+ * sort stable: the runs of a bucket in source-rank order) —, run r = count[r] pairs starting at TILE phys[r] of the A
+ * arrays (runs start at tile boundaries, anywhere in the arrays; the slots behind a run's last pair are padding).
+ *   d_runs: 5 rows of (num_runs + 1) uint32 — [0] first tile of the run in the first pass's own tile numbering =
+ *   exclusive scan of ceil(count / tile), entry num_runs = the total; [1] phys; [2] count; [3] segment of the run;
+ *   [4] first tile (numbering of row 0) of the run's segment.  d_seg_count[s] = sum of the counts of segment s's runs.
+ * Later passes and the output are those of glu_radix_sort_u32kv_segmented (tile-aligned segments, compact result);
+ * max_tiles must also cover the first pass's tiles (d_runs[0][num_runs]). */
+GLU_API int glu_radix_sort_u32kv_segmented_runs(uint32_t* d_keys_a, uint32_t* d_vals_a, uint32_t* d_keys_b,
+                                                uint32_t* d_vals_b, const uint32_t* d_seg_count, size_t num_segments,
+                                                size_t max_tiles, unsigned begin_bit, unsigned end_bit,
+                                                const uint32_t* d_runs, size_t num_runs, void* d_tmp, size_t tmp_bytes,
+                                                glu_stream_t stream, int* result_in_b);
+
 /* The exchange plan of the multi-GPU sort, computed on the device from the all-gathered split-digit histograms
  * d_hist_all[world][256] (world <= 16): bucket -> destination rank by balanced prefix (contiguous bucket ranges),
  * and this rank's destination table for glu_radix_partition_by_dest_u32kv_dyn —

@@ -109,6 +109,93 @@ def test_plan_exchange_gives_stable_global_sort(dmod, oracle, world, kind, layou
         assert plan.recv_totals.max() < 1.1 * allk.size / world
 
 
+def emulate_dma(dmod, shards_k, shards_v, shift, tile):
+    """numpy emulation of the exchange style "dma": tile-aligned bucket-major staging arrays, ONE chunk copy per
+    (source, destination), then the local sort reading its buckets as runs through DmaExchangePlan.run_table — the
+    same tables the GPU path uploads (glu_radix_sort_u32kv_segmented_runs)."""
+    world = len(shards_k)
+    hist_all = np.stack([np.bincount((k >> shift) & 0xFF, minlength=256) for k in shards_k])
+    plan = dmod.plan_dma_exchange(hist_all, tile)
+    PAD = np.uint32(0xDEADBEEF)
+    recv_k = [np.full(int(t) * tile, PAD, dtype=np.uint32) for t in plan.recv_tiles]
+    recv_v = [np.full(int(t) * tile, PAD, dtype=np.uint32) for t in plan.recv_tiles]
+    hits = [np.zeros(int(t), dtype=np.int32) for t in plan.recv_tiles]
+    for s in range(world):
+        digit = (shards_k[s] >> shift) & 0xFF
+        stage_k = np.full(int(plan.stage_tile[s, 256]) * tile, PAD, dtype=np.uint32)
+        stage_v = np.full(int(plan.stage_tile[s, 256]) * tile, PAD, dtype=np.uint32)
+        for b in range(256):
+            sel = np.nonzero(digit == b)[0]
+            at = int(plan.stage_tile[s, b]) * tile
+            stage_k[at:at + sel.size] = shards_k[s][sel]
+            stage_v[at:at + sel.size] = shards_v[s][sel]
+        for g in range(world):  # one contiguous chunk of whole tiles per destination
+            nt = int(plan.chunk_tiles[s, g])
+            src = int(plan.stage_tile[s, plan.first_bucket[g]]) * tile
+            dst = int(plan.recv_base_tile[g, s]) * tile
+            recv_k[g][dst:dst + nt * tile] = stage_k[src:src + nt * tile]
+            recv_v[g][dst:dst + nt * tile] = stage_v[src:src + nt * tile]
+            hits[g][dst // tile:dst // tile + nt] += 1
+    for h in hits:
+        assert np.all(h == 1)  # the chunks tile every receive array exactly once
+    out_k, out_v = [], []
+    for g in range(world):
+        runs, seg_count, nb = plan.run_table(g)
+        R = runs.shape[1] - 1
+        assert R == nb * world and int(runs[2, :R].sum()) == int(plan.recv_totals[g]) == int(seg_count.sum())
+        assert int(runs[0, R]) == int(plan.recv_tiles[g])
+        seg_k = [[] for _ in range(nb)]
+        seg_v = [[] for _ in range(nb)]
+        for r in range(R):
+            c, at, sg = int(runs[2, r]), int(runs[1, r]) * tile, int(runs[3, r])
+            assert int(runs[0, r + 1]) - int(runs[0, r]) == -(-c // tile)
+            assert int(runs[4, r]) == int(runs[0, sg * world])
+            seg_k[sg].append(recv_k[g][at:at + c])
+            seg_v[sg].append(recv_v[g][at:at + c])
+        for sg in range(nb):
+            k, v = np.concatenate(seg_k[sg]), np.concatenate(seg_v[sg])
+            assert int(seg_count[sg]) == k.size
+            low = k & np.uint32((1 << shift) - 1) if shift > 0 else np.zeros_like(k)
+            o = np.argsort(low, kind="stable")  # the local sort only looks at the bits below the split digit
+            out_k.append(k[o])
+            out_v.append(v[o])
+    cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, np.uint32)
+    return plan, cat(out_k), cat(out_v)
+
+
+@pytest.mark.parametrize("tile", [8, 7680])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("kind", ["uniform", "ent16", "dups", "one_bucket"])
+def test_plan_dma_exchange_gives_stable_global_sort(dmod, oracle, world, kind, tile):
+    n = 20011
+    shards_k, shards_v = [], []
+    for r in range(world):
+        if kind == "uniform":
+            k = oracle.mt19937_u32(10 + r, n + 13 * r)
+        elif kind == "ent16":
+            k = oracle.mt19937_u32(10 + r, n) & np.uint32(0xFFFF)
+        elif kind == "dups":
+            k = oracle.random_u32(1 + r, n, 0, 10)
+        else:
+            k = np.full(n, 0x12345678, dtype=np.uint32)
+        shards_k.append(k)
+    base = 0
+    for k in shards_k:
+        shards_v.append(np.arange(base, base + k.size, dtype=np.uint32))
+        base += k.size
+    allk, allv = np.concatenate(shards_k), np.concatenate(shards_v)
+    shift = dmod.choose_split_shift(int(allk.min()), int(allk.max()))
+    plan, gk, gv = emulate_dma(dmod, shards_k, shards_v, shift, tile)
+    ek, ev = oracle.stable_sort_pairs(allk, allv)
+    np.testing.assert_array_equal(gk, ek)
+    np.testing.assert_array_equal(gv, ev)
+    # what the run tables promise the device code
+    for g in range(world):
+        runs, _, nb = plan.run_table(g)
+        assert nb <= 256 and runs.shape[1] - 1 <= 256 * world
+        assert int(plan.recv_tiles[g]) <= -(-int(plan.recv_totals[g]) // tile) + 256 * world
+
+
 WORKER = r'''
 import os, sys
 import numpy as np

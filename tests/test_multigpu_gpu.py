@@ -230,8 +230,8 @@ def gather(obj):
 # exchange "p2p" runs twice: destination-major exchange + full local sort, and bucket-major exchange + segmented local
 # sort on the key bits below the split digit (north_star's MSD split + 24-bit local sort)
 for exchange in os.environ["GLU_EXCHANGES"].split(","):
-  for local, style in ((("full", "staged"), ("segmented", "staged"), ("segmented", "direct")) if exchange == "p2p"
-                       else (("full", "staged"),)):
+  for local, style in ((("full", "staged"), ("segmented", "staged"), ("segmented", "direct"), ("segmented", "dma"))
+                       if exchange == "p2p" else (("full", "staged"),)):
     os.environ["GLU_DIST_EXCHANGE_STYLE"] = style  # how the bucket-major exchange crosses NVLink (segmented only)
     sorter_fixed = glu.DistributedRadixSort(400_000, exchange=exchange, capacity_factor=2.5, local=local)
     sorter_auto = glu.DistributedRadixSort(400_000, exchange=exchange, capacity_factor=2.5, split_shift="auto", local=local)
@@ -269,10 +269,12 @@ os.environ.pop("GLU_DIST_EXCHANGE_STYLE", None)
 
 # ---- the two-lane pipeline (DistributedSortPipeline): consecutive independent jobs, the exchange of job k+1 runs under
 # the local sort of job k; every job's result must equal std::stable_sort of the concatenated inputs
-for pipe_local in ("segmented", "full"):
+for pipe_local, pipe_style in (("segmented", "dma"), ("segmented", "staged"), ("full", "staged")):
   os.environ["GLU_DIST_LOCAL"] = pipe_local
+  os.environ["GLU_DIST_EXCHANGE_STYLE"] = pipe_style
   pipe = glu.DistributedSortPipeline(400_000, capacity_factor=2.5)
   assert pipe.lanes[0].local == pipe_local
+  assert pipe_local == "full" or pipe.lanes[0].exchange_style == pipe_style
   jobs, pending = [], []
 
   def check_job(j, ticket):
@@ -286,7 +288,7 @@ for pipe_local in ("segmented", "full"):
           assert np.array_equal(gk, ek), f"pipeline job {j}: keys differ"
           assert np.array_equal(gv, ev), f"pipeline job {j}: values differ"
 
-  for j in range(5):
+  for j in range(7):
       n = 250_003 + 977 * rank + 1000 * j
       keys = oracle.mt19937_u32(60 + 10 * j + rank, n)
       if j == 3:
@@ -297,12 +299,13 @@ for pipe_local in ("segmented", "full"):
       dk, dv = up(keys), up(vals)
       jobs.append((keys, vals, dk, dv))
       pending.append((j, pipe.submit(dk, dv, n)))
-      if len(pending) == 2:
+      if len(pending) == pipe.num_lanes:
           check_job(*pending.pop(0))
   while pending:
       check_job(*pending.pop(0))
   pipe.close()
 del os.environ["GLU_DIST_LOCAL"]
+del os.environ["GLU_DIST_EXCHANGE_STYLE"]
 
 # ---- reduce / scan sharded by contiguous ranges
 n = 1_000_003 + 31 * rank
