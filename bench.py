@@ -754,11 +754,20 @@ def run_b200(args):
 
 def e2e_single(args, glu, torch, np, n, steps):
     """e2e at one GPU: the same sort through the host-buffer C-ABI, pinned host memory, copies inside the timed region.
-    The steps go through glu_host_sort_queue (depth 2): the upload of step k+1 overlaps the sort and the download of step
-    k, every step still pays its own H2D + sort + D2H.  Results land in place, so every step needs its own unsorted
-    pinned input: K steps are timed in chunks of at most 8 inputs (16 GiB of pinned memory), refilled between chunks
-    outside the clock.  The synchronous single call (glu_radix_sort_u32kv_host) is timed beside it."""
+    The steps go through glu_host_sort_queue (depth 3: with two device slots the upload of step k+2 would wait for the
+    download of step k on the same slot, i.e. the upload engine would idle for one sort per step): the upload of step
+    k+1 overlaps the sort and the download of step k, every step still pays its own H2D + sort + D2H.  Results land in
+    place, so every step needs its own unsorted pinned input: all K inputs are pinned at once when the host has the
+    memory for it (a quarter of MemAvailable), otherwise the steps are timed in chunks of 8 inputs refilled between
+    chunks outside the clock (every chunk then pays the queue's fill and drain).  The synchronous single call
+    (glu_radix_sort_u32kv_host) is timed beside it."""
     slots = min(steps, 8)
+    try:
+        avail = next(int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable"))
+        if 8 * n * min(steps, 24) <= avail // 4:
+            slots = min(steps, 24)
+    except Exception:
+        pass
     host = []
     for i in range(slots):
         hk, hk_ptr = pinned_u32(glu, n)
@@ -772,13 +781,13 @@ def e2e_single(args, glu, torch, np, n, steps):
             hv[:] = np.arange(n, dtype=np.uint32)
             seed[0] += 1
 
-    queue = glu.HostSortQueue(n, depth=2)
+    queue = glu.HostSortQueue(n, depth=3)
     wk, wk_ptr = pinned_u32(glu, 1 << 20)
     wv, wv_ptr = pinned_u32(glu, 1 << 20)
     wk[:] = np.arange(1 << 20, dtype=np.uint32)[::-1]
     wv[:] = 0
-    queue.submit(wk, wv)  # warms the queue's streams
-    queue.submit(wk, wv)
+    for _ in range(3):
+        queue.submit(wk, wv)  # warms the queue's streams
     queue.wait()
     e2e_t, done = 0.0, 0
     while done < steps:
@@ -807,8 +816,8 @@ def e2e_single(args, glu, torch, np, n, steps):
     sync_t = time.perf_counter() - t0
     out = {"value": n * steps / e2e_t / 1e9, "unit": "Gpairs/s", "h2d_bytes_per_step": 8 * n,
            "d2h_bytes_per_step": 8 * n, "steps": steps, "ms_per_step": 1e3 * e2e_t / steps,
-           "api": "glu_host_sort_queue (depth 2; per step: pinned host arrays -> H2D -> sort -> D2H, "
-                  "consecutive steps overlapped)",
+           "api": "glu_host_sort_queue (depth 3; per step: pinned host arrays -> H2D -> sort -> D2H, "
+                  f"consecutive steps overlapped; {slots} pinned inputs per timed chunk)",
            "synchronous_call": {"value": n / sync_t / 1e9, "ms": 1e3 * sync_t, "api": "glu_radix_sort_u32kv_host"}}
     for _, _, p0, p1 in host:
         glu.lib.glu_free_host(p0)
