@@ -308,7 +308,7 @@ class DistributedRadixSort:
         # bucket, what a rank sends to a peer is ONE contiguous chunk, moved by the copy engines (cudaMemcpyAsync over
         # the peer mapping: no SM is spent on the all-to-all); the plan is made on the host from the all-gathered
         # histograms (DmaExchangePlan) and the local sort reads its buckets as runs.
-        self.exchange_style = os.environ.get("GLU_DIST_EXCHANGE_STYLE", "staged")
+        self.exchange_style = os.environ.get("GLU_DIST_EXCHANGE_STYLE", "dma")
         if self.exchange_style not in ("staged", "direct", "dma"):
             raise ValueError(self.exchange_style)
         # every bucket (dma: every run = bucket x source) may end in a partial tile
@@ -768,26 +768,27 @@ class DistributedRadixSort:
 
 
 class DistributedSortPipeline:
-    """A stream of independent distributed sorts with the NVLink-bound exchange of job k+1 overlapping the local sort of
-    job k.  EXPERIMENTAL: written at the end of round 1, after the round's GPU time was spent — it composes only
-    kernels and collectives that `DistributedRadixSort` already uses, but it has NOT been run on GPUs yet, is not used
-    by default anywhere, and has no place in the numbers of DESIGN.md.
+    """A stream of independent distributed sorts with the exchange of job k+1 overlapping the local sort of job k —
+    what `bench.py` times at N > 1 (world-2 and world-8 parity: tests/test_multigpu_gpu.py; every bench step's last
+    output is verified on the device).
 
-    Why: at 8 GPUs a sort step is 0.24 ms histogram / plan + 3.5 ms partition-and-exchange (a onesweep pass that costs
-    1.07 ms on local memory: its SMs mostly wait for NVLink) + 4.5 ms local sort (SM-bound) = 8.3 ms.  Two lanes — each
-    a complete `DistributedRadixSort` with its own receive buffers — and two streams turn that into max(exchange,
-    local sort) per job in the steady state.
+    Why: a step is the split-digit histogram, the plan, a local MSD pass, the NVLink all-to-all and a 3-pass local
+    sort.  The all-to-all (2.4 ms of copy-engine time at 8 GPUs and 2^28 pairs each, no SM involved with the "dma"
+    exchange style) and the host's plan hide under the previous job's local sort when consecutive jobs run on two
+    streams and two lanes — each lane a complete `DistributedRadixSort` with its own receive / staging arrays.
 
         pipe = DistributedSortPipeline(max_count)
         t0 = pipe.submit(keys0, vals0, n)        # enqueues, returns a ticket
         t1 = pipe.submit(keys1, vals1, n)        # its exchange runs under job 0's local sort
-        sk, sv, m = pipe.result(t0)              # valid until the submit after next (lane reuse)
+        sk, sv, m = pipe.result(t0)              # valid until `num_lanes` later submits reuse the lane
 
-    Ordering.  Job k uses lane k % 2.  Stream X carries histogram -> all-gather -> plan -> partition (peer stores) ->
-    all-reduce barrier, stream S the local sort.  Before job k's all-gather, X waits for this rank's local sort of job
-    k - 2 (same lane) and for everything the caller's stream had enqueued at submit time (its consumption of result
-    k - 2); the all-gather completes only when every rank has got that far, so nobody's receive buffers of the lane are
-    overwritten while still in use.  All collectives are issued on X, in the same order on every rank."""
+    Ordering.  Job k uses lane k % num_lanes.  Stream X carries histogram -> all-gather -> plan -> MSD pass -> peer
+    copies -> all-reduce barrier, stream S the local sort.  Before job k's all-gather, X waits for this rank's local sort
+    of job k - num_lanes (same lane) and for everything the caller's stream had enqueued at submit time (its consumption
+    of that job's result); the all-gather completes only when every rank has got that far, so nobody's receive arrays
+    of the lane are overwritten while still in use.  All collectives are issued on X, in the same order on every rank.
+    With the "dma" exchange style `submit` blocks the host until the job's histograms are all-gathered (the plan is made
+    on the host); the GPU keeps working on the previous jobs meanwhile."""
 
     def __init__(self, max_count: int, group=None, capacity_factor: float = 1.25, split_shift: int = 32 - RADIX_BITS,
                  lanes: int | None = None):
@@ -797,11 +798,12 @@ class DistributedSortPipeline:
 
         glu = _glu()
         # Lanes = complete sets of receive / staging arrays and scratch.  Job k uses lane k % lanes; its exchange may
-        # start as soon as the local sort of job k - lanes has finished, so with three lanes the exchange stream runs up to
-        # two jobs ahead of the sorting stream and neither waits for the other in the steady state (with two, every
-        # exchange is fenced by the sort two jobs back: measured 6.7 ms per step at 8 GPUs against ... with three).
+        # start as soon as the local sort of job k - lanes has finished.  Two lanes are enough: the sorting stream is the
+        # longer of the two chains, so the exchange of job k never has to start before the sort of job k - 2 is over
+        # (measured at 2 GPUs, 2^28 pairs each: 5.36 ms per step with two lanes, 5.41 ms with three — and a lane is
+        # ~32 GB at 2^30 pairs per GPU; gpurun_out/r02j).
         if lanes is None:
-            lanes = int(os.environ.get("GLU_PIPE_LANES", "3"))
+            lanes = int(os.environ.get("GLU_PIPE_LANES", "2"))
         if lanes < 2:
             raise ValueError("DistributedSortPipeline needs at least two lanes")
         self.num_lanes = lanes

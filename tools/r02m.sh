@@ -1,6 +1,7 @@
 #!/bin/bash
 # Round 2 multi-GPU session: usage (under gpurun --gpus N): bash tools/r02m.sh N [tag] [steps] [what]
-#   what: comma list of  probe,pytest,phases,sweep,full,ref   (default: all)
+#   what: comma list of  probe,pcie,pytest,phases,sweep,full,ref   (default: all but pcie)
+#   SWEEPS (environment): the sweep's variants, one per line
 set -u
 N=${1:-2}
 TAG=${2:-r02m$N}
@@ -30,16 +31,15 @@ if has phases; then
   cat $OUT/phases.log
 fi
 if has sweep; then
-  for v in "GLU_BENCH_MODE=serial GLU_DIST_LOCAL=full" \
-           "GLU_BENCH_MODE=serial GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=direct" \
-           "GLU_BENCH_MODE=serial GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=staged" \
-           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=full" \
-           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=direct" \
-           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=staged" \
-           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=staged GLU_EXCHANGE_COPY_CTAS=74" \
-           "GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=staged GLU_PIPE_PRIORITY=x"; do
+  # one variant per line in $SWEEPS (environment assignments for bench.py); default: the round's comparison set
+  DEFAULT_SWEEPS="GLU_BENCH_MODE=serial GLU_DIST_LOCAL=full
+GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=staged
+GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=dma
+GLU_BENCH_MODE=serial GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=dma"
+  echo "${SWEEPS:-$DEFAULT_SWEEPS}" | while IFS= read -r v; do
+    [ -z "$v" ] && continue
     echo "== $v" >> $OUT/sweep.log
-    ( env $v timeout 200 $RUN --master-port 29712 bench.py --gpus $N --steps $STEPS --warmup 3 --no-side-metrics 2>&1 \
+    ( env $v timeout 200 $RUN --master-port 29712 bench.py --gpus $N --steps $STEPS --warmup 3 --no-side-metrics < /dev/null 2>&1 \
         | grep -E "^\{|Error|error|assert|Traceback" | tail -3 \
         | python -c "
 import sys, json
