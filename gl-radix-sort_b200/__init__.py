@@ -98,6 +98,8 @@ ABI = {
     "glu_memcpy_d2h": (_int, [_vp, _vp, _sz, _vp]),
     "glu_memcpy_d2d": (_int, [_vp, _vp, _sz, _vp]),
     "glu_memset_u32": (_int, [_vp, ctypes.c_uint32, _sz, _vp]),
+    "glu_signal_peers_u32": (_int, [_vp, _int, ctypes.c_uint32, _vp]),
+    "glu_stream_wait_flags_u32": (_int, [_vp, _int, _int, ctypes.c_uint32, _vp]),
     "glu_stream_create": (_int, [ctypes.POINTER(_vp)]),
     "glu_stream_destroy": (_int, [_vp]),
     "glu_stream_synchronize": (_int, [_vp]),

@@ -102,6 +102,42 @@ namespace glu_b200
         for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x)
             dst[i] = value;
     }
+
+    // Stream-ordered signalling between GPUs (the multi-GPU sort's device-side barrier without a collective): a rank
+    // stores an epoch number into one word of every peer's flag array AFTER its copies into that peer (same stream), a
+    // peer's sorting stream waits until all its words have reached the epoch.
+    struct PeerFlags
+    {
+        uint32_t* ptr[16];
+    };
+
+    __global__ void signal_peers_kernel(PeerFlags flags, int count, uint32_t value)
+    {
+        if (int(threadIdx.x) < count && flags.ptr[threadIdx.x])
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.ptr[threadIdx.x]), "r"(value) : "memory");
+    }
+
+    // thread i waits for flags[i] >= value (wrap-around safe), i != skip.  Bounded: a peer that never signals (it
+    // failed) traps this kernel after ~4 s instead of hanging the GPU.
+    __global__ void wait_flags_kernel(const uint32_t* flags, int count, int skip, uint32_t value)
+    {
+        const int i = int(threadIdx.x);
+        if (i >= count || i == skip)
+            return;
+        unsigned long long t0 = 0, now = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (true)
+        {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + i) : "memory");
+            if (int32_t(v - value) >= 0)
+                return;
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 4000000000ull)
+                __trap();
+        }
+    }
 } // namespace glu_b200
 
 extern "C"
@@ -281,6 +317,33 @@ extern "C"
             fill_u32_kernel<<<grid, 256, 0, s>>>(static_cast<uint32_t*>(d_dst), value, count);
             GLU_LAUNCH_CHECK();
         }
+        return GLU_SUCCESS;
+    }
+
+    int glu_signal_peers_u32(const uint64_t* h_flag_addrs, int count, uint32_t value, glu_stream_t stream)
+    {
+        if (!h_flag_addrs || count < 1 || count > 16)
+            return GLU_ERROR_INVALID_ARGUMENT;
+        glu_b200::PeerFlags f{};
+        for (int i = 0; i < count; i++)
+        {
+            if (h_flag_addrs[i] % sizeof(uint32_t) != 0)
+                return GLU_ERROR_MISALIGNED;
+            f.ptr[i] = reinterpret_cast<uint32_t*>(uintptr_t(h_flag_addrs[i]));
+        }
+        glu_b200::signal_peers_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(f, count, value);
+        GLU_LAUNCH_CHECK();
+        return GLU_SUCCESS;
+    }
+
+    int glu_stream_wait_flags_u32(const uint32_t* d_flags, int count, int skip, uint32_t value, glu_stream_t stream)
+    {
+        if (!d_flags || count < 1 || count > 32)
+            return GLU_ERROR_INVALID_ARGUMENT;
+        if (reinterpret_cast<uintptr_t>(d_flags) % sizeof(uint32_t) != 0)
+            return GLU_ERROR_MISALIGNED;
+        glu_b200::wait_flags_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(d_flags, count, skip, value);
+        GLU_LAUNCH_CHECK();
         return GLU_SUCCESS;
     }
 

@@ -333,8 +333,19 @@ class DistributedRadixSort:
         self.by_dest = self.world <= 16
         self._minmax = None
         self._token = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self._peer_keys = self._peer_vals = None
+        self._peer_keys = self._peer_vals = self._peer_flags = None
+        self._flags = None
         self._stage_keys = self._stage_vals = None
+        # dma style: how the receiver learns that the peers' chunks have landed — "flags": every sender stores the
+        # exchange's epoch into the receiver's flag array after its copies (stream-ordered), the receiver's sorting stream
+        # waits for the flags (no collective; the copies may then run on a stream of their own, `_copy_stream`, set by
+        # DistributedSortPipeline); "nccl": a 4-byte all-reduce after the copies
+        self._dma_sync = os.environ.get("GLU_DIST_DMA_SYNC", "flags")
+        if self._dma_sync not in ("flags", "nccl"):
+            raise ValueError(self._dma_sync)
+        self._copy_stream = None
+        self._trace = None
+        self._epoch = 0
         self.exchange = self._setup_exchange(exchange)
         self.local = "segmented" if (want_seg and self.exchange == "p2p") else "full"
         if local == "segmented" and self.local != "segmented":
@@ -356,6 +367,8 @@ class DistributedRadixSort:
                 self._dma_dev = torch.zeros(words, dtype=torch.int32, device=self.device)
                 self._hist_pinned = torch.zeros(self.world * RADIX, dtype=torch.int32).pin_memory()
                 self._hist_event = torch.cuda.Event()
+                self._msd_event = torch.cuda.Event()
+                self._sent_event = torch.cuda.Event()
                 self._dma_plan = None
                 self._dma_segments = 0
                 self._dma_runs = 0
@@ -404,35 +417,45 @@ class DistributedRadixSort:
             raise ValueError(exchange)
         ok, err = True, ""
         if exchange in ("auto", "p2p"):
+            arrays = [self._recv_keys, self._recv_vals]
+            if self.exchange_style == "dma":
+                # one word per source rank: the epoch of the last exchange whose chunk from that rank has landed here
+                self._flags = _DeviceArray(32, self.device)
+                self._flags.tensor.zero_()
+                torch.cuda.synchronize(self.device)
+                arrays.append(self._flags)
             try:
-                hk = ctypes.create_string_buffer(64)
-                hv = ctypes.create_string_buffer(64)
-                glu.check(glu.lib.glu_ipc_get_handle(self._recv_keys.ptr, hk), "glu_ipc_get_handle")
-                glu.check(glu.lib.glu_ipc_get_handle(self._recv_vals.ptr, hv), "glu_ipc_get_handle")
-                mine = (hk.raw, hv.raw)
+                mine = []
+                for a in arrays:
+                    h = ctypes.create_string_buffer(64)
+                    glu.check(glu.lib.glu_ipc_get_handle(a.ptr, h), "glu_ipc_get_handle")
+                    mine.append(h.raw)
+                mine = tuple(mine)
             except glu.GluError as e:  # pragma: no cover - depends on the box
                 mine, ok, err = None, False, str(e)
             handles = [None] * self.world
             dist.all_gather_object(handles, mine, group=self.group)
             ok = ok and all(h is not None for h in handles)
-            peer_keys, peer_vals = [0] * self.world, [0] * self.world
+            peers = [[0] * self.world for _ in arrays]
             if ok:
                 try:
                     for g, h in enumerate(handles):
-                        if g == self.rank:
-                            peer_keys[g], peer_vals[g] = self._recv_keys.ptr.value, self._recv_vals.ptr.value
-                            continue
-                        pk, pv = ctypes.c_void_p(), ctypes.c_void_p()
-                        glu.check(glu.lib.glu_ipc_open_handle(h[0], ctypes.byref(pk)), "glu_ipc_open_handle")
-                        glu.check(glu.lib.glu_ipc_open_handle(h[1], ctypes.byref(pv)), "glu_ipc_open_handle")
-                        peer_keys[g], peer_vals[g] = pk.value, pv.value
+                        for j, a in enumerate(arrays):
+                            if g == self.rank:
+                                peers[j][g] = a.ptr.value
+                                continue
+                            p = ctypes.c_void_p()
+                            glu.check(glu.lib.glu_ipc_open_handle(h[j], ctypes.byref(p)), "glu_ipc_open_handle")
+                            peers[j][g] = p.value
                 except glu.GluError as e:  # pragma: no cover
                     ok, err = False, str(e)
             flags = [None] * self.world
             dist.all_gather_object(flags, ok, group=self.group)
             if all(flags):
-                self._peer_keys = np.array(peer_keys, dtype=np.int64)
-                self._peer_vals = np.array(peer_vals, dtype=np.int64)
+                self._peer_keys = np.array(peers[0], dtype=np.int64)
+                self._peer_vals = np.array(peers[1], dtype=np.int64)
+                if len(arrays) > 2:
+                    self._peer_flags = np.array(peers[2], dtype=np.int64)
                 return "p2p"
             if exchange == "p2p":
                 raise glu.GluError(7, f"DistributedRadixSort: CUDA IPC peer mapping failed ({err})")
@@ -636,7 +659,15 @@ class DistributedRadixSort:
         world, rank, tile = self.world, self.rank, self._tile
         self._hist_pinned.copy_(self._hist_all, non_blocking=True)
         self._hist_event.record()
+        tr = getattr(self, "_trace", None)
+        if tr is not None:
+            import time
+
+            tr["hist"] = torch.cuda.Event(enable_timing=True)
+            tr["hist"].record()
         self._hist_event.synchronize()
+        if tr is not None:
+            tr["host_hist_seen"] = time.perf_counter()
         hist_all = self._hist_pinned.numpy().view(np.uint32).reshape(world, RADIX)
         plan = plan_dma_exchange(hist_all, tile)
         self._dma_plan = plan
@@ -663,11 +694,25 @@ class DistributedRadixSort:
         r0 = 5 * RADIX
         host[r0: r0 + runs.size] = runs.reshape(-1).view(np.int32)
         self._dma_dev.copy_(self._dma_host, non_blocking=True)
+        if tr is not None:
+            tr["host_plan_done"] = time.perf_counter()
+            tr["plan"] = torch.cuda.Event(enable_timing=True)
+            tr["plan"].record()
         mark("histogram+allgather+plan")
         dptr = self._dma_dev.data_ptr()
         glu.check(glu.lib.glu_radix_partition_u32kv(kptr, vptr, count, shift, RADIX_BITS, dptr, dptr + 8 * RADIX,
                                                     self._part_tmp.data_ptr(), self._part_tmp.numel(), st),
                   "glu_radix_partition_u32kv (local MSD pass)")
+        # the copies: on the exchange stream itself, or (pipeline) on the copy stream once the MSD pass is done, so that
+        # the exchange stream is free for the next job's histogram / plan / MSD pass while the copy engines work
+        cst = st
+        if tr is not None:
+            tr["msd"] = torch.cuda.Event(enable_timing=True)
+            tr["msd"].record()
+        if self._copy_stream is not None:
+            self._msd_event.record()
+            self._copy_stream.wait_event(self._msd_event)
+            cst = self._copy_stream.cuda_stream
         for i in range(1, world):
             g = (rank + i) % world
             nt = int(plan.chunk_tiles[rank, g])
@@ -675,12 +720,22 @@ class DistributedRadixSort:
                 continue
             src = 4 * tile * int(plan.stage_tile[rank, plan.first_bucket[g]])
             dst = 4 * tile * int(plan.recv_base_tile[g, rank])
-            glu.check(glu.lib.glu_memcpy_d2d(int(self._peer_keys[g]) + dst, self._stage_k.data_ptr() + src, 4 * tile * nt, st),
+            glu.check(glu.lib.glu_memcpy_d2d(int(self._peer_keys[g]) + dst, self._stage_k.data_ptr() + src, 4 * tile * nt, cst),
                       "DistributedRadixSort (peer copy, keys)")
-            glu.check(glu.lib.glu_memcpy_d2d(int(self._peer_vals[g]) + dst, self._stage_v.data_ptr() + src, 4 * tile * nt, st),
+            glu.check(glu.lib.glu_memcpy_d2d(int(self._peer_vals[g]) + dst, self._stage_v.data_ptr() + src, 4 * tile * nt, cst),
                       "DistributedRadixSort (peer copy, values)")
-        # device-side barrier: when this tiny all-reduce completes, every rank's copies have completed
-        dist.all_reduce(self._token, group=self.group)
+        self._epoch += 1
+        if self._dma_sync == "flags" and world > 1:
+            addrs = (ctypes.c_uint64 * world)(*[0 if g == rank else int(self._peer_flags[g]) + 4 * rank
+                                                for g in range(world)])
+            glu.check(glu.lib.glu_signal_peers_u32(addrs, world, self._epoch & 0xFFFFFFFF, cst), "glu_signal_peers_u32")
+        if self._copy_stream is not None:
+            self._sent_event.record(self._copy_stream)
+        if self._dma_sync == "nccl":
+            if self._copy_stream is not None:
+                torch.cuda.current_stream(self.device).wait_event(self._sent_event)
+            # device-side barrier: when this tiny all-reduce completes, every rank's copies have completed
+            dist.all_reduce(self._token, group=self.group)
 
     def _enqueue_local_sort(self, shift: int, st: int):
         """The local sort of what this rank received, on stream `st`; returns the arrays that will hold the result."""
@@ -688,6 +743,10 @@ class DistributedRadixSort:
         if self.local == "segmented" and self.exchange_style == "dma":
             if self._dma_segments == 0:  # this rank owns no bucket (heavily skewed keys): it receives nothing
                 return rk, rv
+            if self._dma_sync == "flags" and self.world > 1:
+                glu = _glu()
+                glu.check(glu.lib.glu_stream_wait_flags_u32(self._flags.ptr, self.world, self.rank,
+                                                            self._epoch & 0xFFFFFFFF, st), "glu_stream_wait_flags_u32")
             end_bit = shift if shift > 0 else RADIX_BITS
             dptr = self._dma_dev.data_ptr()
             in_b = self._sorter.sort_segmented(rk, rv, self._alt_keys, self._alt_vals, dptr + 4 * 4 * RADIX,
@@ -746,7 +805,12 @@ class DistributedRadixSort:
                 if g != self.rank:
                     glu.lib.glu_ipc_close_handle(ctypes.c_void_p(int(self._peer_keys[g])))
                     glu.lib.glu_ipc_close_handle(ctypes.c_void_p(int(self._peer_vals[g])))
-            self._peer_keys = self._peer_vals = None
+                    if self._peer_flags is not None:
+                        glu.lib.glu_ipc_close_handle(ctypes.c_void_p(int(self._peer_flags[g])))
+            self._peer_keys = self._peer_vals = self._peer_flags = None
+        if self._flags is not None:
+            self._flags.free()
+            self._flags = None
         self._recv_keys.free()
         self._recv_vals.free()
         self._sorter = None
@@ -815,6 +879,18 @@ class DistributedSortPipeline:
         prio = os.environ.get("GLU_PIPE_PRIORITY", "x")
         self.stream_x = torch.cuda.Stream(device=self.device, priority=-1 if prio == "x" else 0)
         self.stream_s = torch.cuda.Stream(device=self.device, priority=-1 if prio == "s" else 0)
+        # "dma" exchange with flag signalling: the peer copies of job k run on a stream of their own (copy engines only),
+        # so the exchange stream goes on with job k + 1's histogram / plan / MSD pass meanwhile.  GLU_PIPE_COPY_STREAM=0:
+        # the copies stay on the exchange stream.
+        self.stream_d = None
+        lane0 = self.lanes[0]
+        if (lane0.local == "segmented" and lane0.exchange_style == "dma" and lane0._dma_sync == "flags"
+                and os.environ.get("GLU_PIPE_COPY_STREAM", "1") != "0"):
+            self.stream_d = torch.cuda.Stream(device=self.device, priority=-1)
+            for lane in self.lanes:
+                lane._copy_stream = self.stream_d
+        # GLU_PIPE_TRACE=1: timing events around the phases of every job (tools/pipeline_timeline.py)
+        self.trace = [] if os.environ.get("GLU_PIPE_TRACE", "0") == "1" else None
         self._exchanged = [torch.cuda.Event() for _ in range(lanes)]
         self._sorted = [torch.cuda.Event() for _ in range(lanes)]
         self._submitted = 0
@@ -835,16 +911,41 @@ class DistributedSortPipeline:
         if count < 1 or count > lane.max_count:
             raise glu.GluError(1, f"count must be in [1, {lane.max_count}]")
         shift = int(lane.split_shift)
+        tr = None
+        if self.trace is not None:
+            import time
+
+            def ev(stream):
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream)
+                return e
+            tr = {"job": k, "host_submit": time.perf_counter()}
+            lane._trace = tr
+            self.trace.append(tr)
         self.stream_x.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream_x):
             if k >= L:
                 self.stream_x.wait_event(self._sorted[k % L])
+                if self.stream_d is not None:  # the lane's staging arrays: its previous copies have left
+                    self.stream_x.wait_event(lane._sent_event)
+            if tr is not None:
+                tr["x_begin"] = ev(self.stream_x)
             lane._enqueue_exchange(kptr, vptr, count, shift, self.stream_x.cuda_stream)
             self._exchanged[k % L].record(self.stream_x)
+            if tr is not None:
+                tr["x_end"] = ev(self.stream_x)
+                if self.stream_d is not None:
+                    tr["copies_end"] = ev(self.stream_d)
         with torch.cuda.stream(self.stream_s):
             self.stream_s.wait_event(self._exchanged[k % L])
+            if tr is not None:
+                tr["s_begin"] = ev(self.stream_s)
             self._results[k % L] = lane._enqueue_local_sort(shift, self.stream_s.cuda_stream)
             self._sorted[k % L].record(self.stream_s)
+            if tr is not None:
+                tr["s_end"] = ev(self.stream_s)
+                tr["host_return"] = time.perf_counter()
+                lane._trace = None
         self._submitted = k + 1
         return k
 
@@ -870,6 +971,8 @@ class DistributedSortPipeline:
         cur = torch.cuda.current_stream(self.device)
         cur.wait_stream(self.stream_x)
         cur.wait_stream(self.stream_s)
+        if self.stream_d is not None:
+            cur.wait_stream(self.stream_d)
 
     def close(self) -> None:
         """Collective: releases both lanes (receive arrays, peer mappings)."""

@@ -344,6 +344,14 @@ GLU_API int glu_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes, glu_str
 GLU_API int glu_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes, glu_stream_t stream);
 GLU_API int glu_memcpy_d2d(void* d_dst, const void* d_src, size_t bytes, glu_stream_t stream);
 GLU_API int glu_memset_u32(void* d_dst, uint32_t value, size_t count, glu_stream_t stream);
+/* Stream-ordered signalling between GPUs (the device-side barrier of the multi-GPU sort's "dma" exchange, no
+ * collective involved): glu_signal_peers_u32 stores `value` (an epoch number) into the words h_flag_addrs[0..count)
+ * (count <= 16, addresses in peer memory as mapped in this process, 0 = skip) after everything enqueued on `stream`
+ * before it — e.g. the copies into those peers; glu_stream_wait_flags_u32 makes `stream` wait until the local words
+ * d_flags[i] (i < count <= 32, i != skip) have all reached `value` (wrap-around safe; traps after ~4 s instead of
+ * hanging if a peer never signals). */
+GLU_API int glu_signal_peers_u32(const uint64_t* h_flag_addrs, int count, uint32_t value, glu_stream_t stream);
+GLU_API int glu_stream_wait_flags_u32(const uint32_t* d_flags, int count, int skip, uint32_t value, glu_stream_t stream);
 GLU_API int glu_stream_create(glu_stream_t* stream); /* a blocking stream: ordered with the legacy default stream */
 GLU_API int glu_stream_destroy(glu_stream_t stream);
 GLU_API int glu_stream_synchronize(glu_stream_t stream);
