@@ -31,6 +31,7 @@ namespace
     constexpr int k_seg_tile = k_seg_threads * k_seg_ipt;
     static_assert(k_seg_tile == k_seg1_threads * k_seg1_ipt, "one layout for both kernels");
     constexpr int k_max_segments = 256;
+    constexpr int k_seg_hist_group = 2; // tiles whose loads are in flight together in seg_histogram_kernel
 
     struct SegLayout
     {
@@ -196,36 +197,75 @@ namespace
             }
             __syncthreads();
         };
+        // k_seg_hist_group tiles per round: all their loads are issued before the first count (two 128-bit loads per
+        // thread and tile would leave the memory system idle most of the time)
+        constexpr int G = k_seg_hist_group;
+        constexpr int J = (k_seg_tile / 4 + k_hist_threads - 1) / k_hist_threads; // 128-bit units per thread and tile
         uint32_t cur_seg = info[t_begin].x >> 24;
-        for (uint32_t t = t_begin; t < t_end; t++)
-        {
-            const uint2 ti = info[t];
-            const uint32_t valid = ti.x & 0xffffffu, seg = ti.x >> 24;
-            if (seg != cur_seg)
+        // the descriptors (and the mapped source tiles) of the NEXT round are fetched one round ahead: the key loads of a
+        // round then depend on nothing that is still in flight
+        uint2 nti[G];
+        uint32_t nsrc[G];
+        auto fetch = [&](uint32_t t0) {
+#pragma unroll
+            for (int g = 0; g < G; g++)
             {
-                flush(cur_seg);
-                cur_seg = seg;
+                const bool in = t0 + g < t_end;
+                nti[g] = in ? info[t0 + g] : make_uint2(0u, 0u); // valid = 0: nothing to count
+                nsrc[g] = (in && tile_map) ? tile_map[t0 + g] : t0 + g;
             }
-            const uint4* body = reinterpret_cast<const uint4*>(keys + size_t(tile_map ? tile_map[t] : t) * k_seg_tile);
-            for (uint32_t u = threadIdx.x; u < uint32_t(k_seg_tile / 4); u += k_hist_threads)
+        };
+        fetch(t_begin);
+        for (uint32_t t0 = t_begin; t0 < t_end; t0 += G)
+        {
+            uint2 ti[G];
+            uint4 k[G][J];
+#pragma unroll
+            for (int g = 0; g < G; g++)
             {
-                if (u * 4 >= valid)
-                    break;
-                const uint4 k = ld_stream_v4(body + u);
-                const uint32_t kk[4] = {(k.x >> pre_shift) & key_mask, (k.y >> pre_shift) & key_mask,
-                                        (k.z >> pre_shift) & key_mask, (k.w >> pre_shift) & key_mask};
+                ti[g] = nti[g];
+                const uint32_t valid = ti[g].x & 0xffffffu;
+                const uint4* body = reinterpret_cast<const uint4*>(keys + size_t(nsrc[g]) * k_seg_tile);
 #pragma unroll
-                for (int c = 0; c < 4; c++)
+                for (int j = 0; j < J; j++)
                 {
-                    if (u * 4 + c >= valid)
-                        break;
+                    const uint32_t u = threadIdx.x + j * k_hist_threads;
+                    k[g][j] = u * 4 < valid ? ld_stream_v4(body + u) : make_uint4(0, 0, 0, 0);
+                }
+            }
+            fetch(t0 + G);
 #pragma unroll
-                    for (int p = 0; p < k_max_passes; p++)
+            for (int g = 0; g < G; g++)
+            {
+                const uint32_t valid = ti[g].x & 0xffffffu, seg = ti[g].x >> 24;
+                if (valid == 0) // uniform (past the end)
+                    continue;
+                if (seg != cur_seg) // uniform
+                {
+                    flush(cur_seg);
+                    cur_seg = seg;
+                }
+#pragma unroll
+                for (int j = 0; j < J; j++)
+                {
+                    const uint32_t u = threadIdx.x + j * k_hist_threads;
+                    if (u * 4 >= valid)
+                        continue;
+                    const uint32_t kk[4] = {(k[g][j].x >> pre_shift) & key_mask, (k[g][j].y >> pre_shift) & key_mask,
+                                            (k[g][j].z >> pre_shift) & key_mask, (k[g][j].w >> pre_shift) & key_mask};
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
                     {
-                        if (p >= num_passes)
+                        if (u * 4 + c >= valid)
                             break;
-                        const uint32_t d = __byte_perm(kk[c], 0u, 0x4440u + p);
-                        atomicAdd(mine + p * k_radix * k_hist_copies + d * k_hist_copies, 1u);
+#pragma unroll
+                        for (int p = 0; p < k_max_passes; p++)
+                        {
+                            if (p >= num_passes)
+                                break;
+                            const uint32_t d = __byte_perm(kk[c], 0u, 0x4440u + p);
+                            atomicAdd(mine + p * k_radix * k_hist_copies + d * k_hist_copies, 1u);
+                        }
                     }
                 }
             }
