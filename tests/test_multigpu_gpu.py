@@ -355,6 +355,6 @@ def _run_world(tmp_path, nproc, exchanges):
 def test_distributed_world(tmp_path, cuda_device):
     import torch
 
-    # two ranks by default; GLU_TEST_WORLD raises it on boxes with more GPUs (tools/gpu_multi.sh)
+    # two ranks by default; GLU_TEST_WORLD raises it on boxes with more GPUs (tools/gpu_multi_session.sh)
     nproc = min(int(os.environ.get("GLU_TEST_WORLD", "2")), torch.cuda.device_count())
     _run_world(tmp_path, nproc, "p2p,nccl")

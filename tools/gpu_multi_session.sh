@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2 multi-GPU session: usage (under gpurun --gpus N): bash tools/r02m.sh N [tag] [steps] [what]
+# Round 2 multi-GPU session: usage (under gpurun --gpus N): bash tools/gpu_multi_session.sh N [tag] [steps] [what]
 #   what: comma list of  probe,pcie,pytest,phases,sweep,full,ref   (default: all but pcie)
 #   SWEEPS (environment): the sweep's variants, one per line
 set -u

@@ -10,4 +10,4 @@ done
 cat $OUT/diag.log
 ( timeout 300 python -m pytest tests/test_sort_segmented_gpu.py -m gpu -x -q 2>&1 | tail -5 ) > $OUT/pytest_seg.log
 cat $OUT/pytest_seg.log
-bash tools/r02m.sh 2 r02f 10 probe,pytest,phases,sweep
+bash tools/gpu_multi_session.sh 2 r02f 10 probe,pytest,phases,sweep

@@ -3,7 +3,7 @@
 set -u
 python - <<'PY'
 import re
-p='tools/r02m.sh'
+p='tools/gpu_multi_session.sh'
 s=open(p).read()
 start=s.index('  for v in "GLU_BENCH_MODE=serial GLU_DIST_LOCAL=full"')
 end=s.index('    echo "== $v" >> $OUT/sweep.log')
@@ -16,4 +16,4 @@ s=s[:start]+'''  for v in "GLU_BENCH_MODE=serial GLU_DIST_LOCAL=full" \\
 '''+s[end:]
 open(p,'w').write(s)
 PY
-bash tools/r02m.sh 2 r02g 10 pytest,sweep,full,ref
+bash tools/gpu_multi_session.sh 2 r02g 10 pytest,sweep,full,ref

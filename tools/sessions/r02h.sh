@@ -3,7 +3,7 @@
 # reduce / scan, configs[3] at 2^30 pairs per GPU = 2^33 pairs).
 set -u
 python - <<'PY'
-p='tools/r02m.sh'
+p='tools/gpu_multi_session.sh'
 s=open(p).read()
 start=s.index('  for v in "GLU_BENCH_MODE=serial GLU_DIST_LOCAL=full"')
 end=s.index('    echo "== $v" >> $OUT/sweep.log')
@@ -15,4 +15,4 @@ s=s[:start]+'''  for v in "GLU_BENCH_MODE=serial GLU_DIST_LOCAL=full" \\
 '''+s[end:]
 open(p,'w').write(s)
 PY
-bash tools/r02m.sh 8 r02h 10 probe,pcie,pytest,sweep,full
+bash tools/gpu_multi_session.sh 8 r02h 10 probe,pcie,pytest,sweep,full

@@ -5,4 +5,4 @@ GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=dma
 GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=dma GLU_PIPE_LANES=2
 GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=dma GLU_PIPE_PRIORITY=none
 GLU_BENCH_MODE=serial GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=dma"
-bash tools/r02m.sh 2 r02j 10 pytest,sweep
+bash tools/gpu_multi_session.sh 2 r02j 10 pytest,sweep

@@ -4,4 +4,4 @@
 export SWEEPS="GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=dma
 GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=dma GLU_PIPE_LANES=3
 GLU_BENCH_MODE=pipeline GLU_DIST_LOCAL=segmented GLU_DIST_EXCHANGE_STYLE=staged"
-bash tools/r02m.sh 8 r02k 10 pytest,sweep,full
+bash tools/gpu_multi_session.sh 8 r02k 10 pytest,sweep,full
