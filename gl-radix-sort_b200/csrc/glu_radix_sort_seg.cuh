@@ -202,20 +202,7 @@ namespace
         constexpr int G = k_seg_hist_group;
         constexpr int J = (k_seg_tile / 4 + k_hist_threads - 1) / k_hist_threads; // 128-bit units per thread and tile
         uint32_t cur_seg = info[t_begin].x >> 24;
-        // the descriptors (and the mapped source tiles) of the NEXT round are fetched one round ahead: the key loads of a
-        // round then depend on nothing that is still in flight
-        uint2 nti[G];
-        uint32_t nsrc[G];
-        auto fetch = [&](uint32_t t0) {
-#pragma unroll
-            for (int g = 0; g < G; g++)
-            {
-                const bool in = t0 + g < t_end;
-                nti[g] = in ? info[t0 + g] : make_uint2(0u, 0u); // valid = 0: nothing to count
-                nsrc[g] = (in && tile_map) ? tile_map[t0 + g] : t0 + g;
-            }
-        };
-        fetch(t_begin);
+        // (fetching the next round's descriptors a round ahead was measured slower: 0.298 against 0.274 ms at 2^28 keys)
         for (uint32_t t0 = t_begin; t0 < t_end; t0 += G)
         {
             uint2 ti[G];
@@ -223,9 +210,11 @@ namespace
 #pragma unroll
             for (int g = 0; g < G; g++)
             {
-                ti[g] = nti[g];
+                const bool in = t0 + g < t_end;
+                ti[g] = in ? info[t0 + g] : make_uint2(0u, 0u); // valid = 0: nothing to count
                 const uint32_t valid = ti[g].x & 0xffffffu;
-                const uint4* body = reinterpret_cast<const uint4*>(keys + size_t(nsrc[g]) * k_seg_tile);
+                const uint32_t src = (in && tile_map) ? tile_map[t0 + g] : t0 + g;
+                const uint4* body = reinterpret_cast<const uint4*>(keys + size_t(src) * k_seg_tile);
 #pragma unroll
                 for (int j = 0; j < J; j++)
                 {
@@ -233,7 +222,6 @@ namespace
                     k[g][j] = u * 4 < valid ? ld_stream_v4(body + u) : make_uint4(0, 0, 0, 0);
                 }
             }
-            fetch(t0 + G);
 #pragma unroll
             for (int g = 0; g < G; g++)
             {
