@@ -517,6 +517,7 @@ def measure_sort(args, glu, torch, dist, dev, world, rank, n, steps, warmup, mod
             pipe = glu.DistributedSortPipeline(n)
             closers.append(pipe.close)
             exchange = "p2p"
+            last["local"] = pipe.lanes[0].local
 
             def submit(k, v):
                 last["ticket"] = pipe.submit(k, v, n)
@@ -534,6 +535,7 @@ def measure_sort(args, glu, torch, dist, dev, world, rank, n, steps, warmup, mod
             dsort = glu.DistributedRadixSort(n, exchange=os.environ.get("GLU_BENCH_EXCHANGE", "auto"))
             closers.append(dsort.close)
             exchange = dsort.exchange
+            last["local"] = dsort.local
 
             def submit(k, v):
                 last["out"] = dsort(k, v, n)
@@ -637,11 +639,15 @@ def measure_sort(args, glu, torch, dist, dev, world, rank, n, steps, warmup, mod
     assert verified["ok"], f"bench output failed verification: {verified}"
 
     value = world * n * steps / (ms_total * 1e-3) / 1e9
-    step_bytes = SORT_BYTES_PER_PAIR if world == 1 else SORT_BYTES_PER_PAIR + 4 + PASS_BYTES_PER_PAIR
+    # HBM traffic of the SM kernels per pair and step.  One GPU: 68 B.  N > 1, segmented local sort: split-digit histogram
+    # 4 + MSD pass 16 + segment histograms 4 + 3 local passes 48 = 72 B (north_star's figure; the copy engines move
+    # another ~14 B per pair between staging and the peers' receive arrays).  N > 1, full local sort: 4 + 16 + 68 = 88 B.
+    segmented = world > 1 and last.get("local") == "segmented"
+    step_bytes = SORT_BYTES_PER_PAIR if world == 1 else (72 if segmented else SORT_BYTES_PER_PAIR + 4 + PASS_BYTES_PER_PAIR)
     per_launch_ms = sweep_ms / max(1, sweep_launches)
     # single GPU: every launch sweeps the whole array; N > 1: the local sort sweeps what the rank received (~n)
     achieved = PASS_BYTES_PER_PAIR * n / (per_launch_ms * 1e-3) / 1e9 if sweep_launches else None
-    roofline = {"bound": "hbm", "kernel": "onesweep pass (one 8-bit digit; onesweep_ring_kernel / onesweep_kernel)",
+    roofline = {"bound": "hbm", "kernel": "onesweep pass (one 8-bit digit; onesweep_kernel<320,24,3,Ballot>, the SEG flavour in the multi-GPU local sort)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                 "traffic": None, "launches": sweep_launches, "ms_per_launch": per_launch_ms,
                 "algorithmic_bytes_per_launch": PASS_BYTES_PER_PAIR * n,

@@ -222,6 +222,118 @@ TEST_CASE("RadixSort-wide-u64-keys-and-wide-values", "")
     }
 }
 
+// Beyond the reference: the segmented sort (the local step of the multi-GPU sort) through RadixSort::sort_segmented —
+// segments at tile boundaries, and the same segments given as runs placed anywhere (one run per "source rank").
+TEST_CASE("RadixSort-segmented-and-runs", "")
+{
+    const size_t tile = RadixSort::segment_tile();
+    Random rng(5);
+    const std::vector<std::vector<size_t>> run_counts = {{tile + 3, 17}, {0, 2 * tile}, {5, 0}, {tile - 1, tile + 1}};
+    const unsigned begin_bit = 0, end_bit = 24;
+    const uint32_t mask = (1u << end_bit) - 1u;
+    std::vector<size_t> seg_count, flat, seg_of, seg_first_run;
+    for (size_t s = 0; s < run_counts.size(); s++)
+    {
+        seg_first_run.push_back(flat.size());
+        size_t c = 0;
+        for (size_t r : run_counts[s])
+        {
+            flat.push_back(r);
+            seg_of.push_back(s);
+            c += r;
+        }
+        seg_count.push_back(c);
+    }
+    auto tiles_of = [&](size_t c) { return (c + tile - 1) / tile; };
+    // expected result: every segment stable-sorted on the key bits that take part, segments compact one after the other
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> seg_pairs(run_counts.size());
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> run_pairs(flat.size());
+    uint32_t next_val = 0;
+    for (size_t r = 0; r < flat.size(); r++)
+        for (size_t i = 0; i < flat[r]; i++)
+        {
+            const std::pair<uint32_t, uint32_t> p{rng.sample_int<uint32_t>(0, 0xffffffffu) & 0x00ff00ffu, next_val++};
+            run_pairs[r].push_back(p);
+            seg_pairs[seg_of[r]].push_back(p);
+        }
+    std::vector<std::pair<uint32_t, uint32_t>> expected;
+    for (auto& sp : seg_pairs)
+    {
+        std::stable_sort(sp.begin(), sp.end(), [mask](const auto& a, const auto& b) { return (a.first & mask) < (b.first & mask); });
+        expected.insert(expected.end(), sp.begin(), sp.end());
+    }
+    std::vector<uint32_t> counts32(seg_count.begin(), seg_count.end());
+    size_t run_tiles = 0, seg_tiles = 0;
+    for (size_t c : flat)
+        run_tiles += tiles_of(c);
+    for (size_t c : seg_count)
+        seg_tiles += tiles_of(c);
+    const size_t max_tiles = std::max(run_tiles, seg_tiles) + 2;
+    auto check = [&](DeviceBuffer& ka, DeviceBuffer& va, DeviceBuffer& kb, DeviceBuffer& vb, bool in_b) {
+        CHECK(in_b == (((end_bit - begin_bit + 7) / 8) % 2 == 1));
+        const std::vector<uint32_t> k = (in_b ? kb : ka).get_data<uint32_t>();
+        const std::vector<uint32_t> v = (in_b ? vb : va).get_data<uint32_t>();
+        bool equal = true;
+        for (size_t i = 0; i < expected.size() && equal; i++)
+            equal = k[i] == expected[i].first && v[i] == expected[i].second;
+        CHECK(equal);
+    };
+    { // segments at tile boundaries
+        std::vector<uint32_t> ak(max_tiles * tile, 0x0badf00du), av(max_tiles * tile, 0xdeaddeadu);
+        size_t first = 0;
+        for (size_t s = 0, r = 0; s < run_counts.size(); s++)
+        {
+            size_t at = first * tile;
+            for (size_t j = 0; j < run_counts[s].size(); j++, r++)
+                for (const auto& p : run_pairs[r])
+                {
+                    ak[at] = p.first;
+                    av[at++] = p.second;
+                }
+            first += tiles_of(seg_count[s]);
+        }
+        DeviceBuffer ka(ak), va(av), kb(ak), vb(av), cnt(counts32);
+        RadixSort radix_sort;
+        const bool in_b = radix_sort.sort_segmented(ka.handle(), va.handle(), kb.handle(), vb.handle(), cnt.handle(),
+                                                    seg_count.size(), max_tiles, begin_bit, end_bit);
+        check(ka, va, kb, vb, in_b);
+    }
+    { // the same segments as runs, laid out in REVERSE run order
+        std::vector<uint32_t> ak(max_tiles * tile, 0x0badf00du), av(max_tiles * tile, 0xdeaddeadu);
+        const size_t R = flat.size();
+        std::vector<uint32_t> runs(5 * (R + 1), 0u);
+        std::vector<size_t> first(R + 1, 0), phys(R, 0);
+        for (size_t r = 0; r < R; r++)
+            first[r + 1] = first[r] + tiles_of(flat[r]);
+        size_t at = 1;
+        for (size_t r = R; r-- > 0;)
+        {
+            phys[r] = at;
+            at += tiles_of(flat[r]);
+        }
+        for (size_t r = 0; r < R; r++)
+        {
+            size_t e = phys[r] * tile;
+            for (const auto& p : run_pairs[r])
+            {
+                ak[e] = p.first;
+                av[e++] = p.second;
+            }
+            runs[0 * (R + 1) + r] = uint32_t(first[r]);
+            runs[1 * (R + 1) + r] = uint32_t(phys[r]);
+            runs[2 * (R + 1) + r] = uint32_t(flat[r]);
+            runs[3 * (R + 1) + r] = uint32_t(seg_of[r]);
+            runs[4 * (R + 1) + r] = uint32_t(first[seg_first_run[seg_of[r]]]);
+        }
+        runs[R] = uint32_t(first[R]);
+        DeviceBuffer ka(ak), va(av), kb(ak), vb(av), cnt(counts32), run_buffer(runs);
+        RadixSort radix_sort;
+        const bool in_b = radix_sort.sort_segmented(ka.handle(), va.handle(), kb.handle(), vb.handle(), cnt.handle(),
+                                                    seg_count.size(), max_tiles, begin_bit, end_bit, run_buffer.handle(), R);
+        check(ka, va, kb, vb, in_b);
+    }
+}
+
 TEST_CASE("RadixSort-benchmark", "[.][benchmark]")
 {
     for (size_t k_num_elements : {1024, 16384, 65536, 131072, 524288, 1048576, 2097152, 4194304, 8388608, 16777216,

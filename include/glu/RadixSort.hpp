@@ -112,6 +112,28 @@ namespace glu
                 begin_bit, end_bit, m_tmp.handle(), m_tmp.size(), m_stream, &in_b));
             return in_b != 0;
         }
+
+        /// The same with the input given as RUNS (glu_radix_sort_u32kv_segmented_runs): `runs_buffer` holds 5 rows of
+        /// (num_runs + 1) uint32 — first tile of every run in the first pass's own numbering (+ the total), the tile of
+        /// the A arrays it starts at, its count, its segment, the first tile of its segment.  What the multi-GPU sort
+        /// calls after its copy-engine all-to-all (a bucket is spread over one chunk per source rank).
+        bool sort_segmented(DevicePtr keys_a, DevicePtr vals_a, DevicePtr keys_b, DevicePtr vals_b,
+                            DevicePtr seg_count_buffer, size_t num_segments, size_t max_tiles, unsigned begin_bit,
+                            unsigned end_bit, DevicePtr runs_buffer, size_t num_runs)
+        {
+            GLU_CHECK_ARGUMENT(keys_a && vals_a && keys_b && vals_b && seg_count_buffer && runs_buffer, "Invalid buffer");
+            const size_t need = glu_radix_sort_u32kv_segmented_tmp_bytes(max_tiles);
+            GLU_CHECK_ARGUMENT(need != 0, "RadixSort: %zu tiles are too many", max_tiles);
+            if (m_tmp.size() < need)
+                m_tmp.resize(need, false);
+            int in_b = 0;
+            GLU_CHECK_STATUS(glu_radix_sort_u32kv_segmented_runs(
+                static_cast<uint32_t*>(keys_a), static_cast<uint32_t*>(vals_a), static_cast<uint32_t*>(keys_b),
+                static_cast<uint32_t*>(vals_b), static_cast<const uint32_t*>(seg_count_buffer), num_segments, max_tiles,
+                begin_bit, end_bit, static_cast<const uint32_t*>(runs_buffer), num_runs, m_tmp.handle(), m_tmp.size(),
+                m_stream, &in_b));
+            return in_b != 0;
+        }
     };
 } // namespace glu
 
