@@ -143,6 +143,9 @@ if "reduce" in args.what:
     a = torch.empty(n, dtype=torch.int32, device=dev)
     med, best = timeit(lambda: a.copy_(data0))
     print(f"torch copy (read+write) n=2^{args.log2n}: median {med:.3f} ms  {8 * n / med / 1e6:.0f} GB/s")
+    # what an IN-PLACE read-modify-write stream (the scan's access pattern: every line is read, then written) reaches
+    med, best = timeit(lambda: a.add_(1))
+    print(f"torch in-place add_ (read+write, same array) n=2^{args.log2n}: median {med:.3f} ms  {8 * n / med / 1e6:.0f} GB/s")
 
 if "reducef" in args.what.split(","):
     # BASELINE.json configs[4]: Reduce(Float, Min/Max/Sum) over uniform floats in [-1, 1)
