@@ -241,6 +241,25 @@ namespace
                         continue;
                     const uint32_t kk[4] = {(k[g][j].x >> pre_shift) & key_mask, (k[g][j].y >> pre_shift) & key_mask,
                                             (k[g][j].z >> pre_shift) & key_mask, (k[g][j].w >> pre_shift) & key_mask};
+                    if (u * 4 + 4 <= valid)
+                    {
+                        // all four keys count (every unit of a full tile — all but a segment's last tile): three
+                        // instructions per count as in histogram_kernel; the kernel is issue-bound (ncu: 85 % issue
+                        // slots, 47 % DRAM with per-key bounds checks)
+#pragma unroll
+                        for (int p = 0; p < k_max_passes; p++)
+                        {
+                            if (p >= num_passes) // uniform
+                                break;
+#pragma unroll
+                            for (int c = 0; c < 4; c++)
+                            {
+                                const uint32_t d = __byte_perm(kk[c], 0u, 0x4440u + p);
+                                atomicAdd(mine + p * k_radix * k_hist_copies + d * k_hist_copies, 1u);
+                            }
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int c = 0; c < 4; c++)
                     {
