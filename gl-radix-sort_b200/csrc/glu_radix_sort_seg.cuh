@@ -1,13 +1,13 @@
 // glu_radix_sort_seg.cuh — SEGMENTED stable LSD sort: many independent sorts in one set of launches (included by
 // glu_radix_sort.cu).  It is what "each GPU runs the local onesweep on the remaining 24 bits" (BASELINE.json north_star)
 // needs after the MSD split of the multi-GPU sort: a rank receives up to 256 top-digit buckets, every bucket must be
-// sorted by its low key bits, and buckets must not mix.  One histogram launch + ceil(bits / 8) ring passes for ALL
+// sorted by its low key bits, and buckets must not mix.  One histogram launch + ceil(bits / 8) digit passes for ALL
 // segments: 4 + 16 * passes bytes of HBM traffic per pair (52 B for 24 bits) instead of the 68 B of a full 32-bit sort
 // of the received range.
 //
 // Layout.  Segment s holds count[s] pairs (device-resident counts: the exchange plan writes them).  In the INPUT
 // arrays segment s starts at a multiple of the tile size (glu_radix_sort_segment_tile(), 7680 pairs): element offset
-// first_tile[s] * TILE with first_tile = exclusive scan of ceil(count / TILE) — so tile t of the ring kernel is always
+// first_tile[s] * TILE with first_tile = exclusive scan of ceil(count / TILE) — so tile t of a digit pass is always
 // elements [t * TILE, (t + 1) * TILE) (every tile is a bulk copy, tiles never straddle segments) and only the last tile
 // of a segment is partial (its slots past `valid` are padding: never counted, never written).  Intermediate passes
 // keep that layout; the LAST pass writes the compact layout (segment s at sum of the counts before it), so the result
@@ -17,8 +17,15 @@
 // Kernels: seg_setup_kernel / seg_tile_info_kernel (counts -> first tiles, compact bases, per-tile {valid, segment,
 // first tile}), seg_histogram_kernel (all digit places of all segments in one read of the keys, lane-private shared
 // bins as in histogram_kernel), seg_offsets_kernel (counts -> per-(pass, segment) digit offsets incl. the output base),
-// onesweep_ring_kernel<..., SEG = true> (glu_onesweep_ring.cuh: the chain CTAs keep ONE running prefix over all
-// tiles; a tile subtracts the prefix row in front of its segment's first tile).
+// onesweep_kernel<..., SEG = true> (default; GLU_SEG_KERNEL=1: onesweep_ring_kernel<..., SEG = true>, glu_onesweep_ring.cuh):
+// the chain CTAs keep ONE running prefix over all tiles; a tile subtracts the prefix row in front of its segment's
+// first tile.
+//
+// Runs variant (glu_radix_sort_u32kv_segmented_runs, what the multi-GPU sort calls after its copy-engine all-to-all):
+// the input of the FIRST pass is a sequence of tile-aligned runs placed anywhere in the A arrays — a segment is one or
+// more consecutive runs (bucket b = its runs from source rank 0, 1, ...).  run_tile_info_kernel expands the caller's run
+// table into the first pass's own tile descriptors and a tile map (tile t is read from tile map[t] of the input); the
+// histogram and the first pass read through the map, everything after is the layout above.
 
 namespace glu_b200
 {

@@ -1,9 +1,10 @@
 #!/usr/bin/env python
-"""Round-2 starting point: parity check + timing of the EXPERIMENTAL DistributedSortPipeline (exchange of job k+1 under
-the local sort of job k) against back-to-back DistributedRadixSort calls.  Never run on GPUs yet.
+"""Parity check + timing of DistributedSortPipeline (exchange of job k+1 under the local sort of job k) against
+back-to-back DistributedRadixSort calls (development aid; the same checks run in tests/test_multigpu_gpu.py and the
+numbers come from bench.py).
 
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port 29733 tools/pipeline_check.py          # wrap in `timeout`: unverified stream ordering
+        --master-port 29733 tools/pipeline_check.py
 """
 import os
 import sys
