@@ -183,11 +183,17 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def workload_config(args, parallelism: str, cache: str) -> dict:
-    """`config` of the JSON line — the same keys and the same workload string on both arms."""
+def workload_config(args) -> dict:
+    """`config` of the JSON line — it names the WORKLOAD and is identical on both arms (how each arm runs it is in the
+    line's `implementation` object)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     return {"workload": f"RadixSort of 2^{args.log2_pairs} uniform-random uint32 key/value pairs per GPU "
                         f"(BASELINE.json configs[2]), values = input index, one fresh unsorted input per step",
-            "pairs_per_gpu": 1 << args.log2_pairs, "parallelism": parallelism, "cache": cache}
+            "pairs_per_gpu": 1 << args.log2_pairs,
+            "parallelism": f"{world} shard(s) of 2^{args.log2_pairs} pairs, one per GPU (weak scaling); the result is "
+                           f"the stable sort of the concatenated shards, rank r's slice before rank r+1's",
+            "cache": f"every step sorts a fresh unsorted input of {8 << args.log2_pairs >> 20} MiB per shard - larger "
+                     f"than the 126 MB L2 (and any host cache): no flush needed"}
 
 
 def gl_probe() -> str:
@@ -237,16 +243,18 @@ def run_reference(args):
             break
     total = sum(times)
     value = n * len(times) / total / 1e9
-    cfg = workload_config(args, f"host CPU, {threads} threads (__gnu_parallel::stable_sort)",
-                          "each step sorts a fresh copy of the sample (2 GiB, larger than any host cache)")
-    cfg["reference_arm"] = (f"std::stable_sort of the (key, value) pairs on the host (the reference test-suite's oracle; "
-                            f"its GLSL path needs OpenGL 4.6), each step a 2^{args.cpu_sample_log2}-pair uniform-random "
-                            f"(mt19937) sample of that workload")
+    cfg = workload_config(args)
+    implementation = {
+        "parallelism": f"host CPU, {threads} threads (__gnu_parallel::stable_sort)",
+        "cache": "each step sorts a fresh copy of the sample (2 GiB, larger than any host cache)",
+        "reference_arm": (f"std::stable_sort of the (key, value) pairs on the host (the reference test-suite's oracle; "
+                          f"its GLSL path needs OpenGL 4.6), each step a 2^{args.cpu_sample_log2}-pair uniform-random "
+                          f"(mt19937) sample of that workload")}
     line = {
         "impl": "reference", "metric": "radix_sort_u32_key_value_throughput", "value": value, "unit": "Gpairs/s",
         "n_gpus": args.gpus, "steps": len(times), "warmup": done_warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": cfg,
+        "config": cfg, "implementation": implementation,
         "cpu_baseline": {"value": value, "unit": "Gpairs/s", "cores": threads, "kind": "port",
                          "sample": f"2^{args.cpu_sample_log2} pairs per step, __gnu_parallel::stable_sort, "
                                    f"{threads} threads"},
@@ -708,7 +716,7 @@ def run_b200(args):
         "metric": "radix_sort_u32_key_value_throughput", "value": fields["value"], "unit": "Gpairs/s", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": fields["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": workload_config(args, parallelism, cache),
+        "config": workload_config(args), "implementation": {"parallelism": parallelism, "cache": cache},
         "roofline": roofline, "clocks": fields["clocks"], "gpu_launches": fields["gpu_launches"],
         "verified": fields["verified"],
         "published_reference": {"value": 0.05345, "unit": "Gpairs/s", "hardware": "RTX 2060 SUPER (README.md:133)",
