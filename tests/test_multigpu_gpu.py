@@ -202,6 +202,34 @@ def test_scan_init_partitions_and_wide_types(glu, cuda_device, oracle):
     np.testing.assert_array_equal(dd.cpu().numpy(), want)
 
 
+def test_peer_signal_and_flag_wait(glu, cuda_device):
+    """glu_signal_peers_u32 / glu_stream_wait_flags_u32 on one device: the signal is ordered after the stream's earlier
+    work, the wait lets the stream continue once every word (but `skip`) has reached the epoch, wrap-around included."""
+    import ctypes
+
+    import torch
+
+    flags = torch.zeros(32, dtype=torch.int32, device=cuda_device)
+    out = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    st = _stream(cuda_device)
+    base = flags.data_ptr()
+    for epoch in (1, 2, 0x7FFFFFFF, 0x80000001, 0xFFFFFFFF, 3):   # 3 after 0xFFFFFFFF: the counter wrapped
+        addrs = (ctypes.c_uint64 * 5)(base, base + 4, 0, base + 12, base + 16)   # word 2 is never signalled
+        glu.check(glu.lib.glu_signal_peers_u32(addrs, 5, epoch, st), "signal")
+        glu.check(glu.lib.glu_stream_wait_flags_u32(base, 5, 2, epoch, st), "wait")
+        out.add_(1)
+    torch.cuda.synchronize()
+    assert int(out.item()) == 6
+    got = flags[:5].cpu().numpy().view(np.uint32).tolist()
+    assert got == [3, 3, 0, 3, 3]
+    # argument checks
+    addrs = (ctypes.c_uint64 * 1)(base + 2)
+    assert glu.lib.glu_signal_peers_u32(addrs, 1, 1, st) != 0          # misaligned word
+    assert glu.lib.glu_signal_peers_u32(addrs, 17, 1, st) != 0         # more than 16 peers
+    assert glu.lib.glu_stream_wait_flags_u32(base, 33, 0, 1, st) != 0  # more than 32 words
+    assert glu.lib.glu_stream_wait_flags_u32(0, 4, 0, 1, st) != 0
+
+
 WORKER = r'''
 import os, sys
 import numpy as np
