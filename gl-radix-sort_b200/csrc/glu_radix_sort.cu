@@ -810,6 +810,7 @@ namespace glu_b200
                 }
 
                 // ---- this digit's count in all earlier tiles: one row, written by the chain CTA
+                auto look_back = [&]() {
                 if (tid < k_radix)
                 {
                     uint32_t exclusive = 0;
@@ -844,6 +845,14 @@ namespace glu_b200
                         s.gbase[tid] = digit_offset[(SEG ? (info.x >> 24) * uint32_t(k_radix) : 0u) + tid] + exclusive -
                                        s.tile_start[tid];
                 }
+                };
+                // The plain key/value pass asks for the prefix row AFTER the values have been scattered: the row trails the
+                // publication of the predecessor's counts by a chain batch, so the later a tile asks, the less it waits
+                // (4.48 against 4.53 ms per 2^28-pair sort; the SEG pass, which reads two rows, was 2 % slower that way
+                // and keeps the early order, like the PEER pass).
+                constexpr bool LATE = !KEYS_ONLY && !SEG && !PEER;
+                if constexpr (!LATE)
+                    look_back();
                 if constexpr (!KEYS_ONLY)
                 {
                     __syncthreads(); // all values are in registers
@@ -854,6 +863,8 @@ namespace glu_b200
                         s.vals[rank2[i / 2] >> 16] = val[i + 1];
                     }
                 }
+                if constexpr (LATE)
+                    look_back();
             }
             __syncthreads(); // tile-sorted keys and values, gbase
 
