@@ -249,6 +249,49 @@ if rank == 0:
     ek, ev = oracle.stable_sort_pairs(allk, allv)
     assert np.array_equal(gk, ek) and np.array_equal(gv, ev), "distributed plan does not reproduce the stable sort"
     print("OK", world, shift, [int(x) for x in plan.recv_totals])
+
+# ---- the same job through the "dma" exchange layout (plan_dma_exchange): tile-aligned bucket-major staging arrays, ONE
+# chunk of whole tiles per (source, destination) — moved here by all_to_all_single, on the GPU by one copy-engine transfer
+# per peer — and the receiver reading its buckets as runs through the run table the GPU path uploads
+TILE = 64
+dplan = dmod.plan_dma_exchange(torch.stack(hists).numpy(), TILE)
+PAD = np.uint32(0xDEADBEEF)
+stage_k = np.full(int(dplan.stage_tile[rank, 256]) * TILE, PAD, dtype=np.uint32)
+stage_v = np.full(int(dplan.stage_tile[rank, 256]) * TILE, PAD, dtype=np.uint32)
+for b in range(256):
+    sel = np.nonzero(digit == b)[0]
+    at = int(dplan.stage_tile[rank, b]) * TILE
+    stage_k[at:at + sel.size] = keys[sel]
+    stage_v[at:at + sel.size] = vals[sel]
+send_splits = [int(dplan.chunk_tiles[rank, g]) * TILE for g in range(world)]
+recv_splits = [int(dplan.chunk_tiles[s, rank]) * TILE for s in range(world)]
+assert sum(send_splits) == stage_k.size and sum(recv_splits) == int(dplan.recv_tiles[rank]) * TILE
+rk2 = torch.zeros(sum(recv_splits), dtype=torch.int32)
+rv2 = torch.zeros(sum(recv_splits), dtype=torch.int32)
+dist.all_to_all_single(rk2, torch.from_numpy(stage_k.view(np.int32).copy()), recv_splits, send_splits)
+dist.all_to_all_single(rv2, torch.from_numpy(stage_v.view(np.int32).copy()), recv_splits, send_splits)
+rk2, rv2 = rk2.numpy().view(np.uint32), rv2.numpy().view(np.uint32)
+assert [int(x) * TILE for x in dplan.recv_base_tile[rank]] == list(np.cumsum([0] + recv_splits[:-1]))
+runs, seg_count, nb = dplan.run_table(rank)
+out_k, out_v = [], []
+for sg in range(nb):
+    ks, vs = [], []
+    for r in range(sg * world, (sg + 1) * world):
+        c, at = int(runs[2, r]), int(runs[1, r]) * TILE
+        ks.append(rk2[at:at + c]); vs.append(rv2[at:at + c])
+    k, v = np.concatenate(ks), np.concatenate(vs)
+    assert k.size == int(seg_count[sg])
+    low = k & np.uint32((1 << shift) - 1) if shift > 0 else np.zeros_like(k)
+    o = np.argsort(low, kind="stable")   # the segmented local sort: key bits below the split digit only
+    out_k.append(k[o]); out_v.append(v[o])
+ok2 = np.concatenate(out_k) if out_k else np.zeros(0, np.uint32)
+ov2 = np.concatenate(out_v) if out_v else np.zeros(0, np.uint32)
+gathered = [None] * world
+dist.gather_object((ok2, ov2), gathered if rank == 0 else None, dst=0)
+if rank == 0:
+    gk = np.concatenate([g[0] for g in gathered]); gv = np.concatenate([g[1] for g in gathered])
+    assert np.array_equal(gk, ek) and np.array_equal(gv, ev), "dma exchange layout does not reproduce the stable sort"
+    print("OK-DMA", world, [int(x) for x in dplan.recv_tiles])
 dist.destroy_process_group()
 '''
 
@@ -263,4 +306,4 @@ def test_gloo_world2_exchange(tmp_path, kind, oracle):
                         "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    assert "OK 2" in r.stdout
+    assert "OK 2" in r.stdout and "OK-DMA 2" in r.stdout
