@@ -943,6 +943,100 @@ namespace glu_b200
 
 #include "glu_onesweep_ring.cuh"
 
+        // ------------------------------------------------------------------------------------ small inputs
+        //
+        // Up to k_small_tile pairs: ONE CTA, ONE launch — the pairs stay in shared memory for all digit passes (count,
+        // 256-digit scan, ballot ranking against per-warp running offsets, scatter, exactly the tile-local part of
+        // onesweep_kernel).  The general path costs a memset + a histogram + a launch per digit with a chain hand-off
+        // in each: 40-49 us whatever the size (profiles/r02_glu_test_benchmark.md); this one is a single short kernel.
+        constexpr int k_small_threads = 256, k_small_ipt = 8, k_small_tile = k_small_threads * k_small_ipt;
+
+        __global__ void __launch_bounds__(k_small_threads, 1)
+            small_sort_kernel(uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t n, PassPlan plan)
+        {
+            constexpr int WARPS = k_small_threads / 32;
+            __shared__ uint32_t s_keys[k_small_tile], s_vals[k_small_tile];
+            __shared__ uint32_t s_hist[WARPS][k_radix];
+            __shared__ uint32_t s_scan[k_radix / 32];
+            const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+            // slots past the end hold the largest key and sit behind every real pair: they rank after all real pairs
+            // in every pass (equal digits keep their order) and are never written back
+            for (uint32_t i = tid; i < uint32_t(k_small_tile); i += k_small_threads)
+            {
+                s_keys[i] = i < n ? keys[i] : 0xffffffffu;
+                s_vals[i] = i < n ? vals[i] : 0u;
+            }
+            const uint32_t my_off = warp * (k_small_ipt * 32) + lane; // + i * 32 (warp-striped: input order)
+            const uint32_t lt = lanemask_lt();
+            uint32_t* wh = s_hist[warp];
+            for (int p = 0; p < plan.num_passes; p++)
+            {
+                for (int i = tid; i < WARPS * k_radix; i += k_small_threads)
+                    (&s_hist[0][0])[i] = 0u;
+                __syncthreads(); // staged pairs (first pass), cleared counters
+                uint32_t key[k_small_ipt], val[k_small_ipt], dig[k_small_ipt];
+#pragma unroll
+                for (int i = 0; i < k_small_ipt; i++)
+                {
+                    key[i] = s_keys[my_off + i * 32];
+                    val[i] = s_vals[my_off + i * 32];
+                    dig[i] = (key[i] >> plan.shift[p]) & plan.mask[p];
+                    atomicAdd(&wh[dig[i]], 1u);
+                }
+                __syncthreads(); // every pair is in registers; the counts are final
+                uint32_t total = 0, inc = 0;
+                if (tid < k_radix)
+                {
+#pragma unroll
+                    for (int w = 0; w < WARPS; w++)
+                        total += s_hist[w][tid];
+                    inc = total;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1)
+                    {
+                        const uint32_t t = __shfl_up_sync(k_full_mask, inc, o);
+                        if (lane >= unsigned(o))
+                            inc += t;
+                    }
+                    if (lane == 31)
+                        s_scan[warp] = inc;
+                }
+                __syncthreads();
+                if (tid < k_radix)
+                {
+                    uint32_t running = inc - total;
+                    for (unsigned w = 0; w < warp; w++)
+                        running += s_scan[w];
+#pragma unroll
+                    for (int w = 0; w < WARPS; w++)
+                    {
+                        const uint32_t c = s_hist[w][tid];
+                        s_hist[w][tid] = running; // first slot of (warp w, digit tid)
+                        running += c;
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int i = 0; i < k_small_ipt; i++)
+                {
+                    const uint32_t peers = match_digit<Rank_Ballot>(dig[i]);
+                    const uint32_t before = wh[dig[i]];
+                    __syncwarp();
+                    wh[dig[i]] = before + __popc(peers); // every peer stores the same value
+                    __syncwarp();
+                    const uint32_t r = before + __popc(peers & lt);
+                    s_keys[r] = key[i];
+                    s_vals[r] = val[i];
+                }
+                __syncthreads(); // the scatter is complete and nobody needs its running offsets any more
+            }
+            for (uint32_t i = tid; i < n; i += k_small_threads)
+            {
+                keys[i] = s_keys[i];
+                vals[i] = s_vals[i];
+            }
+        }
+
         // ------------------------------------------------------------------------------------ host side
 
         struct SweepConfig
@@ -1315,6 +1409,15 @@ int sort_impl(uint32_t* d_keys, uint32_t* d_vals, size_t count, const uint32_t* 
         return GLU_ERROR_CUDA;
 
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // small inputs: one CTA, one launch, no scratch (GLU_SORT_SMALL_MAX=0 sends them down the general path)
+    static const int small_max = env_int("GLU_SORT_SMALL_MAX", k_small_tile);
+    if (flavor == 0 && !d_n && count <= size_t(small_max < k_small_tile ? small_max : k_small_tile))
+    {
+        ScopedKernelProfile prof(GLU_KERNEL_SORT_ONESWEEP, s);
+        small_sort_kernel<<<1, k_small_threads, 0, s>>>(d_keys, d_vals, uint32_t(count), plan);
+        GLU_LAUNCH_CHECK();
+        return GLU_SUCCESS;
+    }
     char* tmp = static_cast<char*>(d_tmp);
     uint32_t* tickets = reinterpret_cast<uint32_t*>(tmp); // [0..3] sweep passes, [4] histogram
     uint32_t* hist = reinterpret_cast<uint32_t*>(tmp + l.off_hist);

@@ -166,10 +166,15 @@ def test_sort_without_tma_path_matches(glu, cuda_device, oracle):
         assert r.returncode == 0 and "ok" in r.stdout, (env_extra, r.stdout, r.stderr)
 
 
-@pytest.mark.parametrize("env_extra", [{"GLU_SORT_CONFIG": "9"}, {"GLU_SORT_CONFIG": "10"}, {"GLU_SORT_CONFIG": "15"},
-                                       {"GLU_SORT_CONFIG": "12", "GLU_SORT_TMA": "0"}, {"GLU_SORT_CONFIG": "8"},
-                                       {"GLU_SORT_CONFIG": "13", "GLU_SORT_CHAIN_ROWS": "104"},
-                                       {"GLU_SORT_CONFIG": "10", "GLU_SORT_RING_CTAS_PER_SM": "1"}],
+# GLU_SORT_SMALL_MAX=0: the tiny sizes go through the forced kernel form too (not through small_sort_kernel)
+@pytest.mark.parametrize("env_extra", [{"GLU_SORT_CONFIG": "9", "GLU_SORT_SMALL_MAX": "0"},
+                                       {"GLU_SORT_CONFIG": "10", "GLU_SORT_SMALL_MAX": "0"},
+                                       {"GLU_SORT_CONFIG": "15", "GLU_SORT_SMALL_MAX": "0"},
+                                       {"GLU_SORT_CONFIG": "12", "GLU_SORT_TMA": "0", "GLU_SORT_SMALL_MAX": "0"},
+                                       {"GLU_SORT_CONFIG": "8", "GLU_SORT_SMALL_MAX": "0"},
+                                       {"GLU_SORT_CONFIG": "13", "GLU_SORT_CHAIN_ROWS": "104", "GLU_SORT_SMALL_MAX": "0"},
+                                       {"GLU_SORT_CONFIG": "10", "GLU_SORT_RING_CTAS_PER_SM": "1", "GLU_SORT_SMALL_MAX": "0"},
+                                       {"GLU_SORT_SMALL_MAX": "0"}, {}],
                          ids=lambda e: "-".join(f"{k[9:]}{v}" for k, v in e.items()))
 def test_sort_both_kernel_forms(cuda_device, env_extra):
     """Every size class through BOTH forms of the digit pass, whatever the default selection is: the persistent ring
@@ -220,6 +225,43 @@ print('ok')
     env = dict(os.environ, **env_extra)
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, (env_extra, r.stdout[-2000:], r.stderr[-4000:])
+
+
+@pytest.mark.parametrize("n", [2, 3, 31, 32, 33, 255, 256, 257, 1000, 2047, 2048, 2049])
+def test_sort_small_inputs_single_cta_path(glu, cuda_device, oracle, n):
+    """Up to 2048 pairs are sorted by small_sort_kernel (one CTA, one launch); 2049 is the first size of the general
+    path.  Full keys, num_steps, heavy duplicates, all-equal keys, unaligned buffers, and key-bit ranges through
+    sort_ex — all against std::stable_sort of the pairs."""
+    import torch
+
+    vals = (np.arange(n, dtype=np.uint32) * np.uint32(2654435761)) ^ np.uint32(n)
+    cases = [("uniform", oracle.mt19937_u32(n, n)), ("dups", oracle.random_u32(n, n, 0, 5)),
+             ("equal", np.full(n, 0xFFFFFFFF, dtype=np.uint32)), ("ent16", oracle.mt19937_u32(n + 1, n) << np.uint32(16))]
+    for name, keys in cases:
+        for num_steps in (0, 1, 3, 5):
+            dk, dv = to_device(keys, cuda_device), to_device(vals, cuda_device)
+            glu.RadixSort()(dk, dv, n, num_steps)
+            ek, ev = oracle.stable_sort_pairs(keys, vals, num_steps)
+            np.testing.assert_array_equal(to_host(dk, np.uint32), ek, err_msg=f"{name} steps={num_steps} keys")
+            np.testing.assert_array_equal(to_host(dv, np.uint32), ev, err_msg=f"{name} steps={num_steps} values")
+    keys = oracle.mt19937_u32(7 * n, n + 3)
+    vals3 = np.arange(n + 3, dtype=np.uint32)
+    for off in (1, 3):   # 4-byte aligned only
+        dk, dv = to_device(keys, cuda_device), to_device(vals3, cuda_device)
+        glu.RadixSort()(dk[off:], dv[off:], n)
+        ek, ev = oracle.stable_sort_pairs(keys[off:off + n], vals3[off:off + n])
+        np.testing.assert_array_equal(to_host(dk, np.uint32)[off:off + n], ek)
+        np.testing.assert_array_equal(to_host(dv, np.uint32)[off:off + n], ev)
+        np.testing.assert_array_equal(to_host(dk, np.uint32)[:off], keys[:off])          # nothing outside [off, off + n)
+        np.testing.assert_array_equal(to_host(dk, np.uint32)[off + n:], keys[off + n:])
+    for begin_bit, end_bit in ((0, 32), (4, 20), (24, 32), (5, 6)):
+        k = oracle.mt19937_u32(11 * n, n)
+        dk, dv = to_device(k, cuda_device), to_device(vals, cuda_device)
+        glu.RadixSort().sort_ex(dk, dv, n, begin_bit, end_bit)
+        ek, ev = oracle.stable_sort_ex(k, vals, begin_bit, end_bit)
+        np.testing.assert_array_equal(to_host(dk, np.uint32), ek, err_msg=f"bits [{begin_bit}, {end_bit}) keys")
+        np.testing.assert_array_equal(to_host(dv, np.uint32), ev, err_msg=f"bits [{begin_bit}, {end_bit}) values")
+    torch.cuda.synchronize()
 
 
 def test_sort_full_size_2_28(glu, cuda_device, oracle):
