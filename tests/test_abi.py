@@ -156,3 +156,22 @@ def test_no_product_import_of_oracle(glu):
                     assert not bad.search(text), os.path.join(dirpath, f)
     syms = subprocess.run(["nm", "-D", glu.LIB_PATH], capture_output=True, text=True).stdout
     assert "glu_oracle" not in syms
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/glu_b200.h must compile as C99 (what a cgo / JNI / ctypes-cffi binding feeds it to),
+    with no C++ and no CUDA or torch types in the signatures."""
+    import shutil
+    import subprocess
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "c.c"
+    src.write_text('#include "glu_b200.h"\nint main(void) { return GLU_SUCCESS; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(os.path.join(ROOT, "include", "glu_b200.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", text, flags=re.S)   # declarations only, comments may name what a handle is
+    for banned in ("torch", "at::", "cudaStream_t", "cudaEvent_t", "std::"):
+        assert banned not in code, banned
